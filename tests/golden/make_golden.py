@@ -1,0 +1,196 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz from the (patched) reference.  BUILD-CONTAINER ONLY.
+
+Run:  python tests/golden/make_golden.py            (about 3-4 minutes, one core)
+
+Every array is produced by woolgathering/pyPeriod at /root/reference loaded through
+tests/golden/patched_reference.py (SURVEY.md §8c patch set), on inputs regenerated
+from seeds by pyperiod_b200/synth.py.  The fixtures are what pins the oracle
+(tests/test_oracle_golden.py) and, through it or directly, the CUDA path.
+"""
+from __future__ import annotations
+
+import contextlib
+import hashlib
+import io
+import os
+import sys
+import warnings
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import patched_reference  # noqa: E402
+from pyperiod_b200 import synth  # noqa: E402
+
+ref = patched_reference.load()
+Periods, QOPeriods, RamanujanPeriods = ref.Periods, ref.QOPeriods, ref.RamanujanPeriods
+
+
+def sha(a: np.ndarray) -> str:
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return fn(*a, **k)
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print(f"{name}.npz  {os.path.getsize(path) / 1024:.0f} KiB")
+
+
+# ------------------------------------------------------------------ 1. project() vectors
+def gen_project():
+    out = {}
+    cases = []
+    for n, seed in [(200, 1), (2000, 2), (2048, 3), (4096, 4), (8192, 5), (4095, 6)]:
+        x = synth.synth(n, seed)
+        out[f"in_sha_{n}_{seed}"] = np.array(sha(x))
+        ps = [2, 3, 7, 12, 30, 33, 64, 97, 128, 210, 255, 360, 512, 840, 1000, 1024, n // 3, n // 2]
+        for p in sorted({p for p in ps if 2 <= p <= n // 2}):
+            for trunc in (False, True):
+                for orth in (False, True):
+                    y = quiet(Periods.project, x, p, trunc, orth)
+                    key = f"{n}_{seed}_{p}_{int(trunc)}{int(orth)}"
+                    if orth:  # non-orth cases are pinned bit-exactly by the sha alone
+                        out["one_" + key] = y[:p].copy()
+                    out["sha_" + key] = np.array(sha(y))
+                    out["norm_" + key] = np.array([Periods.periodic_norm(y), Periods.periodic_norm(y, p)])
+                    cases.append(key)
+    out["cases"] = np.array(cases)
+    # tiny exact KATs
+    out["kat_arange10_p3"] = Periods.project(np.arange(10.0), 3)
+    out["kat_arange10_p3_trunc"] = Periods.project(np.arange(10.0), 3, True)
+    out["kat_arange12_p4_orth"] = quiet(Periods.project, np.arange(12.0), 4, False, True)
+    save("project", **out)
+
+
+# ------------------------------------------------------------------ 2. config 1 (README signal)
+def gen_readme():
+    c = synth.readme_signal(0)
+    out = {"in_sha": np.array(sha(c))}
+    for tag, (trunc, orth) in {"00": (False, False), "11": (True, True)}.items():
+        P = Periods(trunc, orth)
+        per, pw, bs = quiet(P.small_to_large, c, 0.1)
+        out[f"s2l_{tag}_periods"], out[f"s2l_{tag}_powers"] = np.array(per), np.array(pw)
+        out[f"s2l_{tag}_bases"] = np.array(bs)
+        for name, fn in (("mbest", P.m_best), ("gamma", P.m_best_gamma)):
+            per, pw, bs = quiet(fn, c, num=10)
+            out[f"{name}_{tag}_periods"], out[f"{name}_{tag}_powers"], out[f"{name}_{tag}_bases"] = per, pw, bs
+        per, pw, bs = quiet(P.best_correlation, c, num=3)
+        out[f"bcorr_{tag}_periods"], out[f"bcorr_{tag}_powers"], out[f"bcorr_{tag}_bases"] = per, pw, bs
+    save("readme", **out)
+
+    # QOPeriods / Ramanujan on the README signal
+    out = {"in_sha": np.array(sha(c))}
+    q = QOPeriods()
+    d, res = quiet(q.find_periods, c, num=2, thresh=0.05)
+    out.update(qo_periods=np.array(d["periods"]), qo_norms=np.array(d["norms"]), qo_weights=d["weights"],
+               qo_res=res, qo_dict_keys=np.array([int(k) for k in d["basis_dictionary"]]),
+               qo_dict_vals=np.array(list(d["basis_dictionary"].values())))
+    gp = quiet(q.get_periods, d["weights"], d["basis_dictionary"], "lstsq")
+    for i, g in enumerate(gp):
+        out[f"qo_getp_lstsq_{i}"] = g
+    d3, res3 = quiet(q.find_periods, c, num=3, thresh=0.05)
+    out.update(qo3_periods=np.array(d3["periods"]), qo3_norms=np.array(d3["norms"]), qo3_weights=d3["weights"],
+               qo3_res=res3, qo3_dict_keys=np.array([int(k) for k in d3["basis_dictionary"]]),
+               qo3_dict_vals=np.array(list(d3["basis_dictionary"].values())))
+    for kind in ("row reduction", "lstsq"):
+        try:
+            gp = quiet(q.get_periods, d3["weights"], d3["basis_dictionary"], kind)
+            for i, g in enumerate(gp):
+                out[f"qo3_getp_{kind.replace(' ', '')}_{i}"] = g
+        except np.linalg.LinAlgError:
+            out[f"qo3_getp_{kind.replace(' ', '')}_linalgerror"] = np.array(1)
+    r = RamanujanPeriods()
+    norms = quiet(r.find_periods, c, 2, 120)
+    d, res = quiet(r.find_periods_with_weights, c, max_length=120, thresh=0.2)
+    out.update(ram_norms=norms, ram_periods=np.array(d["periods"]), ram_sel_norms=np.array(d["norms"]),
+               ram_weights=d["weights"], ram_res=res,
+               ram_dict_keys=np.array([int(k) for k in d["basis_dictionary"]]),
+               ram_dict_vals=np.array(list(d["basis_dictionary"].values())))
+    out["cq6"] = RamanujanPeriods.Cq(6)
+    out["cq12"] = RamanujanPeriods.Cq(12)
+    out["cq30"] = RamanujanPeriods.Cq(30)
+    save("readme_qo_ram", **out)
+
+
+# ------------------------------------------------------------------ 3. config 3: M-best on stream windows
+def gen_mbest_stream():
+    stream = synth.synth_stream(n_windows=128 * 3 + 1, n=4096, hop=512, seed0=30_000)
+    win = synth.windows_from_stream(stream)
+    out = {"stream_sha": np.array(sha(stream)), "window_ids": np.array([0, 128, 300])}
+    P = Periods()
+    for b in (0, 128, 300):
+        x = np.array(win[b])
+        for name, fn in (("mbest", P.m_best), ("gamma", P.m_best_gamma)):
+            per, pw, bs = quiet(fn, x, num=10, max_length=1024)
+            out[f"{name}_{b}_periods"], out[f"{name}_{b}_powers"] = per, pw
+            out[f"{name}_{b}_bases_sha"] = np.array(sha(bs))
+            out[f"{name}_{b}_bases_one"] = np.concatenate([bs[i, : int(per[i])] for i in range(10)])
+    save("mbest_stream", **out)
+
+
+# ------------------------------------------------------------------ 4. config 2: small-to-large, N=2048
+def gen_s2l():
+    out = {}
+    for b in range(4):
+        x = synth.synth(2048, 20_000 + b)
+        for tag, (trunc, orth) in {"00": (False, False), "10": (True, False), "11": (True, True)}.items():
+            per, pw, bs = quiet(Periods(trunc, orth).small_to_large, x, 0.1)
+            out[f"s2l_{b}_{tag}_periods"], out[f"s2l_{b}_{tag}_powers"] = np.array(per), np.array(pw)
+            out[f"s2l_{b}_{tag}_bases_sha"] = np.array(sha(np.array(bs)))
+    save("s2l_2048", **out)
+
+
+# ------------------------------------------------------------------ 5. config 4: best_correlation
+def gen_bcorr():
+    out = {}
+    for b in range(3):
+        x = synth.synth(2048, 40_000 + b)
+        for tag, (trunc, orth) in {"00": (False, False), "11": (True, True)}.items():
+            per, pw, bs = quiet(Periods(trunc, orth).best_correlation, x, num=5)
+            out[f"n2048_{b}_{tag}_periods"], out[f"n2048_{b}_{tag}_powers"] = per, pw
+            out[f"n2048_{b}_{tag}_bases_sha"] = np.array(sha(bs))
+    x = synth.synth(8192, 40_000)
+    per, pw, bs = quiet(Periods(True, True).best_correlation, x, num=2)
+    out["n8192_0_11_periods"], out["n8192_0_11_powers"] = per, pw
+    out["n8192_0_11_bases_sha"] = np.array(sha(bs))
+    out["n8192_0_11_bases_one"] = np.concatenate([bs[i, : int(per[i])] for i in range(2)])
+    save("bcorr", **out)
+
+
+# ------------------------------------------------------------------ 6. config 5: QO + Ramanujan on synth windows
+def gen_qo_ram():
+    out = {}
+    for b in range(2):
+        x = synth.synth(4096, 50_000 + b)
+        d, res = quiet(QOPeriods().find_periods, x, num=4, thresh=0.05)
+        out[f"qo_{b}_periods"], out[f"qo_{b}_norms"] = np.array(d["periods"]), np.array(d["norms"])
+        out[f"qo_{b}_weights"], out[f"qo_{b}_res"] = d["weights"], res
+        out[f"qo_{b}_dict_keys"] = np.array([int(k) for k in d["basis_dictionary"]])
+        out[f"qo_{b}_dict_vals"] = np.array(list(d["basis_dictionary"].values()))
+    for b in range(2):
+        x = synth.synth(1024, 50_000 + b)
+        r = RamanujanPeriods()
+        norms = quiet(r.find_periods, x)  # q = 2..341
+        d, res = quiet(r.find_periods_with_weights, x, thresh=0.2)
+        out[f"ram_{b}_norms"] = norms
+        out[f"ram_{b}_periods"], out[f"ram_{b}_sel_norms"] = np.array(d["periods"]), np.array(d["norms"])
+        out[f"ram_{b}_weights"], out[f"ram_{b}_res"] = d["weights"], res
+        out[f"ram_{b}_dict_keys"] = np.array([int(k) for k in d["basis_dictionary"]])
+        out[f"ram_{b}_dict_vals"] = np.array(list(d["basis_dictionary"].values()))
+    save("qo_ram_synth", **out)
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["project", "readme", "mbest_stream", "s2l", "bcorr", "qo_ram"]
+    for w in which:
+        globals()["gen_" + w]()
