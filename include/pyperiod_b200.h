@@ -1,0 +1,130 @@
+/*
+ * pyperiod_b200 -- C ABI of the B200-native periodicity-projection hot path.
+ *
+ * The reference (woolgathering/pyPeriod) is pure Python; it has no FFI.  The drop-in
+ * boundary is its Python class API, and this header is what the Python layer
+ * (pyperiod_b200/*.py, ctypes) binds underneath it.  Each entry point names the
+ * reference interface it replaces (file:line relative to the reference root).
+ *
+ * Conventions
+ *  - extern "C", plain pointers and sizes; no C++ or torch types cross the edge.
+ *  - Every data pointer is a DEVICE pointer unless the name ends in `_host`.
+ *  - x is a batch of B windows of N float64 samples; window b starts at x + b*ldx
+ *    (ldx in ELEMENTS; ldx < N is allowed and means overlapping windows cut from one
+ *    stream, e.g. ldx = hop = 512 for config 3).
+ *  - `stream` is a cudaStream_t passed as void*; calls only enqueue work (no sync)
+ *    unless documented.  The library allocates nothing the caller must free:
+ *    workspaces are caller-owned, sized by pp_workspace_bytes().
+ *  - Return value: 0 on success, <0 on argument / CUDA error (text via
+ *    pp_last_error()).  Data-dependent outcomes (no period found, singular Gram, kmax
+ *    overflow) go to the per-window int32 status[B] output, never to the return code.
+ *  - Integer side tables (pp_tables_*) are built on the host by evaluating the
+ *    reference's own divisor-set expression, because CPython set iteration order
+ *    decides the orthogonalisation order and M-best step 2.
+ */
+#ifndef PYPERIOD_B200_H
+#define PYPERIOD_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PP_ABI_VERSION 1
+
+/* sweep metrics */
+#define PP_METRIC_NORM 0   /* ||proj_p|| / sqrt(N)                 Periods.py:221-241, 507-508 */
+#define PP_METRIC_GAMMA 1  /* ... / sqrt(p)                        Periods.py:239, 509-510      */
+#define PP_METRIC_MAXABS 2 /* max_s |sum x[s::p]|                  Periods.py:327-331           */
+#define PP_METRIC_IMPOSED 3 /* (||r|| - ||r - proj_p r||)/||x||    Periods.py:278-280           */
+
+/* per-window status codes */
+#define PP_STATUS_OK 0
+#define PP_STATUS_NO_PERIOD 1   /* sweep found no positive metric (reference raises TypeError) */
+#define PP_STATUS_OVERFLOW 2    /* more accepted periods than kmax (small_to_large)            */
+#define PP_STATUS_SINGULAR 3    /* Gram matrix not positive definite (reference: LinAlgError)  */
+#define PP_STATUS_GUARD 4       /* iteration guard tripped                                     */
+
+/* workspace selector for pp_workspace_bytes */
+#define PP_ALGO_SWEEP 0
+#define PP_ALGO_MBEST 1
+#define PP_ALGO_S2L 2
+#define PP_ALGO_BCORR 3
+#define PP_ALGO_QO 4
+#define PP_ALGO_RAMANUJAN 5
+
+int pp_abi_version(void);
+const char *pp_last_error(void);
+
+/* Device facts the host uses for grid sizing / roofline arithmetic (current device). */
+int pp_device_info(int32_t *sm_count, int32_t *smem_optin_bytes, int32_t *cc_major, int32_t *cc_minor,
+                   int32_t *clock_khz);
+
+/* Number of persistent CTAs the library launches for this shape (grid size), and the
+ * caller-owned workspace it needs.  `orth` matters because orthogonalised sweeps use a
+ * per-warp global scratch. */
+int pp_grid_size(int32_t algo, int32_t N, int32_t pmax, int32_t orth);
+size_t pp_workspace_bytes(int32_t algo, int32_t N, int32_t pmax, int32_t num, int32_t orth);
+
+/* Integer side tables (device arrays, indexed by period p in [0, table_pmax]):
+ *   chain_off[p] .. chain_off[p+1] : cofactors p//f, f prime divisor of p, reference set order
+ *                                    (Periods.py:208-214)
+ *   fac_off[p] .. fac_off[p+1]     : non-trivial divisors of p, reference set order
+ *                                    (Periods.py:548-549)
+ * Passed as five arguments wherever a call may orthogonalise or run M-best step 2. */
+
+/* ---- Periods.project (Periods.py:142-219) -------------------------------------------
+ * out[b, 0:out_len] = project(x[b], p, trunc, orth)[0:out_len]; out_len = N, or p for
+ * return_single_period.  chain_q_host[0:chain_len] = cofactors for this p (empty = no
+ * orthogonalisation).  Bit-exact with the reference's numpy arithmetic. */
+int pp_project(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t p, int32_t trunc,
+               const int32_t *chain_q_host, int32_t chain_len, double *out, int64_t ldo, int32_t out_len,
+               void *stream);
+
+/* ---- Periods.periodic_norm (Periods.py:221-241) -------------------------------------
+ * out[b] = ||x_b||_2 / sqrt(N), additionally / sqrt(p) when p > 0 (the "gamma" norm). */
+int pp_periodic_norm(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t p, double *out, void *stream);
+
+/* ---- one sweep over p in [pmin, pmax] (inner loops of Periods.py:501-515, 324-331,
+ *      QOPeriods.py:470-478) ------------------------------------------------------------
+ * metric_out (nullable): [B, pmax+1] row-major, entries below pmin untouched.
+ * best_p / best_val: strict-'>' argmax from 0 in ascending p (lowest p wins ties); best_p = 0
+ * when no metric is positive.  PP_METRIC_IMPOSED is evaluated against the window itself
+ * as both residual and data (thresholding is done by pp_small_to_large). */
+int pp_sweep(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, int32_t pmax, int32_t metric,
+             int32_t trunc, int32_t orth, const int32_t *chain_off, const int32_t *chain_q, int32_t table_pmax,
+             double *metric_out, int32_t *best_p, double *best_val, void *workspace, size_t workspace_bytes,
+             void *stream);
+
+/* ---- Periods.m_best / m_best_gamma (Periods.py:408-601) -------------------------------
+ * periods[B,num] u32, powers[B,num] f64, bases[B,num,N] f64 (nullable: bases stay on chip /
+ * in the workspace), sweeps[B] = step-1 sweeps executed (nullable), status[B]. */
+int pp_mbest(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t num, int32_t pmin, int32_t pmax,
+             int32_t gamma, int32_t trunc, int32_t orth, const int32_t *chain_off, const int32_t *chain_q,
+             const int32_t *fac_off, const int32_t *fac, int32_t table_pmax, uint32_t *periods, double *powers,
+             double *bases, int32_t *sweeps, int32_t *status, void *workspace, size_t workspace_bytes,
+             void *stream);
+
+/* ---- Periods.small_to_large (Periods.py:246-287) --------------------------------------
+ * p runs 2..n_periods; periods[B,kmax] u32, powers[B,kmax], bases[B,kmax,N] (nullable),
+ * count[B] = number accepted (may exceed kmax: then status = PP_STATUS_OVERFLOW and only
+ * the first kmax are stored). */
+int pp_small_to_large(const double *x, int64_t ldx, int32_t B, int32_t N, double thresh, int32_t n_periods,
+                      int32_t trunc, int32_t orth, const int32_t *chain_off, const int32_t *chain_q,
+                      int32_t table_pmax, int32_t kmax, uint32_t *periods, double *powers, double *bases,
+                      int32_t *count, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- Periods.best_correlation (Periods.py:289-349) ------------------------------------
+ * candidates p in [2, max_length) (max_length excluded, :324); rejected rounds leave
+ * periods/powers/bases rows at zero. */
+int pp_best_correlation(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t num, int32_t max_length,
+                        double ratio, int32_t trunc, int32_t orth, const int32_t *chain_off,
+                        const int32_t *chain_q, int32_t table_pmax, uint32_t *periods, double *powers,
+                        double *bases, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PYPERIOD_B200_H */

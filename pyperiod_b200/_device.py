@@ -1,0 +1,120 @@
+"""Buffer plumbing: torch owns every device buffer; kernels get raw pointers + a stream."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+
+
+def require_cuda(device=None) -> torch.device:
+    if not torch.cuda.is_available():
+        raise RuntimeError("pyperiod_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise RuntimeError("pyperiod_b200 only computes on CUDA devices")
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+@dataclass
+class Windows:
+    """A batch of windows resident on the device: window b = base[b*ldx : b*ldx + n]."""
+    tensor: torch.Tensor   # keeps the storage alive; data_ptr() is window 0
+    b: int
+    n: int
+    ldx: int
+    was_1d: bool
+    from_host: bool        # results go back to numpy
+
+    @property
+    def ptr(self) -> int:
+        return self.tensor.data_ptr()
+
+    @property
+    def device(self) -> torch.device:
+        return self.tensor.device
+
+
+def stage_windows(data, device=None) -> Windows:
+    """Accept a 1-D signal or a (B, N) batch (numpy / torch, host / device) and put it on the GPU.
+
+    Overlapping row-strided views (stride0 < N, e.g. hop-512 frames of one stream) are uploaded
+    once as the underlying stream and read in place by the kernels (ldx = hop).
+    """
+    if isinstance(data, torch.Tensor):
+        t = data
+        if t.dtype != torch.float64:
+            t = t.to(torch.float64)
+        was_1d = t.dim() == 1
+        if was_1d:
+            t = t.unsqueeze(0)
+        if t.dim() != 2:
+            raise ValueError("data must be 1-D or (B, N)")
+        from_host = t.device.type != "cuda"
+        dev = require_cuda(device if from_host else t.device)
+        b, n = t.shape
+        if b > 1 and t.stride(1) == 1 and 0 < t.stride(0) < n:       # overlapping frames
+            span = (b - 1) * t.stride(0) + n
+            flat = torch.as_strided(t, (span,), (1,))
+            flat = flat.to(dev, non_blocking=True) if from_host else flat
+            view = torch.as_strided(flat, (b, n), (t.stride(0), 1))
+            return Windows(view, b, n, t.stride(0), was_1d, from_host)
+        if t.stride(1) != 1 or (b > 1 and t.stride(0) < n):
+            t = t.contiguous()
+        if from_host:
+            t = t.to(dev, non_blocking=True)
+        return Windows(t, b, n, t.stride(0) if b > 1 else n, was_1d, from_host)
+
+    arr = np.asarray(data)
+    if arr.dtype != np.float64:
+        arr = arr.astype(np.float64)
+    was_1d = arr.ndim == 1
+    if was_1d:
+        arr = arr[None, :]
+    if arr.ndim != 2:
+        raise ValueError("data must be 1-D or (B, N)")
+    dev = require_cuda(device)
+    b, n = arr.shape
+    s0, s1 = arr.strides
+    if b > 1 and s1 == 8 and 0 < s0 < n * 8 and s0 % 8 == 0:          # overlapping frames
+        hop = s0 // 8
+        span = (b - 1) * hop + n
+        flat = np.lib.stride_tricks.as_strided(arr, shape=(span,), strides=(8,), writeable=False)
+        dflat = torch.from_numpy(np.ascontiguousarray(flat)).to(dev)
+        view = torch.as_strided(dflat, (b, n), (hop, 1))
+        return Windows(view, b, n, hop, was_1d, True)
+    t = torch.from_numpy(np.ascontiguousarray(arr)).to(dev)
+    return Windows(t, b, n, n, was_1d, True)
+
+
+class Workspace:
+    """Per-device growable scratch buffer handed to the library (caller-owned workspace)."""
+    _bufs: dict = {}
+
+    @classmethod
+    def get(cls, device: torch.device, nbytes: int) -> torch.Tensor:
+        key = str(device)
+        buf = cls._bufs.get(key)
+        if buf is None or buf.numel() < nbytes:
+            buf = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
+            cls._bufs[key] = buf
+        return buf
+
+
+def stream_ptr(device: torch.device) -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def ptr(t) -> C.c_void_p:
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def to_host(t: torch.Tensor) -> np.ndarray:
+    return t.cpu().numpy()

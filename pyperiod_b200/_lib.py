@@ -1,0 +1,83 @@
+"""ctypes binding of libpyperiod_b200.so (include/pyperiod_b200.h).
+
+There is no CPU fallback: if the shared object is missing the import of any product
+class raises, telling the user to run `python -m pyperiod_b200.build`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libpyperiod_b200.so")
+
+ABI_VERSION = 1
+
+METRIC_NORM, METRIC_GAMMA, METRIC_MAXABS, METRIC_IMPOSED = 0, 1, 2, 3
+STATUS_OK, STATUS_NO_PERIOD, STATUS_OVERFLOW, STATUS_SINGULAR, STATUS_GUARD = 0, 1, 2, 3, 4
+ALGO_SWEEP, ALGO_MBEST, ALGO_S2L, ALGO_BCORR, ALGO_QO, ALGO_RAMANUJAN = 0, 1, 2, 3, 4, 5
+
+_p = C.c_void_p
+_i32 = C.c_int32
+_i64 = C.c_int64
+_f64 = C.c_double
+_sz = C.c_size_t
+
+# name -> (restype, argtypes); every symbol include/pyperiod_b200.h declares
+SIGNATURES = {
+    "pp_abi_version": (C.c_int, []),
+    "pp_last_error": (C.c_char_p, []),
+    "pp_device_info": (C.c_int, [_p, _p, _p, _p, _p]),
+    "pp_grid_size": (C.c_int, [_i32, _i32, _i32, _i32]),
+    "pp_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "pp_project": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _p, _i64, _i32, _p]),
+    "pp_periodic_norm": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p]),
+    "pp_sweep": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _sz, _p]),
+    "pp_mbest": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i32,
+                           _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "pp_small_to_large": (C.c_int, [_p, _i64, _i32, _i32, _f64, _i32, _i32, _i32, _p, _p, _i32, _i32,
+                                    _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "pp_best_correlation": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _f64, _i32, _i32, _p, _p, _i32,
+                                      _p, _p, _p, _p, _p, _sz, _p]),
+}
+
+_lib = None
+
+
+class PPError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the library once and attach signatures.  Raises if it was never built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} not found: the CUDA library is not built and there is no CPU path. "
+            "Run `python -m pyperiod_b200.build` (needs nvcc).")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    got = lib.pp_abi_version()
+    if got != ABI_VERSION:
+        raise ImportError(f"libpyperiod_b200.so ABI {got} != expected {ABI_VERSION}; rebuild it")
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = load().pp_last_error().decode("utf-8", "replace")
+        raise PPError(f"{what} failed ({rc}): {msg}")
+
+
+def device_info() -> dict:
+    lib = load()
+    vals = [C.c_int32() for _ in range(5)]
+    check(lib.pp_device_info(*[C.byref(v) for v in vals]), "pp_device_info")
+    keys = ["sm_count", "smem_optin_bytes", "cc_major", "cc_minor", "clock_khz"]
+    return {k: v.value for k, v in zip(keys, vals)}

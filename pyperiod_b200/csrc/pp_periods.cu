@@ -1,0 +1,843 @@
+// pyperiod_b200 -- persistent on-chip kernels for the Sethares-Staley `Periods` algorithms
+// (project, sweep, M-best / M-best-gamma, small-to-large, best-correlation) and their C ABI.
+//
+// One CTA owns one window at a time: the window is staged once into shared memory by a TMA
+// bulk copy, every sweep / projection / residual update happens there, and only the compact
+// periods / powers (and, on request, the bases) go back to HBM.  The grid is persistent:
+// 2 CTAs per SM x SM count, looping over windows.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/pyperiod_b200.h"
+#include "pp_common.cuh"
+#include "pp_sweep.cuh"
+
+namespace pp {
+
+// ------------------------------------------------------------------------------------------
+// host-side error text
+// ------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+int fail(int code, const char* fmt, const char* a = "") {
+  snprintf(g_err, sizeof(g_err), fmt, a);
+  return code;
+}
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  snprintf(g_err, sizeof(g_err), "%s: %s", what, cudaGetErrorString(e));
+  return -100 - (int)e;
+}
+
+// ------------------------------------------------------------------------------------------
+// shared-memory plan (identical on host and device)
+// ------------------------------------------------------------------------------------------
+struct SmemPlan {
+  int xs_len;   // doubles: window + zero pad
+  int pv;       // doubles: single-period vectors (vwin, utmp)
+  int num;      // slots (M-best) / rounds
+  int skip_words;
+  __host__ __device__ size_t off_vwin() const { return (size_t)xs_len * 8; }
+  __host__ __device__ size_t off_utmp() const { return off_vwin() + (size_t)pv * 8; }
+  __host__ __device__ size_t off_red() const { return off_utmp() + (size_t)pv * 8; }
+  __host__ __device__ size_t off_norms() const { return off_red() + 2 * kWarps * 8; }
+  __host__ __device__ size_t off_fval() const { return off_norms() + (size_t)((num + 1) & ~1) * 8; }
+  __host__ __device__ size_t off_bar() const { return off_fval() + (size_t)kMaxFactors * 8; }
+  __host__ __device__ size_t off_sweep() const { return off_bar() + 16; }
+  __host__ __device__ size_t off_periods() const { return off_sweep() + ((sizeof(SweepShared) + 15) & ~15); }
+  __host__ __device__ size_t off_slot() const { return off_periods() + (size_t)num * 4; }
+  __host__ __device__ size_t off_skip() const { return off_slot() + (size_t)num * 4; }
+  __host__ __device__ size_t off_misc() const { return off_skip() + (size_t)skip_words * 4; }
+  __host__ __device__ size_t bytes() const { return off_misc() + 64; }
+};
+
+__host__ __device__ inline SmemPlan make_plan(int N, int pmax, int num, bool sweep_pad) {
+  SmemPlan pl;
+  pl.xs_len = sweep_pad ? ((N + pmax + kSweepPad + 1) & ~1) : ((N + 1) & ~1);
+  pl.pv = (pmax + 2) & ~1;
+  pl.num = num;
+  pl.skip_words = (pmax + 32) / 32;
+  return pl;
+}
+
+struct Smem {
+  double* xs;
+  double* vwin;
+  double* utmp;
+  double* red;
+  double* norms;
+  double* fval;
+  uint64_t* bar;
+  SweepShared* sweep;
+  int* periods;
+  int* slot;
+  uint32_t* skip;
+  int* misc;
+  __device__ Smem(unsigned char* base, const SmemPlan& pl) {
+    xs = reinterpret_cast<double*>(base);
+    vwin = reinterpret_cast<double*>(base + pl.off_vwin());
+    utmp = reinterpret_cast<double*>(base + pl.off_utmp());
+    red = reinterpret_cast<double*>(base + pl.off_red());
+    norms = reinterpret_cast<double*>(base + pl.off_norms());
+    fval = reinterpret_cast<double*>(base + pl.off_fval());
+    bar = reinterpret_cast<uint64_t*>(base + pl.off_bar());
+    sweep = reinterpret_cast<SweepShared*>(base + pl.off_sweep());
+    periods = reinterpret_cast<int*>(base + pl.off_periods());
+    slot = reinterpret_cast<int*>(base + pl.off_slot());
+    skip = reinterpret_cast<uint32_t*>(base + pl.off_skip());
+    misc = reinterpret_cast<int*>(base + pl.off_misc());
+  }
+};
+
+__device__ __forceinline__ void zero_pad(double* xs, int from, int to) {
+  for (int i = from + threadIdx.x; i < to; i += kThreads) xs[i] = 0.0;
+}
+
+struct Tables {
+  const int32_t* chain_off;
+  const int32_t* chain_q;
+  const int32_t* fac_off;
+  const int32_t* fac;
+};
+
+// ------------------------------------------------------------------------------------------
+// K0: Periods.project for a batch (Periods.py:142-219)
+// ------------------------------------------------------------------------------------------
+struct ChainArg {
+  int32_t q[16];
+  int32_t len;
+};
+
+__global__ void __launch_bounds__(kThreads, 2)
+project_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int p, int trunc, ChainArg chain,
+               double* __restrict__ out, int64_t ldo, int out_len) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const SmemPlan pl = make_plan(N, p, 0, false);
+  Smem sm(smem_raw, pl);
+  __shared__ int32_t s_chain[16];
+  if (threadIdx.x < 16) s_chain[threadIdx.x] = chain.q[threadIdx.x];
+  WindowLoader loader;
+  loader.init(sm.bar);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    loader.load(sm.xs, x + (size_t)b * ldx, N);
+    cta_project_exact<false>(sm.xs, 0, N, p, trunc != 0, s_chain, chain.len, sm.vwin, sm.utmp);
+    cta_store_tiled(out + (size_t)b * ldo, out_len, sm.vwin, p);
+  }
+}
+
+// periodic_norm for a batch (Periods.py:221-241): out[b] = ||x_b|| / sqrt(N) [/ sqrt(p)]
+__global__ void __launch_bounds__(kThreads)
+norm_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int p, double* __restrict__ out) {
+  __shared__ double red[kWarps];
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    const double e = cta_sum_sq(x + (size_t)b * ldx, N, red);
+    if (threadIdx.x == 0) {
+      double v = sqrt(e) / sqrt((double)N);
+      if (p > 0) v = v / sqrt((double)p);
+      out[b] = v;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K1: one sweep per window (parity probe and building block)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2)
+sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, int pmax, int metric, int trunc,
+             int orth, Tables tb, double* __restrict__ metric_out, int32_t* __restrict__ best_p,
+             double* __restrict__ best_val, double* __restrict__ warp_scr) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const SmemPlan pl = make_plan(N, pmax, 0, true);
+  Smem sm(smem_raw, pl);
+  WindowLoader loader;
+  loader.init(sm.bar);
+  zero_pad(sm.xs, N, pl.xs_len);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    loader.load(sm.xs, x + (size_t)b * ldx, N);
+    SweepParams sp;
+    sp.xs = sm.xs;
+    sp.N = N;
+    sp.pmin = pmin;
+    sp.pmax = pmax;
+    sp.metric = metric;
+    sp.trunc = trunc != 0;
+    sp.orth = orth != 0;
+    sp.chain_off = tb.chain_off;
+    sp.chain_q = tb.chain_q;
+    sp.warp_scr = warp_scr ? warp_scr + (size_t)blockIdx.x * kWarps * 2 * pl.pv : nullptr;
+    sp.pv = pl.pv;
+    sp.sqrtN = sqrt((double)N);
+    sp.e_res = 0.0;
+    sp.data_norm = 1.0;
+    if (metric == PP_METRIC_IMPOSED) {
+      sp.e_res = cta_sum_sq(sm.xs, N, sm.red);
+      sp.data_norm = sqrt(sp.e_res) / sp.sqrtN;
+    }
+    sp.thresh = -1.0;
+    sp.skip = nullptr;
+    sp.metric_out = metric_out ? metric_out + (size_t)b * (pmax + 1) : nullptr;
+    const SweepResult r = cta_sweep(sp, sm.sweep);
+    if (threadIdx.x == 0) {
+      best_p[b] = r.p;
+      best_val[b] = r.val;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K2: M-best / M-best-gamma, whole selection loop on chip (Periods.py:456-601)
+// ------------------------------------------------------------------------------------------
+// Norm of the projection of a P-periodic slot basis (tiled to N) onto a divisor f, by one warp.
+// Ranking only (multiplicity sums instead of N sequential adds).
+__device__ __forceinline__ double warp_slot_factor_norm(const double* slot, int P, int f, int N,
+                                                        bool trunc, bool orth, const Tables& tb, double* scr,
+                                                        double sqrtN) {
+  const int lane = threadIdx.x & 31;
+  const int t = P / f;
+  const int Mf = N / f, r0f = N - Mf * f;
+  double e = 0.0;
+  for (int r = lane; r < f; r += 32) {
+    const int K = trunc ? Mf : (Mf + (r < r0f ? 1 : 0));
+    const int base = K / t, rem = K - base * t;
+    double s = 0.0;
+    for (int j = 0; j < t; ++j) s = fma((double)(base + (j < rem ? 1 : 0)), slot[r + j * f], s);
+    const double mean = s / (double)K;
+    if (orth) scr[r] = mean;
+    else e = fma((double)(Mf + (r < r0f ? 1 : 0)) * mean, mean, e);
+  }
+  if (orth) {
+    __syncwarp();
+    warp_orth_chain_approx(scr, f, N, trunc, tb.chain_q + tb.chain_off[f], tb.chain_off[f + 1] - tb.chain_off[f]);
+    for (int r = lane; r < f; r += 32) {
+      const double v = scr[r];
+      e = fma((double)(Mf + (r < r0f ? 1 : 0)) * v, v, e);
+    }
+    __syncwarp();
+  }
+  return sqrt(warp_sum(e)) / sqrtN;
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, int pmin, int pmax, int gamma,
+             int trunc_i, int orth_i, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
+             double* __restrict__ bases_out, int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
+             double* __restrict__ ws_slots, double* __restrict__ ws_scr) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const SmemPlan pl = make_plan(N, pmax, num, true);
+  Smem sm(smem_raw, pl);
+  const bool trunc = trunc_i != 0, orth = orth_i != 0;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const double sqrtN = sqrt((double)N);
+  double* my_slots = ws_slots + (size_t)blockIdx.x * num * pl.pv;
+  double* my_scr = ws_scr ? ws_scr + (size_t)blockIdx.x * kWarps * 2 * pl.pv : nullptr;
+  // misc: [0]=filled [1]=repeats [2]=action [3]=slot storage id [4]=status [5]=step-2 decision [6]=chosen factor
+  int* misc = sm.misc;
+
+  WindowLoader loader;
+  loader.init(sm.bar);
+  zero_pad(sm.xs, N, pl.xs_len);
+
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    loader.load(sm.xs, x + (size_t)b * ldx, N);
+    const double e_data = cta_sum_sq(sm.xs, N, sm.red);
+    const double data_norm = sqrt(e_data) / sqrtN;  // periodic_norm(data), Periods.py:600
+    if (threadIdx.x == 0) {
+      misc[0] = 0;
+      misc[1] = 0;
+      misc[4] = PP_STATUS_OK;
+    }
+    for (int i = threadIdx.x; i < num; i += kThreads) {
+      sm.periods[i] = 0;
+      sm.norms[i] = 0.0;
+      sm.slot[i] = i;
+    }
+    for (int i = threadIdx.x; i < pl.skip_words; i += kThreads) sm.skip[i] = 0u;
+    __syncthreads();
+
+    SweepParams sp;
+    sp.xs = sm.xs;
+    sp.N = N;
+    sp.pmin = pmin;
+    sp.pmax = pmax;
+    sp.metric = gamma ? PP_METRIC_GAMMA : PP_METRIC_NORM;
+    sp.trunc = trunc;
+    sp.orth = orth;
+    sp.chain_off = tb.chain_off;
+    sp.chain_q = tb.chain_q;
+    sp.warp_scr = my_scr;
+    sp.pv = pl.pv;
+    sp.sqrtN = sqrtN;
+    sp.e_res = 0.0;
+    sp.data_norm = 1.0;
+    sp.thresh = -1.0;
+    sp.skip = sm.skip;
+    sp.metric_out = nullptr;
+
+    // ---------------- step 1 (Periods.py:494-537)
+    int sweeps = 0;
+    const int guard = 12 * (pmax - pmin + 2) + 12 * num;
+    while (true) {
+      if (misc[0] >= num || misc[4] != PP_STATUS_OK) break;  // uniform: read after a barrier
+      const SweepResult top = cta_sweep(sp, sm.sweep);
+      ++sweeps;
+      if (top.p == 0 || sweeps > guard) {
+        if (threadIdx.x == 0) misc[4] = top.p == 0 ? PP_STATUS_NO_PERIOD : PP_STATUS_GUARD;
+        __syncthreads();
+        break;
+      }
+      const int clen = orth ? tb.chain_off[top.p + 1] - tb.chain_off[top.p] : 0;
+      cta_project_exact<false>(sm.xs, 0, N, top.p, trunc, orth ? tb.chain_q + tb.chain_off[top.p] : nullptr, clen,
+                               sm.vwin, sm.utmp);
+      if (threadIdx.x == 0) {
+        int found = -1;
+        for (int i = 0; i < num; ++i)
+          if (sm.periods[i] == top.p) found = i;
+        if (found >= 0 && misc[1] < 10) {          // strengthen an existing slot (:518-524)
+          sm.norms[found] += top.val;
+          misc[1] += 1;
+          misc[2] = 0;
+          misc[3] = sm.slot[found];
+        } else if (found >= 0) {                   // blacklist it (:525-529)
+          sm.skip[top.p >> 5] |= 1u << (top.p & 31);
+          misc[1] = 0;
+          misc[2] = 1;
+        } else {                                   // new slot (:530-535)
+          const int i = misc[0];
+          sm.periods[i] = top.p;
+          sm.norms[i] = top.val;
+          misc[0] = i + 1;
+          misc[1] = 0;
+          misc[2] = 2;
+          misc[3] = sm.slot[i];
+        }
+      }
+      __syncthreads();
+      const int action = misc[2];
+      if (action != 1) {
+        double* sl = my_slots + (size_t)misc[3] * pl.pv;
+        if (action == 0) {
+          for (int r = threadIdx.x; r < top.p; r += kThreads) sl[r] += sm.vwin[r];
+        } else {
+          for (int r = threadIdx.x; r < top.p; r += kThreads) sl[r] = sm.vwin[r];
+        }
+      }
+      cta_subtract_tiled(sm.xs, N, sm.vwin, top.p);  // always (:537)
+      __syncthreads();
+    }
+
+    // ---------------- step 2 (Periods.py:540-598), one pass
+    if (misc[4] == PP_STATUS_OK) {
+      const double stale_div = sqrt((double)pmax);  // gamma norms divide by sqrt(max_length) (:559,:572)
+      int i = 0;
+      int changes = 0;
+      while (i < num) {
+        const int P = sm.periods[i];
+        const double* sl = my_slots + (size_t)sm.slot[i] * pl.pv;
+        const int f0 = tb.fac_off[P], nf = tb.fac_off[P + 1] - f0;
+        if (nf > kMaxFactors || changes > 64 * num) {
+          if (threadIdx.x == 0) misc[4] = PP_STATUS_GUARD;
+          __syncthreads();
+          break;
+        }
+        __threadfence_block();
+        for (int fi = wid; fi < nf; fi += kWarps) {
+          const int f = tb.fac[f0 + fi];
+          double v = warp_slot_factor_norm(sl, P, f, N, trunc, orth, tb, my_scr ? my_scr + (size_t)wid * 2 * pl.pv : nullptr,
+                                           sqrtN);
+          if (gamma) v = v / stale_div;
+          if (lane == 0) sm.fval[fi] = v;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+          double top = 0.0;
+          int top_f = 0;
+          for (int fi = 0; fi < nf; ++fi) {
+            if (sm.fval[fi] > top) {
+              top = sm.fval[fi];
+              top_f = tb.fac[f0 + fi];
+            }
+          }
+          int decision = 0;
+          if (top_f != 0) {
+            bool present = false;
+            for (int k = 0; k < num; ++k) present |= (sm.periods[k] == top_f);
+            if (!present) {
+              const double n_strong = top;
+              const double n_weak = sm.fval[nf - 1];  // norm of the LAST factor's projection (:570-572)
+              double floor_n = sm.norms[0];
+              for (int k = 1; k < num; ++k) floor_n = fmin(floor_n, sm.norms[k]);
+              if ((n_weak + n_strong) > (sm.norms[num - 1] + sm.norms[i]) && n_weak > floor_n && n_strong > floor_n) {
+                decision = 1;
+                // slot i keeps its period with the weakened basis; the strong factor is inserted before it
+                const int freed = sm.slot[num - 1];
+                for (int k = num - 1; k > i; --k) {
+                  sm.periods[k] = sm.periods[k - 1];
+                  sm.norms[k] = sm.norms[k - 1];
+                  sm.slot[k] = sm.slot[k - 1];
+                }
+                // after the shift, entries i and i+1 both describe the old slot (when i+1 < num)
+                if (i + 1 < num) sm.norms[i + 1] = n_weak;
+                sm.periods[i] = top_f;
+                sm.norms[i] = n_strong;
+                sm.slot[i] = freed;
+                misc[3] = freed;
+              }
+            }
+          }
+          misc[5] = decision;
+          misc[6] = top_f;
+        }
+        __syncthreads();
+        if (misc[5]) {
+          const int f = misc[6];
+          const int clen = orth ? tb.chain_off[f + 1] - tb.chain_off[f] : 0;
+          // exact xQ = project(bases[i], f) from the (still unmodified) old slot storage
+          cta_project_exact<true>(sl, P, N, f, trunc, orth ? tb.chain_q + tb.chain_off[f] : nullptr, clen, sm.vwin,
+                                  sm.utmp);
+          double* old_sl = const_cast<double*>(sl);
+          double* new_sl = my_slots + (size_t)misc[3] * pl.pv;
+          const bool old_survives = (i + 1 < num);
+          // xq = bases[i] - xQ (elementwise on one period), unless the old slot was the one dropped
+          if (old_survives) {
+            int rq = threadIdx.x % f;
+            const int step = kThreads % f;
+            for (int r = threadIdx.x; r < P; r += kThreads) {
+              old_sl[r] = old_sl[r] - sm.vwin[rq];
+              rq += step;
+              if (rq >= f) rq -= f;
+            }
+          }
+          __syncthreads();  // old_sl may alias new_sl when the old slot was dropped
+          for (int r = threadIdx.x; r < f; r += kThreads) new_sl[r] = sm.vwin[r];
+          ++changes;
+          __syncthreads();
+        } else {
+          ++i;
+        }
+      }
+    }
+
+    // ---------------- outputs
+    __syncthreads();
+    const int status = misc[4];
+    for (int i = threadIdx.x; i < num; i += kThreads) {
+      const bool ok = status == PP_STATUS_OK;
+      periods_out[(size_t)b * num + i] = ok ? (uint32_t)sm.periods[i] : 0u;
+      powers_out[(size_t)b * num + i] = ok ? sm.norms[i] / data_norm : 0.0;
+    }
+    if (threadIdx.x == 0) {
+      status_out[b] = status;
+      if (sweeps_out) sweeps_out[b] = sweeps;
+    }
+    if (bases_out != nullptr) {
+      for (int i = 0; i < num; ++i) {
+        double* dst = bases_out + ((size_t)b * num + i) * N;
+        const int P = sm.periods[i];
+        if (status == PP_STATUS_OK && P > 0) {
+          cta_store_tiled(dst, N, my_slots + (size_t)sm.slot[i] * pl.pv, P);
+        } else {
+          for (int n = threadIdx.x; n < N; n += kThreads) __stcs(dst + n, 0.0);
+        }
+      }
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K3: small-to-large (Periods.py:246-287): speculative sweep, restart after each acceptance
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2)
+s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thresh, int n_periods, int trunc_i,
+           int orth_i, Tables tb, int kmax, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
+           double* __restrict__ bases_out, int32_t* __restrict__ count_out, int32_t* __restrict__ status_out,
+           double* __restrict__ ws_scr) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const SmemPlan pl = make_plan(N, n_periods, 0, true);
+  Smem sm(smem_raw, pl);
+  const bool trunc = trunc_i != 0, orth = orth_i != 0;
+  const double sqrtN = sqrt((double)N);
+  double* my_scr = ws_scr ? ws_scr + (size_t)blockIdx.x * kWarps * 2 * pl.pv : nullptr;
+  WindowLoader loader;
+  loader.init(sm.bar);
+  zero_pad(sm.xs, N, pl.xs_len);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    loader.load(sm.xs, x + (size_t)b * ldx, N);
+    const double e_data = cta_sum_sq(sm.xs, N, sm.red);
+    SweepParams sp;
+    sp.xs = sm.xs;
+    sp.N = N;
+    sp.pmax = n_periods;
+    sp.metric = PP_METRIC_IMPOSED;
+    sp.trunc = trunc;
+    sp.orth = orth;
+    sp.chain_off = tb.chain_off;
+    sp.chain_q = tb.chain_q;
+    sp.warp_scr = my_scr;
+    sp.pv = pl.pv;
+    sp.sqrtN = sqrtN;
+    sp.e_res = e_data;
+    sp.data_norm = sqrt(e_data) / sqrtN;
+    sp.thresh = thresh < 0.0 ? 0.0 : thresh;
+    sp.skip = nullptr;
+    sp.metric_out = nullptr;
+    int count = 0;
+    int pstart = 2;
+    // thresh < 0 would accept every period in the reference; first-hit mode needs thresh >= 0,
+    // the host rejects negative thresholds.
+    while (pstart <= n_periods) {
+      sp.pmin = pstart;
+      const SweepResult hit = cta_sweep(sp, sm.sweep);
+      if (hit.p == 0) break;
+      const int clen = orth ? tb.chain_off[hit.p + 1] - tb.chain_off[hit.p] : 0;
+      cta_project_exact<false>(sm.xs, 0, N, hit.p, trunc, orth ? tb.chain_q + tb.chain_off[hit.p] : nullptr, clen,
+                               sm.vwin, sm.utmp);
+      cta_subtract_tiled(sm.xs, N, sm.vwin, hit.p);
+      if (count < kmax) {
+        if (threadIdx.x == 0) {
+          periods_out[(size_t)b * kmax + count] = (uint32_t)hit.p;
+          powers_out[(size_t)b * kmax + count] = hit.val;
+        }
+        if (bases_out) cta_store_tiled(bases_out + ((size_t)b * kmax + count) * N, N, sm.vwin, hit.p);
+      }
+      ++count;
+      __syncthreads();
+      sp.e_res = cta_sum_sq(sm.xs, N, sm.red);
+      pstart = hit.p + 1;
+    }
+    for (int k = count + threadIdx.x; k < kmax; k += kThreads) {
+      periods_out[(size_t)b * kmax + k] = 0u;
+      powers_out[(size_t)b * kmax + k] = 0.0;
+    }
+    if (threadIdx.x == 0) {
+      count_out[b] = count;
+      status_out[b] = count > kmax ? PP_STATUS_OVERFLOW : PP_STATUS_OK;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// K4: best-correlation (Periods.py:289-349)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2)
+bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, int max_length, double ratio,
+             int trunc_i, int orth_i, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
+             double* __restrict__ bases_out, int32_t* __restrict__ status_out) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const SmemPlan pl = make_plan(N, max_length, 0, true);
+  Smem sm(smem_raw, pl);
+  const bool trunc = trunc_i != 0, orth = orth_i != 0;
+  const double sqrtN = sqrt((double)N);
+  WindowLoader loader;
+  loader.init(sm.bar);
+  zero_pad(sm.xs, N, pl.xs_len);
+  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+    loader.load(sm.xs, x + (size_t)b * ldx, N);
+    const double og = sqrt(cta_sum_sq(sm.xs, N, sm.red)) / sqrtN;
+    double prev = og;
+    int status = PP_STATUS_OK;
+    SweepParams sp;
+    sp.xs = sm.xs;
+    sp.N = N;
+    sp.pmin = 2;
+    sp.pmax = max_length - 1;  // range(2, max_length) excludes max_length (:324)
+    sp.metric = PP_METRIC_MAXABS;
+    sp.trunc = false;          // the correlation metric always folds all N samples
+    sp.orth = false;
+    sp.chain_off = tb.chain_off;
+    sp.chain_q = tb.chain_q;
+    sp.warp_scr = nullptr;
+    sp.pv = pl.pv;
+    sp.sqrtN = sqrtN;
+    sp.e_res = 0.0;
+    sp.data_norm = 1.0;
+    sp.thresh = -1.0;
+    sp.skip = nullptr;
+    sp.metric_out = nullptr;
+    for (int i = 0; i < num; ++i) {
+      uint32_t out_p = 0u;
+      double out_v = 0.0;
+      bool keep = false;
+      int p_sel = 0;
+      if (status == PP_STATUS_OK) {
+        const SweepResult top = cta_sweep(sp, sm.sweep);
+        if (top.p == 0) {
+          status = PP_STATUS_NO_PERIOD;
+        } else {
+          p_sel = top.p;
+          const int clen = orth ? tb.chain_off[top.p + 1] - tb.chain_off[top.p] : 0;
+          cta_project_exact<false>(sm.xs, 0, N, top.p, trunc, orth ? tb.chain_q + tb.chain_off[top.p] : nullptr, clen,
+                                   sm.vwin, sm.utmp);
+          cta_subtract_tiled(sm.xs, N, sm.vwin, top.p);  // always (:340)
+          __syncthreads();
+          const double now = sqrt(cta_sum_sq(sm.xs, N, sm.red)) / sqrtN;
+          const double drop = (prev - now) / og;
+          if (drop > ratio) {
+            keep = true;
+            out_p = (uint32_t)top.p;
+            out_v = drop;
+            prev = now;
+          }
+        }
+      }
+      if (threadIdx.x == 0) {
+        periods_out[(size_t)b * num + i] = out_p;
+        powers_out[(size_t)b * num + i] = out_v;
+      }
+      if (bases_out) {
+        double* dst = bases_out + ((size_t)b * num + i) * N;
+        if (keep) cta_store_tiled(dst, N, sm.vwin, p_sel);
+        else
+          for (int n = threadIdx.x; n < N; n += kThreads) __stcs(dst + n, 0.0);
+      }
+      __syncthreads();
+    }
+    if (threadIdx.x == 0) status_out[b] = status;
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------
+struct DeviceFacts {
+  int sm_count = 0, smem_optin = 0, major = 0, minor = 0, clock_khz = 0;
+  bool ok = false;
+};
+static int device_facts(DeviceFacts& f) {
+  int dev = 0;
+  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
+  cudaDeviceGetAttribute(&f.sm_count, cudaDevAttrMultiProcessorCount, dev);
+  cudaDeviceGetAttribute(&f.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&f.major, cudaDevAttrComputeCapabilityMajor, dev);
+  cudaDeviceGetAttribute(&f.minor, cudaDevAttrComputeCapabilityMinor, dev);
+  cudaDeviceGetAttribute(&f.clock_khz, cudaDevAttrClockRate, dev);
+  f.ok = true;
+  return 0;
+}
+
+static int plan_for(int algo, int N, int pmax, int num, SmemPlan& pl) {
+  pl = make_plan(N, pmax, algo == PP_ALGO_MBEST ? num : 0, true);
+  return 0;
+}
+
+// persistent grid: CTAs per SM limited by shared memory (<= 2 by registers)
+static int grid_for(const DeviceFacts& f, size_t smem_bytes, int B) {
+  int per_sm = (int)((size_t)(f.smem_optin + 1024) / (smem_bytes + 1024));
+  if (per_sm > 2) per_sm = 2;
+  if (per_sm < 1) per_sm = 1;
+  int g = f.sm_count * per_sm;
+  if (B > 0 && g > B) g = B;
+  return g < 1 ? 1 : g;
+}
+
+template <typename K>
+static int prep_kernel(K kernel, size_t smem_bytes, const DeviceFacts& f) {
+  if (smem_bytes > (size_t)f.smem_optin)
+    return fail(-2, "window (N + pmax) does not fit in shared memory for on-chip staging%s");
+  return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
+                    "cudaFuncSetAttribute");
+}
+
+}  // namespace pp
+
+using namespace pp;
+
+extern "C" {
+
+int pp_abi_version(void) { return PP_ABI_VERSION; }
+const char* pp_last_error(void) { return g_err; }
+
+int pp_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_major, int32_t* cc_minor,
+                   int32_t* clock_khz) {
+  DeviceFacts f;
+  if (int rc = device_facts(f)) return rc;
+  if (sm_count) *sm_count = f.sm_count;
+  if (smem_optin_bytes) *smem_optin_bytes = f.smem_optin;
+  if (cc_major) *cc_major = f.major;
+  if (cc_minor) *cc_minor = f.minor;
+  if (clock_khz) *clock_khz = f.clock_khz;
+  return 0;
+}
+
+int pp_grid_size(int32_t algo, int32_t N, int32_t pmax, int32_t orth) {
+  (void)orth;
+  DeviceFacts f;
+  if (int rc = device_facts(f)) return rc;
+  SmemPlan pl;
+  plan_for(algo, N, pmax, 16, pl);
+  return grid_for(f, pl.bytes(), 0);
+}
+
+size_t pp_workspace_bytes(int32_t algo, int32_t N, int32_t pmax, int32_t num, int32_t orth) {
+  DeviceFacts f;
+  if (device_facts(f)) return 0;
+  SmemPlan pl;
+  plan_for(algo, N, pmax, num, pl);
+  const size_t grid = (size_t)f.sm_count * 2;  // upper bound on the persistent grid
+  size_t bytes = 1024;
+  if (algo == PP_ALGO_MBEST) bytes += grid * (size_t)num * pl.pv * 8;
+  if (orth && algo != PP_ALGO_BCORR) bytes += grid * kWarps * 2 * (size_t)pl.pv * 8;
+  return bytes;
+}
+
+static int check_common(const void* x, int64_t ldx, int B, int N) {
+  if (x == nullptr) return fail(-1, "x is null%s");
+  if (B < 0 || N < 2) return fail(-1, "need B >= 0 and N >= 2%s");
+  if (ldx < 1) return fail(-1, "ldx must be >= 1%s");
+  return 0;
+}
+
+int pp_project(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t p, int32_t trunc,
+               const int32_t* chain_q_host, int32_t chain_len, double* out, int64_t ldo, int32_t out_len,
+               void* stream) {
+  if (int rc = check_common(x, ldx, B, N)) return rc;
+  if (p < 1 || p > N) return fail(-1, "period must satisfy 1 <= p <= N%s");
+  if (chain_len < 0 || chain_len > 16) return fail(-1, "chain_len must be in [0,16]%s");
+  if (out == nullptr || out_len < 1 || out_len > N || ldo < out_len) return fail(-1, "bad output shape%s");
+  if (B == 0) return 0;
+  DeviceFacts f;
+  if (int rc = device_facts(f)) return rc;
+  const SmemPlan pl = make_plan(N, p, 0, false);
+  if (int rc = prep_kernel(project_kernel, pl.bytes(), f)) return rc;
+  ChainArg ca;
+  memset(&ca, 0, sizeof(ca));
+  ca.len = chain_len;
+  for (int i = 0; i < chain_len; ++i) {
+    if (chain_q_host[i] < 1 || chain_q_host[i] >= p || p % chain_q_host[i]) return fail(-1, "chain cofactor must divide p%s");
+    ca.q[i] = chain_q_host[i];
+  }
+  project_kernel<<<grid_for(f, pl.bytes(), B), kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, p, trunc, ca,
+                                                                                            out, ldo, out_len);
+  return check_cuda(cudaGetLastError(), "project_kernel launch");
+}
+
+int pp_periodic_norm(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t p, double* out, void* stream) {
+  if (x == nullptr || out == nullptr || B < 0 || N < 1 || ldx < 1 || p < 0) return fail(-1, "bad arguments%s");
+  if (B == 0) return 0;
+  DeviceFacts f;
+  if (int rc = device_facts(f)) return rc;
+  int grid = f.sm_count * 4;
+  if (grid > B) grid = B;
+  norm_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, ldx, B, N, p, out);
+  return check_cuda(cudaGetLastError(), "norm_kernel launch");
+}
+
+static double* carve(void* ws, size_t ws_bytes, size_t& off, size_t bytes) {
+  off = (off + 255) & ~(size_t)255;
+  if (ws == nullptr || off + bytes > ws_bytes) return nullptr;
+  double* p = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + off);
+  off += bytes;
+  return p;
+}
+
+int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, int32_t pmax, int32_t metric,
+             int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q, int32_t table_pmax,
+             double* metric_out, int32_t* best_p, double* best_val, void* workspace, size_t workspace_bytes,
+             void* stream) {
+  if (int rc = check_common(x, ldx, B, N)) return rc;
+  if (pmin < 1 || pmax < pmin || pmax > N) return fail(-1, "need 1 <= pmin <= pmax <= N%s");
+  if (metric < 0 || metric > 3) return fail(-1, "unknown metric%s");
+  if (metric == PP_METRIC_MAXABS && (trunc || orth)) return fail(-1, "MAXABS ignores trunc/orth; pass 0%s");
+  if (orth && (chain_off == nullptr || chain_q == nullptr || table_pmax < pmax)) return fail(-1, "orth needs tables covering pmax%s");
+  if (best_p == nullptr || best_val == nullptr) return fail(-1, "best_p/best_val are null%s");
+  if (B == 0) return 0;
+  DeviceFacts f;
+  if (int rc = device_facts(f)) return rc;
+  const SmemPlan pl = make_plan(N, pmax, 0, true);
+  if (int rc = prep_kernel(sweep_kernel, pl.bytes(), f)) return rc;
+  const int grid = grid_for(f, pl.bytes(), B);
+  size_t off = 0;
+  double* scr = nullptr;
+  if (orth) {
+    scr = carve(workspace, workspace_bytes, off, (size_t)grid * kWarps * 2 * pl.pv * 8);
+    if (!scr) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
+  }
+  Tables tb{chain_off, chain_q, nullptr, nullptr};
+  sweep_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, pmin, pmax, metric, trunc, orth, tb,
+                                                                     metric_out, best_p, best_val, scr);
+  return check_cuda(cudaGetLastError(), "sweep_kernel launch");
+}
+
+int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, int32_t pmin, int32_t pmax,
+             int32_t gamma, int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q,
+             const int32_t* fac_off, const int32_t* fac, int32_t table_pmax, uint32_t* periods, double* powers,
+             double* bases, int32_t* sweeps, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_common(x, ldx, B, N)) return rc;
+  if (num < 1 || num > 4096) return fail(-1, "need 1 <= num <= 4096%s");
+  if (pmin < 2 || pmax < pmin || pmax > N) return fail(-1, "need 2 <= pmin <= pmax <= N%s");
+  if (pmax - pmin + 1 < num) return fail(-1, "fewer candidate periods than num%s");
+  if (fac_off == nullptr || fac == nullptr || table_pmax < pmax) return fail(-1, "factor tables must cover pmax%s");
+  if (orth && (chain_off == nullptr || chain_q == nullptr)) return fail(-1, "orth needs chain tables%s");
+  if (!periods || !powers || !status) return fail(-1, "output pointers are null%s");
+  if (B == 0) return 0;
+  DeviceFacts f;
+  if (int rc = device_facts(f)) return rc;
+  const SmemPlan pl = make_plan(N, pmax, num, true);
+  if (int rc = prep_kernel(mbest_kernel, pl.bytes(), f)) return rc;
+  const int grid = grid_for(f, pl.bytes(), B);
+  size_t off = 0;
+  double* slots = carve(workspace, workspace_bytes, off, (size_t)grid * num * pl.pv * 8);
+  double* scr = orth ? carve(workspace, workspace_bytes, off, (size_t)grid * kWarps * 2 * pl.pv * 8) : nullptr;
+  if (!slots || (orth && !scr)) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
+  Tables tb{chain_off, chain_q, fac_off, fac};
+  mbest_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,
+                                                                     tb, periods, powers, bases, sweeps, status, slots,
+                                                                     scr);
+  return check_cuda(cudaGetLastError(), "mbest_kernel launch");
+}
+
+int pp_small_to_large(const double* x, int64_t ldx, int32_t B, int32_t N, double thresh, int32_t n_periods,
+                      int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q,
+                      int32_t table_pmax, int32_t kmax, uint32_t* periods, double* powers, double* bases,
+                      int32_t* count, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  if (int rc = check_common(x, ldx, B, N)) return rc;
+  if (!(thresh >= 0.0)) return fail(-1, "thresh must be >= 0%s");
+  if (n_periods < 2 || n_periods > N) return fail(-1, "need 2 <= n_periods <= N%s");
+  if (kmax < 1) return fail(-1, "kmax must be >= 1%s");
+  if (orth && (chain_off == nullptr || chain_q == nullptr || table_pmax < n_periods)) return fail(-1, "orth needs tables covering n_periods%s");
+  if (!periods || !powers || !count || !status) return fail(-1, "output pointers are null%s");
+  if (B == 0) return 0;
+  DeviceFacts f;
+  if (int rc = device_facts(f)) return rc;
+  const SmemPlan pl = make_plan(N, n_periods, 0, true);
+  if (int rc = prep_kernel(s2l_kernel, pl.bytes(), f)) return rc;
+  const int grid = grid_for(f, pl.bytes(), B);
+  size_t off = 0;
+  double* scr = nullptr;
+  if (orth) {
+    scr = carve(workspace, workspace_bytes, off, (size_t)grid * kWarps * 2 * pl.pv * 8);
+    if (!scr) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
+  }
+  Tables tb{chain_off, chain_q, nullptr, nullptr};
+  s2l_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, thresh, n_periods, trunc, orth, tb,
+                                                                   kmax, periods, powers, bases, count, status, scr);
+  return check_cuda(cudaGetLastError(), "s2l_kernel launch");
+}
+
+int pp_best_correlation(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, int32_t max_length,
+                        double ratio, int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q,
+                        int32_t table_pmax, uint32_t* periods, double* powers, double* bases, int32_t* status,
+                        void* workspace, size_t workspace_bytes, void* stream) {
+  (void)workspace;
+  (void)workspace_bytes;
+  if (int rc = check_common(x, ldx, B, N)) return rc;
+  if (num < 1) return fail(-1, "num must be >= 1%s");
+  if (max_length < 3 || max_length > N + 1) return fail(-1, "need 3 <= max_length <= N+1%s");
+  if (orth && (chain_off == nullptr || chain_q == nullptr || table_pmax < max_length - 1)) return fail(-1, "orth needs tables covering max_length%s");
+  if (!periods || !powers || !status) return fail(-1, "output pointers are null%s");
+  if (B == 0) return 0;
+  DeviceFacts f;
+  if (int rc = device_facts(f)) return rc;
+  const SmemPlan pl = make_plan(N, max_length, 0, true);
+  if (int rc = prep_kernel(bcorr_kernel, pl.bytes(), f)) return rc;
+  const int grid = grid_for(f, pl.bytes(), B);
+  Tables tb{chain_off, chain_q, nullptr, nullptr};
+  bcorr_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, max_length, ratio, trunc, orth,
+                                                                     tb, periods, powers, bases, status);
+  return check_cuda(cudaGetLastError(), "bcorr_kernel launch");
+}
+
+}  // extern "C"

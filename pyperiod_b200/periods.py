@@ -1,0 +1,319 @@
+"""`Periods` -- drop-in for pyPeriod.Periods (pyPeriod/Periods.py:90-644) on the B200.
+
+Both call shapes of the reference are accepted:
+  README form   Periods(x, trunc_to_integer_multiple=False, orthogonalize=False); p.m_best(num=10)
+  HEAD form     Periods(trunc_to_integer_multiple=False, orthogonalize=False);   p.m_best(x, num=10)
+and every method also takes a (B, N) batch of windows.  All arithmetic runs in the CUDA
+library (csrc/, through include/pyperiod_b200.h); this file only stages buffers, builds the
+integer side tables and shapes the results like the reference does.
+
+1-D input  -> exactly the reference's return types (numpy uint32/float64 arrays; Python
+              lists for small_to_large).
+(B, N) input -> BatchResult (unpacks as `periods, powers, bases`), bases only when
+              return_bases=True (they are 8*num*N bytes per window).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass
+from warnings import warn
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._device import Windows, Workspace, ptr, stage_windows, stream_ptr, to_host
+from .tables import get_tables, orth_chain
+
+
+@dataclass
+class BatchResult:
+    """Result of a batched call.  Arrays are numpy for host input, torch (device) otherwise."""
+    periods: object          # (B, K) uint32
+    powers: object           # (B, K) float64
+    bases: object            # (B, K, N) float64 or None
+    status: object           # (B,) int32, _lib.STATUS_*
+    count: object = None     # (B,) int32 -- small_to_large only: periods accepted
+    sweeps: object = None    # (B,) int32 -- M-best only: step-1 sweeps executed
+
+    def __iter__(self):
+        yield self.periods
+        yield self.powers
+        yield self.bases
+
+    def window(self, b: int):
+        """Per-window result in the reference's own form."""
+        k = int(self.count[b]) if self.count is not None else self.periods.shape[1]
+        per, pw = self.periods[b, :k], self.powers[b, :k]
+        bs = None if self.bases is None else self.bases[b, :k]
+        if self.count is not None:  # small_to_large returns lists (Periods.py:266-268)
+            return (list(map(int, per)), list(map(float, pw)), None if bs is None else [r for r in bs])
+        return per, pw, bs
+
+
+def _is_data(obj) -> bool:
+    if isinstance(obj, (bool, np.bool_)) or obj is None:
+        return False
+    if isinstance(obj, torch.Tensor):
+        return obj.dim() >= 1
+    return isinstance(obj, (np.ndarray, list, tuple)) and np.ndim(obj) >= 1
+
+
+def _u32(t: torch.Tensor):
+    return t.view(torch.uint32) if hasattr(torch, "uint32") else t
+
+
+def _export(w: Windows, t, as_u32=False):
+    if t is None:
+        return None
+    if w.from_host:
+        a = to_host(t)
+        return a.view(np.uint32) if as_u32 else a
+    return _u32(t) if as_u32 else t
+
+
+class Periods:
+    """Sethares-Staley periodicity transforms, B200-native.  See module docstring."""
+
+    def __init__(self, *args, trunc_to_integer_multiple=None, orthogonalize=None, device=None):
+        args = list(args)
+        self._data = None
+        if args and _is_data(args[0]):
+            self._data = args.pop(0)                      # README form (README.md:71)
+        if len(args) > 2:
+            raise TypeError("Periods([data,] trunc_to_integer_multiple=False, orthogonalize=False)")
+        trunc = args[0] if len(args) >= 1 else False
+        orth = args[1] if len(args) >= 2 else False
+        if trunc_to_integer_multiple is not None:
+            trunc = trunc_to_integer_multiple
+        if orthogonalize is not None:
+            orth = orthogonalize
+        self._trunc_to_integer_multiple = bool(trunc)
+        self._orthogonalize = bool(orth)
+        self._device = device
+        _lib.load()  # fail loudly now if the CUDA library is missing
+
+    # ------------------------------------------------------------------ argument plumbing
+    def _split(self, args, names):
+        """Peel an optional leading `data` argument off *args (HEAD form) else use the bound data."""
+        args = list(args)
+        if args and _is_data(args[0]):
+            data = args.pop(0)
+        elif self._data is not None:
+            data = self._data
+        else:
+            raise TypeError("no data: pass it to the method or to Periods(data)")
+        if len(args) > len(names):
+            raise TypeError("too many positional arguments")
+        return data, dict(zip(names, args))
+
+    # ------------------------------------------------------------------ static operators
+    @staticmethod
+    def project(data, p=2, trunc_to_integer_multiple=False, orthogonalize=False, return_single_period=False,
+                device=None):
+        """Projection onto the p-periodic subspace (Periods.py:142-219); bit-exact with the reference.
+
+        1-D -> (N,) (or (p,) with return_single_period); (B, N) -> (B, N) / (B, p).
+        """
+        lib = _lib.load()
+        w = stage_windows(data, device)
+        p = int(p)
+        if not 1 <= p <= w.n:
+            raise ValueError("need 1 <= p <= len(data)")
+        chain = np.asarray(orth_chain(p) if orthogonalize else [], dtype=np.int32)
+        out_len = p if return_single_period else w.n
+        out = torch.empty((w.b, out_len), dtype=torch.float64, device=w.device)
+        _lib.check(lib.pp_project(ptr(w.tensor), w.ldx, w.b, w.n, p, int(bool(trunc_to_integer_multiple)),
+                                  chain.ctypes.data_as(C.c_void_p), len(chain), ptr(out), out_len, out_len,
+                                  stream_ptr(w.device)), "pp_project")
+        res = _export(w, out)
+        return res[0] if w.was_1d else res
+
+    @staticmethod
+    def periodic_norm(x, p=None, device=None):
+        """||x|| / sqrt(len) [/ sqrt(p)] (Periods.py:221-241).  1-D -> float, (B, N) -> (B,)."""
+        lib = _lib.load()
+        w = stage_windows(x, device)
+        out = torch.empty((w.b,), dtype=torch.float64, device=w.device)
+        _lib.check(lib.pp_periodic_norm(ptr(w.tensor), w.ldx, w.b, w.n, int(p) if p else 0, ptr(out),
+                                        stream_ptr(w.device)), "pp_periodic_norm")
+        res = _export(w, out)
+        return float(res[0]) if w.was_1d else res
+
+    # ------------------------------------------------------------------ one sweep (parity probe)
+    def sweep(self, *args, **kw):
+        """Metric of every candidate period for each window: returns (metrics[B, pmax+1], best_p[B], best_val[B]).
+
+        metric in {"norm", "gamma", "maxabs", "imposed"}.  Not part of the reference API; it exposes
+        the inner loop of Periods.py:501-515 / 324-331 for parity tests and profiling.
+        """
+        data, pos = self._split(args, ["metric", "min_length", "max_length"])
+        kw = {**pos, **kw}
+        metric = {"norm": 0, "gamma": 1, "maxabs": 2, "imposed": 3}[kw.get("metric", "norm")]
+        lib = _lib.load()
+        w = stage_windows(data, self._device)
+        pmin = int(kw.get("min_length", 2))
+        pmax = kw.get("max_length")
+        pmax = math.floor(w.n / 3) if pmax is None else int(pmax)
+        trunc = self._trunc_to_integer_multiple and metric != 2
+        orth = self._orthogonalize and metric != 2
+        tb = get_tables(pmax)
+        co, cq, _, _ = tb.device(w.device)
+        ws_bytes = lib.pp_workspace_bytes(_lib.ALGO_SWEEP, w.n, pmax, 0, int(orth))
+        ws = Workspace.get(w.device, ws_bytes)
+        metrics = torch.zeros((w.b, pmax + 1), dtype=torch.float64, device=w.device)
+        best_p = torch.empty((w.b,), dtype=torch.int32, device=w.device)
+        best_v = torch.empty((w.b,), dtype=torch.float64, device=w.device)
+        _lib.check(lib.pp_sweep(ptr(w.tensor), w.ldx, w.b, w.n, pmin, pmax, metric, int(trunc), int(orth),
+                                ptr(co), ptr(cq), tb.pmax, ptr(metrics), ptr(best_p), ptr(best_v), ptr(ws),
+                                ws.numel(), stream_ptr(w.device)), "pp_sweep")
+        return _export(w, metrics), _export(w, best_p), _export(w, best_v)
+
+    # ------------------------------------------------------------------ M-best family
+    def m_best(self, *args, **kw):
+        """M-best (Periods.py:408-430).  m_best([data,] num=5, max_length=None, min_length=2)."""
+        return self._m_best_meta(False, args, kw)
+
+    def m_best_gamma(self, *args, **kw):
+        """M-best gamma (Periods.py:432-454)."""
+        return self._m_best_meta(True, args, kw)
+
+    def _m_best_meta(self, gamma, args, kw):
+        data, pos = self._split(args, ["num", "max_length", "min_length"])
+        kw = {**pos, **kw}
+        return_bases = kw.pop("return_bases", None)
+        num = int(kw.pop("num", 5))
+        max_length = kw.pop("max_length", None)
+        min_length = int(kw.pop("min_length", 2))
+        if kw:
+            raise TypeError(f"unexpected arguments {sorted(kw)}")
+        if self._orthogonalize:
+            warn("`Orthogonalize = True` has no effect in M-best.")  # Periods.py:482-483 (HEAD still applies it)
+        lib = _lib.load()
+        w = stage_windows(data, self._device)
+        if return_bases is None:
+            return_bases = w.was_1d
+        pmax = math.floor(w.n / 3) if max_length is None else int(max_length)
+        tb = get_tables(pmax)
+        co, cq, fo, fc = tb.device(w.device)
+        orth = int(self._orthogonalize)
+        ws_bytes = lib.pp_workspace_bytes(_lib.ALGO_MBEST, w.n, pmax, num, orth)
+        ws = Workspace.get(w.device, ws_bytes)
+        periods = torch.empty((w.b, num), dtype=torch.int32, device=w.device)
+        powers = torch.empty((w.b, num), dtype=torch.float64, device=w.device)
+        bases = torch.empty((w.b, num, w.n), dtype=torch.float64, device=w.device) if return_bases else None
+        sweeps = torch.empty((w.b,), dtype=torch.int32, device=w.device)
+        status = torch.empty((w.b,), dtype=torch.int32, device=w.device)
+        _lib.check(lib.pp_mbest(ptr(w.tensor), w.ldx, w.b, w.n, num, min_length, pmax, int(gamma),
+                                int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq), ptr(fo), ptr(fc),
+                                tb.pmax, ptr(periods), ptr(powers), ptr(bases), ptr(sweeps), ptr(status), ptr(ws),
+                                ws.numel(), stream_ptr(w.device)), "pp_mbest")
+        res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases), _export(w, status),
+                          sweeps=_export(w, sweeps))
+        if w.was_1d:
+            if int(res.status[0]) == _lib.STATUS_NO_PERIOD:
+                # the reference dies on `bases[i] = None` when no period has a positive norm
+                raise TypeError("no period with a positive norm (all-zero input?)")
+            return res.periods[0], res.powers[0], (None if res.bases is None else res.bases[0])
+        return res
+
+    # ------------------------------------------------------------------ small-to-large
+    def small_to_large(self, *args, **kw):
+        """Small-to-large (Periods.py:246-287).  small_to_large([data,] thresh=0.1, n_periods=None).
+
+        Batch extras: kmax (capacity per window, default 32), return_bases.
+        """
+        data, pos = self._split(args, ["thresh", "n_periods"])
+        kw = {**pos, **kw}
+        thresh = float(kw.pop("thresh", 0.1))
+        n_periods = kw.pop("n_periods", None)
+        kmax = int(kw.pop("kmax", 32))
+        return_bases = kw.pop("return_bases", None)
+        if kw:
+            raise TypeError(f"unexpected arguments {sorted(kw)}")
+        lib = _lib.load()
+        w = stage_windows(data, self._device)
+        if return_bases is None:
+            return_bases = w.was_1d
+        n_periods = math.floor(w.n / 2) if n_periods is None else int(n_periods)
+        tb = get_tables(n_periods)
+        co, cq, _, _ = tb.device(w.device)
+        orth = int(self._orthogonalize)
+        ws = Workspace.get(w.device, lib.pp_workspace_bytes(_lib.ALGO_S2L, w.n, n_periods, 0, orth))
+        while True:
+            periods = torch.empty((w.b, kmax), dtype=torch.int32, device=w.device)
+            powers = torch.empty((w.b, kmax), dtype=torch.float64, device=w.device)
+            bases = torch.empty((w.b, kmax, w.n), dtype=torch.float64, device=w.device) if return_bases else None
+            count = torch.empty((w.b,), dtype=torch.int32, device=w.device)
+            status = torch.empty((w.b,), dtype=torch.int32, device=w.device)
+            _lib.check(lib.pp_small_to_large(ptr(w.tensor), w.ldx, w.b, w.n, thresh, n_periods,
+                                             int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq), tb.pmax,
+                                             kmax, ptr(periods), ptr(powers), ptr(bases), ptr(count), ptr(status),
+                                             ptr(ws), ws.numel(), stream_ptr(w.device)), "pp_small_to_large")
+            need = int(count.max()) if w.b else 0
+            if need <= kmax or not w.was_1d:
+                break
+            kmax = need  # 1-D drop-in: rerun with enough room so nothing is truncated
+        res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases), _export(w, status),
+                          count=_export(w, count))
+        return res.window(0) if w.was_1d else res
+
+    # ------------------------------------------------------------------ best correlation
+    def best_correlation(self, *args, **kw):
+        """Best-correlation (Periods.py:289-349).  best_correlation([data,] num=5, max_length=None, ratio=0.01)."""
+        data, pos = self._split(args, ["num", "max_length", "ratio"])
+        kw = {**pos, **kw}
+        num = int(kw.pop("num", 5))
+        max_length = kw.pop("max_length", None)
+        ratio = float(kw.pop("ratio", 0.01))
+        return_bases = kw.pop("return_bases", None)
+        if kw:
+            raise TypeError(f"unexpected arguments {sorted(kw)}")
+        lib = _lib.load()
+        w = stage_windows(data, self._device)
+        if return_bases is None:
+            return_bases = w.was_1d
+        max_length = math.floor(w.n / 3) if max_length is None else int(max_length)
+        tb = get_tables(max_length)
+        co, cq, _, _ = tb.device(w.device)
+        periods = torch.empty((w.b, num), dtype=torch.int32, device=w.device)
+        powers = torch.empty((w.b, num), dtype=torch.float64, device=w.device)
+        bases = torch.empty((w.b, num, w.n), dtype=torch.float64, device=w.device) if return_bases else None
+        status = torch.empty((w.b,), dtype=torch.int32, device=w.device)
+        _lib.check(lib.pp_best_correlation(ptr(w.tensor), w.ldx, w.b, w.n, num, max_length, ratio,
+                                           int(self._trunc_to_integer_multiple), int(self._orthogonalize), ptr(co),
+                                           ptr(cq), tb.pmax, ptr(periods), ptr(powers), ptr(bases), ptr(status),
+                                           C.c_void_p(0), 0, stream_ptr(w.device)), "pp_best_correlation")
+        res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases), _export(w, status))
+        if w.was_1d:
+            if int(res.status[0]) == _lib.STATUS_NO_PERIOD:
+                raise TypeError("no period with a non-zero correlation (all-zero input?)")
+            return res.periods[0], res.powers[0], (None if res.bases is None else res.bases[0])
+        return res
+
+    # ------------------------------------------------------------------ properties (Periods.py:606-644)
+    @property
+    def trunc_to_integer_multiple(self):
+        # the reference's getter returns BOTH flags as a tuple (Periods.py:610-611); kept for fidelity
+        return self._trunc_to_integer_multiple, self._orthogonalize
+
+    @trunc_to_integer_multiple.setter
+    def trunc_to_integer_multiple(self, value):
+        self._trunc_to_integer_multiple, self._orthogonalize = value
+
+    @property
+    def orthogonalize(self):
+        return self._orthogonalize
+
+    @orthogonalize.setter
+    def orthogonalize(self, value):
+        self._orthogonalize = value
+
+    @property
+    def window(self):
+        return self._window
+
+    @window.setter
+    def window(self, value):
+        self._window = value

@@ -1,0 +1,258 @@
+"""GPU parity tests for the `Periods` path: CUDA (through the C ABI) vs the oracle and vs the
+golden fixtures generated from the reference.  Run with `-m gpu` on a B200.
+
+Bars: project() bit-exact; period lists exact; powers/bases <= 1e-10 relative (they are in fact
+bit-exact for bases in the non-trivial cases below, which is asserted where it holds by design).
+"""
+import warnings
+
+import numpy as np
+import pytest
+
+from conftest import load_golden, sha
+from oracle import periods as op
+from pyperiod_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10  # north-star tolerance for powers and bases (fp64 path)
+
+
+@pytest.fixture(scope="module")
+def P():
+    from pyperiod_b200 import Periods
+    return Periods
+
+
+def _native_loaded():
+    with open("/proc/self/maps") as fh:
+        return "libpyperiod_b200.so" in fh.read()
+
+
+def test_native_library_is_what_runs(P):
+    P.project(synth.synth(256, 1), 7)
+    assert _native_loaded()
+
+
+# ---------------------------------------------------------------- project: bit-exact
+def test_project_kats(P):
+    assert np.array_equal(P.project(np.arange(10.0), 3), [4.5, 4, 5, 4.5, 4, 5, 4.5, 4, 5, 4.5])
+    assert np.array_equal(P.project(np.arange(10.0), 3, True), [3, 4, 5, 3, 4, 5, 3, 4, 5, 3])
+    assert np.array_equal(P.project(np.arange(12.0), 4, False, True), [-1, -1, 1, 1] * 3)
+    assert np.array_equal(P.project(np.arange(12.0), 4, False, True, True), [-1, -1, 1, 1])
+
+
+def test_project_golden_bit_exact(P):
+    g = load_golden("project")
+    cache = {}
+    for key in g["cases"]:
+        n, seed, p, mode = str(key).split("_")
+        n, seed, p = int(n), int(seed), int(p)
+        x = cache.setdefault((n, seed), synth.synth(n, seed))
+        y = P.project(x, p, mode[0] == "1", mode[1] == "1")
+        assert sha(y) == str(g["sha_" + str(key)]), key
+
+
+def test_project_all_periods_vs_oracle(P):
+    x = synth.synth(1000, 77)
+    for p in range(2, 501):
+        for trunc, orth in ((False, False), (True, False), (False, True), (True, True)):
+            got = P.project(x, p, trunc, orth)
+            assert np.array_equal(got, op.project(x, p, trunc, orth)), (p, trunc, orth)
+
+
+def test_project_batch_and_ragged_lengths(P):
+    for n in (257, 1000, 4095, 4096):
+        xb = synth.synth_batch(5, n, 900)
+        for p, trunc, orth in ((3, False, False), (30, True, True), (n // 2, False, True), (n, False, False)):
+            got = P.project(xb, p, trunc, orth)
+            for b in range(5):
+                assert np.array_equal(got[b], op.project(xb[b], p, trunc, orth)), (n, p, b)
+    one = P.project(synth.synth(300, 5), 12, True, True, True)
+    assert one.shape == (12,)
+
+
+def test_project_idempotent_and_periodic(P):
+    x = synth.synth(4096, 11)
+    for p in (5, 64, 1000):
+        y = P.project(x, p)
+        assert np.array_equal(y[: 4096 - p], y[p:])           # p-periodic
+        assert np.allclose(P.project(y, p), y, rtol=0, atol=1e-15)  # idempotent
+
+
+def test_periodic_norm(P):
+    x = synth.synth(2000, 3)
+    assert abs(P.periodic_norm(x) - op.periodic_norm(x)) <= 1e-15
+    assert abs(P.periodic_norm(x, 7) - op.periodic_norm(x, 7)) <= 1e-15
+
+
+# ---------------------------------------------------------------- sweep: energies and argmax
+@pytest.mark.parametrize("trunc,orth", [(False, False), (True, False), (False, True), (True, True)])
+def test_sweep_metrics_vs_oracle(P, trunc, orth):
+    x = synth.synth(2000, 21)
+    pmax = 666
+    for metric in ("norm", "gamma"):
+        m, bp, bv = P(trunc, orth).sweep(x[None, :], metric=metric, max_length=pmax)
+        want = np.zeros(pmax + 1)
+        for p in range(2, pmax + 1):
+            base = op.project(x, p, trunc, orth)
+            want[p] = op.periodic_norm(base, p) if metric == "gamma" else op.periodic_norm(base)
+        np.testing.assert_allclose(m[0, 2:], want[2:], rtol=1e-12, atol=1e-15)
+        assert int(bp[0]) == int(np.argmax(want))
+    # imposed norm (small-to-large metric)
+    m, _, _ = P(trunc, orth).sweep(x[None, :], metric="imposed", max_length=pmax)
+    ref = op.periodic_norm(x)
+    for p in (2, 3, 58, 59, 100, 333, 666):
+        base = op.project(x, p, trunc, orth)
+        want_p = (op.periodic_norm(x) - op.periodic_norm(x - base)) / ref
+        assert abs(m[0, p] - want_p) <= 1e-13, p
+
+
+def test_sweep_maxabs_bit_exact(P):
+    x = synth.synth(2048, 40_000)
+    m, bp, bv = P().sweep(x[None, :], metric="maxabs", max_length=681)
+    want = np.array([0, 0] + [op.fold_abs_max(x, p) for p in range(2, 682)])
+    assert np.array_equal(m[0, 2:], want[2:])
+    assert int(bp[0]) == int(np.argmax(want)) and bv[0] == want.max()
+
+
+# ---------------------------------------------------------------- config 1: README signal
+@pytest.mark.parametrize("tag", ["00", "11"])
+def test_readme_algorithms_vs_golden(P, tag):
+    g = load_golden("readme")
+    c = synth.readme_signal(0)
+    trunc, orth = tag[0] == "1", tag[1] == "1"
+    inst = P(c, trunc, orth)  # README call shape
+    per, pw, bs = inst.small_to_large(thresh=0.1)
+    assert per == g[f"s2l_{tag}_periods"].tolist()
+    np.testing.assert_allclose(pw, g[f"s2l_{tag}_powers"], rtol=RTOL)
+    np.testing.assert_allclose(np.array(bs), g[f"s2l_{tag}_bases"], rtol=RTOL, atol=1e-14)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for name, fn in (("mbest", inst.m_best), ("gamma", inst.m_best_gamma)):
+            per, pw, bs = fn(num=10)
+            assert per.dtype == np.uint32 and np.array_equal(per, g[f"{name}_{tag}_periods"]), name
+            np.testing.assert_allclose(pw, g[f"{name}_{tag}_powers"], rtol=RTOL)
+            np.testing.assert_allclose(bs, g[f"{name}_{tag}_bases"], rtol=RTOL, atol=1e-14)
+    per, pw, bs = inst.best_correlation(num=3)
+    assert np.array_equal(per, g[f"bcorr_{tag}_periods"])
+    np.testing.assert_allclose(pw, g[f"bcorr_{tag}_powers"], rtol=RTOL, atol=1e-15)
+    np.testing.assert_allclose(bs, g[f"bcorr_{tag}_bases"], rtol=RTOL, atol=1e-14)
+
+
+def test_readme_bases_bit_exact_nonorth(P):
+    g = load_golden("readme")
+    c = synth.readme_signal(0)
+    per, pw, bs = P().m_best(c, num=10)  # HEAD call shape
+    assert np.array_equal(bs, g["mbest_00_bases"])
+    per, pw, bs = P().best_correlation(c, num=3)
+    assert np.array_equal(bs, g["bcorr_00_bases"])
+    per, pw, bs = P().small_to_large(c, 0.1)
+    assert np.array_equal(np.array(bs), g["s2l_00_bases"])
+
+
+# ---------------------------------------------------------------- config 3: stream windows, N=4096
+def test_mbest_stream_windows_vs_golden(P):
+    g = load_golden("mbest_stream")
+    stream = synth.synth_stream(n_windows=128 * 3 + 1)
+    win = synth.windows_from_stream(stream)        # overlapping strided view, uploaded once
+    inst = P()
+    for name, fn in (("mbest", inst.m_best), ("gamma", inst.m_best_gamma)):
+        res = fn(win, num=10, max_length=1024, return_bases=True)
+        assert res.status.max() == 0
+        for b in (0, 128, 300):
+            assert np.array_equal(res.periods[b], g[f"{name}_{b}_periods"]), (name, b)
+            np.testing.assert_allclose(res.powers[b], g[f"{name}_{b}_powers"], rtol=RTOL)
+            assert sha(res.bases[b]) == str(g[f"{name}_{b}_bases_sha"]), (name, b)
+        assert res.sweeps.min() >= 10
+
+
+def test_mbest_batch_vs_oracle_and_loop(P):
+    xb = synth.synth_batch(6, 2048, 5000)
+    inst = P()
+    for gamma in (False, True):
+        fn = inst.m_best_gamma if gamma else inst.m_best
+        res = fn(xb, num=8, max_length=600, return_bases=True)
+        for b in range(6):
+            st = {}
+            per, pw, bs = op.m_best_meta(xb[b], gamma, 8, 600, 2, stats=st)
+            assert np.array_equal(res.periods[b], per), (gamma, b)
+            np.testing.assert_allclose(res.powers[b], pw, rtol=RTOL)
+            np.testing.assert_allclose(res.bases[b], bs, rtol=RTOL, atol=1e-14)
+            assert int(res.sweeps[b]) == st["sweeps"]
+            one = fn(xb[b], num=8, max_length=600)               # (N,) call == row of the batch
+            assert np.array_equal(one[0], res.periods[b]) and np.array_equal(one[1], res.powers[b])
+            assert np.array_equal(one[2], res.bases[b])
+
+
+def test_mbest_trunc_modes_vs_oracle(P):
+    x = synth.synth(2000, 6001)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for trunc, orth in ((True, False), (True, True), (False, True)):
+            for gamma in (False, True):
+                fn = P(trunc, orth).m_best_gamma if gamma else P(trunc, orth).m_best
+                per, pw, bs = fn(x, num=6, max_length=400)
+                per0, pw0, bs0 = op.m_best_meta(x, gamma, 6, 400, 2, trunc, orth)
+                assert np.array_equal(per, per0), (trunc, orth, gamma)
+                np.testing.assert_allclose(pw, pw0, rtol=RTOL)
+                np.testing.assert_allclose(bs, bs0, rtol=RTOL, atol=1e-14)
+
+
+def test_mbest_zero_input_raises(P):
+    with pytest.raises(TypeError):
+        P().m_best(np.zeros(512), num=3)
+    res = P().m_best(np.zeros((2, 512)), num=3)
+    assert res.status.tolist() == [1, 1]
+
+
+# ---------------------------------------------------------------- config 2: small-to-large
+def test_s2l_vs_golden(P):
+    g = load_golden("s2l_2048")
+    xb = synth.synth_batch(4, 2048, 20_000)
+    for tag in ("00", "10", "11"):
+        res = P(tag[0] == "1", tag[1] == "1").small_to_large(xb, thresh=0.1, return_bases=True)
+        for b in range(4):
+            per, pw, bs = res.window(b)
+            assert per == g[f"s2l_{b}_{tag}_periods"].tolist(), (tag, b)
+            np.testing.assert_allclose(pw, g[f"s2l_{b}_{tag}_powers"], rtol=RTOL)
+            if tag == "00":
+                assert sha(np.array(bs)) == str(g[f"s2l_{b}_{tag}_bases_sha"])
+
+
+def test_s2l_kmax_overflow_and_rerun(P):
+    x = synth.synth(1024, 31)
+    per, pw, bs = P().small_to_large(x, thresh=0.001, kmax=2)   # 1-D: reruns with enough room
+    per0, pw0, _ = op.small_to_large(x, 0.001)
+    assert per == per0 and len(per) > 2
+    res = P().small_to_large(x[None, :].repeat(2, 0), thresh=0.001, kmax=2)
+    assert res.status.tolist() == [2, 2] and res.count.tolist() == [len(per0)] * 2
+    assert res.periods[0].tolist() == per0[:2]
+
+
+# ---------------------------------------------------------------- config 4: best correlation
+def test_bcorr_vs_golden(P):
+    g = load_golden("bcorr")
+    xb = synth.synth_batch(3, 2048, 40_000)
+    for tag in ("00", "11"):
+        res = P(tag[0] == "1", tag[1] == "1").best_correlation(xb, num=5, return_bases=True)
+        for b in range(3):
+            assert np.array_equal(res.periods[b], g[f"n2048_{b}_{tag}_periods"]), (tag, b)
+            np.testing.assert_allclose(res.powers[b], g[f"n2048_{b}_{tag}_powers"], rtol=RTOL, atol=1e-15)
+            assert sha(res.bases[b]) == str(g[f"n2048_{b}_{tag}_bases_sha"]), (tag, b)
+    x = synth.synth(8192, 40_000)
+    per, pw, bs = P(True, True).best_correlation(x, num=2)
+    assert np.array_equal(per, g["n8192_0_11_periods"])
+    np.testing.assert_allclose(pw, g["n8192_0_11_powers"], rtol=RTOL)
+    assert sha(bs) == str(g["n8192_0_11_bases_sha"])
+
+
+# ---------------------------------------------------------------- device-resident input / output
+def test_device_tensor_io(P):
+    import torch
+    x = torch.from_numpy(synth.synth_batch(3, 1024, 7)).cuda()
+    res = P().m_best(x, num=4, max_length=300)
+    assert res.periods.is_cuda and res.bases is None
+    host = P().m_best(x.cpu().numpy(), num=4, max_length=300)
+    assert np.array_equal(res.periods.cpu().numpy().view(np.uint32), host.periods)
+    assert np.array_equal(res.powers.cpu().numpy(), host.powers)

@@ -1,0 +1,89 @@
+"""CPU-only checks of the host side: the C-ABI library loads and exports every declared symbol,
+the integer side tables agree with the oracle's, and the product never falls back to a CPU path."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib_path():
+    from pyperiod_b200 import build
+    return build.build()
+
+
+def test_library_exports_every_declared_symbol(lib_path):
+    header = open(os.path.join(ROOT, "include", "pyperiod_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(pp_[a-z_0-9]+)\s*\(", header))
+    assert len(declared) >= 10
+    lib = ctypes.CDLL(lib_path)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/pyperiod_b200.h but not exported"
+    from pyperiod_b200 import _lib
+    assert set(_lib.SIGNATURES) == declared
+    assert _lib.load().pp_abi_version() == _lib.ABI_VERSION
+
+
+def test_argument_errors_do_not_need_a_gpu(lib_path):
+    from pyperiod_b200 import _lib
+    lib = _lib.load()
+    rc = lib.pp_project(None, 8, 1, 8, 2, 0, None, 0, None, 8, 8, None)
+    assert rc == -1 and b"null" in lib.pp_last_error()
+    rc = lib.pp_periodic_norm(None, 1, 1, 1, 0, None, None)
+    assert rc == -1
+
+
+def test_tables_match_oracle_set_order():
+    from oracle import numtheory
+    from pyperiod_b200 import tables
+    tb = tables.get_tables(1024)
+    assert tb.pmax >= 1024
+    for p in list(range(2, 400)) + [840, 1000, 1024]:
+        assert tb.factors_of(p).tolist() == numtheory.factors_in_set_order(p)
+        assert tb.chain_of(p).tolist() == numtheory.orth_chain(p) == tables.orth_chain(p)
+    assert tb.factors_of(33).tolist() == [11, 3]
+    assert tb.chain_of(97).tolist() == []
+    big = tables.get_tables(2730)
+    assert big.pmax >= 2730 and big.chain_of(2730).tolist() == numtheory.orth_chain(2730)
+
+
+def test_product_does_not_import_oracle_or_fall_back():
+    pkg = os.path.join(ROOT, "pyperiod_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+    from pyperiod_b200 import Periods
+    import torch
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="CUDA"):
+            Periods.project(np.arange(10.0), 3)
+
+
+def test_constructor_call_shapes():
+    from pyperiod_b200 import Periods
+    x = np.arange(16.0)
+    a = Periods(x)                      # README form
+    b = Periods(True, True)             # HEAD form
+    c = Periods(x, trunc_to_integer_multiple=True)
+    assert a._data is x and a.orthogonalize is False
+    assert b._data is None and b.trunc_to_integer_multiple == (True, True)   # getter returns a tuple, as the reference
+    assert c._trunc_to_integer_multiple is True
+    b.trunc_to_integer_multiple = (False, True)
+    assert b.orthogonalize is True and b._trunc_to_integer_multiple is False
+    with pytest.raises(TypeError):
+        Periods().m_best(num=3)         # no data anywhere
+
+
+def test_synth_stream_windows_are_views():
+    from pyperiod_b200 import synth
+    s = synth.synth_stream(5, n=64, hop=16, segment=32)
+    w = synth.windows_from_stream(s, 64, 16)
+    assert w.shape == (5, 64) and w.strides == (128, 8)
+    assert np.array_equal(w[3], s[48:112]) and np.max(np.abs(s)) == 1.0
