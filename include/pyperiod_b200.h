@@ -124,6 +124,13 @@ int pp_best_correlation(const double *x, int64_t ldx, int32_t B, int32_t N, int3
                         const int32_t *chain_q, int32_t table_pmax, uint32_t *periods, double *powers,
                         double *bases, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- roofline denominators measured live -----------------------
+ * kind 0: shared-memory load bandwidth, out_host[0] = bytes/s over the whole chip;
+ * kind 1: FP64 add throughput,           out_host[0] = adds/s  over the whole chip;
+ * out_host[1] = SM clock (MHz) observed during the run, out_host[2] = kernel ms.
+ * Synchronous; allocates and frees its own 64-byte scratch. */
+int pp_microbench(int32_t kind, int32_t iters, double *out_host);
+
 #ifdef __cplusplus
 }
 #endif

@@ -39,6 +39,7 @@ SIGNATURES = {
                                     _p, _p, _p, _p, _p, _p, _sz, _p]),
     "pp_best_correlation": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _f64, _i32, _i32, _p, _p, _i32,
                                       _p, _p, _p, _p, _p, _sz, _p]),
+    "pp_microbench": (C.c_int, [_i32, _i32, _p]),
 }
 
 _lib = None
@@ -73,6 +74,13 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().pp_last_error().decode("utf-8", "replace")
         raise PPError(f"{what} failed ({rc}): {msg}")
+
+
+def microbench(kind: int, iters: int = 4000) -> dict:
+    """Measured chip-wide peak: kind 0 = shared-memory bytes/s, kind 1 = FP64 adds/s."""
+    out = (C.c_double * 3)()
+    check(load().pp_microbench(kind, iters, out), "pp_microbench")
+    return {"per_s": out[0], "sm_mhz": out[1], "ms": out[2]}
 
 
 def device_info() -> dict:
