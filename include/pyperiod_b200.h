@@ -58,6 +58,18 @@ extern "C" {
 int pp_abi_version(void);
 const char *pp_last_error(void);
 
+/* How ranking sweeps (NORM / GAMMA, no trunc, no orth) obtain the residue sums:
+ *   PP_FOLD_HIERARCHICAL (default): only periods in (pmax/2, pmax] are folded from the window;
+ *       S_p for smaller p follows from S_2p[r] + S_2p[r+p].  Half the shared-memory traffic;
+ *       energies differ from the sequential fold by rounding only (a few ulp).
+ *   PP_FOLD_DIRECT: every candidate period is folded sequentially from the window.
+ * Outputs that must be bit-exact (project(), the bases, MAXABS metrics) never use the
+ * hierarchical sums.  Process-wide setting. */
+#define PP_FOLD_HIERARCHICAL 0
+#define PP_FOLD_DIRECT 1
+int pp_set_fold_mode(int32_t mode);
+int pp_get_fold_mode(void);
+
 /* Device facts the host uses for grid sizing / roofline arithmetic (current device). */
 int pp_device_info(int32_t *sm_count, int32_t *smem_optin_bytes, int32_t *cc_major, int32_t *cc_minor,
                    int32_t *clock_khz);

@@ -27,6 +27,8 @@ _sz = C.c_size_t
 SIGNATURES = {
     "pp_abi_version": (C.c_int, []),
     "pp_last_error": (C.c_char_p, []),
+    "pp_set_fold_mode": (C.c_int, [_i32]),
+    "pp_get_fold_mode": (C.c_int, []),
     "pp_device_info": (C.c_int, [_p, _p, _p, _p, _p]),
     "pp_grid_size": (C.c_int, [_i32, _i32, _i32, _i32]),
     "pp_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
@@ -74,6 +76,14 @@ def check(rc: int, what: str):
     if rc != 0:
         msg = load().pp_last_error().decode("utf-8", "replace")
         raise PPError(f"{what} failed ({rc}): {msg}")
+
+
+FOLD_HIERARCHICAL, FOLD_DIRECT = 0, 1
+
+
+def set_fold_mode(mode: int):
+    """FOLD_HIERARCHICAL (default) or FOLD_DIRECT; see include/pyperiod_b200.h."""
+    check(load().pp_set_fold_mode(int(mode)), "pp_set_fold_mode")
 
 
 def microbench(kind: int, iters: int = 4000) -> dict:

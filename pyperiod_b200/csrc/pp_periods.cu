@@ -37,12 +37,14 @@ struct SmemPlan {
   int pv;       // doubles: single-period vectors (vwin, utmp)
   int num;      // slots (M-best) / rounds
   int skip_words;
+  int hier_len; // doubles per warp of hierarchical-sweep scratch (0 = none)
   __host__ __device__ size_t off_vwin() const { return (size_t)xs_len * 8; }
   __host__ __device__ size_t off_utmp() const { return off_vwin() + (size_t)pv * 8; }
   __host__ __device__ size_t off_red() const { return off_utmp() + (size_t)pv * 8; }
   __host__ __device__ size_t off_norms() const { return off_red() + 2 * kWarps * 8; }
   __host__ __device__ size_t off_fval() const { return off_norms() + (size_t)((num + 1) & ~1) * 8; }
-  __host__ __device__ size_t off_bar() const { return off_fval() + (size_t)kMaxFactors * 8; }
+  __host__ __device__ size_t off_hier() const { return off_fval() + (size_t)kMaxFactors * 8; }
+  __host__ __device__ size_t off_bar() const { return off_hier() + (size_t)kWarps * hier_len * 8; }
   __host__ __device__ size_t off_sweep() const { return off_bar() + 16; }
   __host__ __device__ size_t off_periods() const { return off_sweep() + ((sizeof(SweepShared) + 15) & ~15); }
   __host__ __device__ size_t off_slot() const { return off_periods() + (size_t)num * 4; }
@@ -51,8 +53,9 @@ struct SmemPlan {
   __host__ __device__ size_t bytes() const { return off_misc() + 64; }
 };
 
-__host__ __device__ inline SmemPlan make_plan(int N, int pmax, int num, bool sweep_pad) {
+__host__ __device__ inline SmemPlan make_plan(int N, int pmax, int num, bool sweep_pad, bool hier = false) {
   SmemPlan pl;
+  pl.hier_len = hier ? hier_scratch_len(pmax) : 0;
   pl.xs_len = sweep_pad ? ((N + pmax + kSweepPad + 1) & ~1) : ((N + 1) & ~1);
   pl.pv = (pmax + 2) & ~1;
   pl.num = num;
@@ -67,6 +70,7 @@ struct Smem {
   double* red;
   double* norms;
   double* fval;
+  double* hier;
   uint64_t* bar;
   SweepShared* sweep;
   int* periods;
@@ -80,6 +84,7 @@ struct Smem {
     red = reinterpret_cast<double*>(base + pl.off_red());
     norms = reinterpret_cast<double*>(base + pl.off_norms());
     fval = reinterpret_cast<double*>(base + pl.off_fval());
+    hier = pl.hier_len ? reinterpret_cast<double*>(base + pl.off_hier()) : nullptr;
     bar = reinterpret_cast<uint64_t*>(base + pl.off_bar());
     sweep = reinterpret_cast<SweepShared*>(base + pl.off_sweep());
     periods = reinterpret_cast<int*>(base + pl.off_periods());
@@ -145,10 +150,10 @@ norm_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int p, doub
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads, 2)
 sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, int pmax, int metric, int trunc,
-             int orth, Tables tb, double* __restrict__ metric_out, int32_t* __restrict__ best_p,
+             int orth, int hier, Tables tb, double* __restrict__ metric_out, int32_t* __restrict__ best_p,
              double* __restrict__ best_val, double* __restrict__ warp_scr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const SmemPlan pl = make_plan(N, pmax, 0, true);
+  const SmemPlan pl = make_plan(N, pmax, 0, true, hier != 0);
   Smem sm(smem_raw, pl);
   WindowLoader loader;
   loader.init(sm.bar);
@@ -176,6 +181,8 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
     }
     sp.thresh = -1.0;
     sp.skip = nullptr;
+    sp.hier_scr = sm.hier;
+    sp.hier_len = pl.hier_len;
     sp.metric_out = metric_out ? metric_out + (size_t)b * (pmax + 1) : nullptr;
     const SweepResult r = cta_sweep(sp, sm.sweep);
     if (threadIdx.x == 0) {
@@ -220,11 +227,11 @@ __device__ __forceinline__ double warp_slot_factor_norm(const double* slot, int 
 
 __global__ void __launch_bounds__(kThreads, 2)
 mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, int pmin, int pmax, int gamma,
-             int trunc_i, int orth_i, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
+             int trunc_i, int orth_i, int hier, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
              double* __restrict__ bases_out, int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
              double* __restrict__ ws_slots, double* __restrict__ ws_scr) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  const SmemPlan pl = make_plan(N, pmax, num, true);
+  const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0);
   Smem sm(smem_raw, pl);
   const bool trunc = trunc_i != 0, orth = orth_i != 0;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -273,6 +280,8 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     sp.thresh = -1.0;
     sp.skip = sm.skip;
     sp.metric_out = nullptr;
+    sp.hier_scr = sm.hier;
+    sp.hier_len = pl.hier_len;
 
     // ---------------- step 1 (Periods.py:494-537)
     int sweeps = 0;
@@ -482,6 +491,8 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
     sp.thresh = thresh < 0.0 ? 0.0 : thresh;
     sp.skip = nullptr;
     sp.metric_out = nullptr;
+    sp.hier_scr = nullptr;
+    sp.hier_len = 0;
     int count = 0;
     int pstart = 2;
     // thresh < 0 would accept every period in the reference; first-hit mode needs thresh >= 0,
@@ -556,6 +567,8 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     sp.thresh = -1.0;
     sp.skip = nullptr;
     sp.metric_out = nullptr;
+    sp.hier_scr = nullptr;
+    sp.hier_len = 0;
     for (int i = 0; i < num; ++i) {
       uint32_t out_p = 0u;
       double out_v = 0.0;
@@ -618,8 +631,15 @@ static int device_facts(DeviceFacts& f) {
   return 0;
 }
 
+// 0 = hierarchical ranking sweeps where they apply (default), 1 = always fold every period directly
+static int g_fold_mode = 0;
+
+static bool hier_applies(int metric, int trunc, int orth) {
+  return g_fold_mode == 0 && !trunc && !orth && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
+}
+
 static int plan_for(int algo, int N, int pmax, int num, SmemPlan& pl) {
-  pl = make_plan(N, pmax, algo == PP_ALGO_MBEST ? num : 0, true);
+  pl = make_plan(N, pmax, algo == PP_ALGO_MBEST ? num : 0, true, g_fold_mode == 0 && (algo == PP_ALGO_MBEST || algo == PP_ALGO_SWEEP));
   return 0;
 }
 
@@ -648,6 +668,13 @@ using namespace pp;
 extern "C" {
 
 int pp_abi_version(void) { return PP_ABI_VERSION; }
+
+int pp_set_fold_mode(int32_t mode) {
+  if (mode != PP_FOLD_HIERARCHICAL && mode != PP_FOLD_DIRECT) return fail(-1, "unknown fold mode%s");
+  g_fold_mode = mode;
+  return 0;
+}
+int pp_get_fold_mode(void) { return g_fold_mode; }
 const char* pp_last_error(void) { return g_err; }
 
 int pp_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_major, int32_t* cc_minor,
@@ -746,7 +773,8 @@ int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, i
   if (B == 0) return 0;
   DeviceFacts f;
   if (int rc = device_facts(f)) return rc;
-  const SmemPlan pl = make_plan(N, pmax, 0, true);
+  const int hier = hier_applies(metric, trunc, orth) ? 1 : 0;
+  const SmemPlan pl = make_plan(N, pmax, 0, true, hier != 0);
   if (int rc = prep_kernel(sweep_kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B);
   size_t off = 0;
@@ -756,8 +784,8 @@ int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, i
     if (!scr) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
   }
   Tables tb{chain_off, chain_q, nullptr, nullptr};
-  sweep_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, pmin, pmax, metric, trunc, orth, tb,
-                                                                     metric_out, best_p, best_val, scr);
+  sweep_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, pmin, pmax, metric, trunc, orth, hier,
+                                                                     tb, metric_out, best_p, best_val, scr);
   return check_cuda(cudaGetLastError(), "sweep_kernel launch");
 }
 
@@ -775,7 +803,8 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   if (B == 0) return 0;
   DeviceFacts f;
   if (int rc = device_facts(f)) return rc;
-  const SmemPlan pl = make_plan(N, pmax, num, true);
+  const int hier = hier_applies(gamma ? PP_METRIC_GAMMA : PP_METRIC_NORM, trunc, orth) ? 1 : 0;
+  const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0);
   if (int rc = prep_kernel(mbest_kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B);
   size_t off = 0;
@@ -784,8 +813,8 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   if (!slots || (orth && !scr)) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
   Tables tb{chain_off, chain_q, fac_off, fac};
   mbest_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,
-                                                                     tb, periods, powers, bases, sweeps, status, slots,
-                                                                     scr);
+                                                                     hier, tb, periods, powers, bases, sweeps, status,
+                                                                     slots, scr);
   return check_cuda(cudaGetLastError(), "mbest_kernel launch");
 }
 

@@ -33,6 +33,8 @@ struct SweepParams {
   double thresh;      // IMPOSED early-stop threshold; <0 disables first-hit mode
   const uint32_t* skip;  // bitmap of periods to ignore (M-best), nullable
   double* metric_out;    // global [pmax+1], nullable
+  double* hier_scr;      // shared scratch for the hierarchical sweep: kWarps * hier_len doubles (nullable => direct)
+  int hier_len;
 };
 
 struct SweepResult {
@@ -175,6 +177,215 @@ __device__ __forceinline__ double warp_period_metric_any(const SweepParams& sp, 
   return warp_period_metric<kPassEnergy>(sp, p);
 }
 
+
+// ------------------------------------------------------------------------------------------
+// hierarchical sweep (ranking only): fold only the "top" periods q in (pmax/2, pmax] from the
+// window; every smaller candidate is q / 2^k of exactly one top and its sums follow from
+// S_{p}[r] = S_{2p}[r] + S_{2p}[r + p].  Halves the shared-memory traffic of a sweep.  The
+// derived sums differ from the sequential ones by rounding only (<= a few ulp), which is the
+// same order as the reference's own BLAS norm noise; exact projections of the winners are
+// always recomputed sequentially (cta_project_exact).
+//
+// A top q = g * 2^L (L <= 3) is folded at base period g with 2^L accumulator sets selected by
+// (row mod 2^L): set s holds S_q[r + s g].  Pairwise in-register adds then give the sums of
+// q/2, q/4, .. g.  If g is still even the chain continues through a small per-warp scratch.
+// ------------------------------------------------------------------------------------------
+__host__ __device__ inline int hier_scratch_len(int pmax) { return ((((pmax >> 3) + 2) * 3) / 2 + 3) & ~1; }
+
+struct HierLevels {
+  int r0[4];
+  double inv_hi[4], inv_lo[4];
+};
+
+// compile-time recursion over the levels l = LV .. 0 (keeps every accumulator index static)
+template <int L, int W, int LV>
+struct hier_levels {
+  static __device__ __forceinline__ void run(double (&acc)[1 << L][W], int r_base, int g, const HierLevels& lv,
+                                             double (&E)[4]) {
+    constexpr int sets = 1 << LV;
+#pragma unroll
+    for (int s = 0; s < sets; ++s) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) {
+        const double v = acc[s][w];
+        const int rho = r_base + 32 * w + s * g;
+        E[LV] = fma(v * v, rho < lv.r0[LV] ? lv.inv_hi[LV] : lv.inv_lo[LV], E[LV]);
+      }
+    }
+    if constexpr (LV > 0) {
+      constexpr int half = sets >> 1;
+#pragma unroll
+      for (int s = 0; s < half; ++s)
+#pragma unroll
+        for (int w = 0; w < W; ++w) acc[s][w] += acc[s + half][w];
+      hier_levels<L, W, LV - 1>::run(acc, r_base, g, lv, E);
+    }
+  }
+};
+
+template <int L, int W>
+__device__ __forceinline__ void hier_chunk(const double* __restrict__ ptr, int cb, int g, int rows,
+                                           const HierLevels& lv, double (&E)[4], double* scr) {
+  constexpr int S = 1 << L;
+  const int lane = threadIdx.x & 31;
+  double acc[S][W];
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int w = 0; w < W; ++w) acc[s][w] = 0.0;
+  int k = 0;
+  if (S == 1) {
+#pragma unroll 4
+    for (; k < rows; ++k) {
+#pragma unroll
+      for (int w = 0; w < W; ++w) acc[0][w] += ptr[32 * w];
+      ptr += g;
+    }
+  } else {
+#pragma unroll 1
+    for (; k + S <= rows; k += S) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) acc[s][w] += ptr[32 * w];
+        ptr += g;
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < S - 1; ++s) {
+      if (k + s < rows) {
+#pragma unroll
+        for (int w = 0; w < W; ++w) acc[s][w] += ptr[32 * w];
+        ptr += g;
+      }
+    }
+  }
+  // lanes past g hold sums of the next row's samples: drop them once
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    if (cb + lane + 32 * w >= g) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) acc[s][w] = 0.0;
+    }
+  }
+  hier_levels<L, W, L>::run(acc, cb + lane, g, lv, E);
+  if (scr != nullptr) {
+#pragma unroll
+    for (int w = 0; w < W; ++w)
+      if (cb + lane + 32 * w < g) scr[cb + lane + 32 * w] = acc[0][w];
+  }
+}
+
+template <int L>
+__device__ __forceinline__ void hier_top_fold(const double* xs, int g, int rows, const HierLevels& lv,
+                                              double (&E)[4], double* scr) {
+  constexpr int WMAX = (L == 3) ? 4 : 8;
+  const int lane = threadIdx.x & 31;
+  for (int cb = 0; cb < g; cb += 32 * WMAX) {
+    const int w = (min(g - cb, 32 * WMAX) + 31) >> 5;
+    const double* ptr = xs + cb + lane;
+    switch (w) {
+      case 1: hier_chunk<L, 1>(ptr, cb, g, rows, lv, E, scr); break;
+      case 2: hier_chunk<L, 2>(ptr, cb, g, rows, lv, E, scr); break;
+      case 3: hier_chunk<L, 3>(ptr, cb, g, rows, lv, E, scr); break;
+      case 4: hier_chunk<L, 4>(ptr, cb, g, rows, lv, E, scr); break;
+      default:
+        if (WMAX == 8) {
+          switch (w) {
+            case 5: hier_chunk<L, (WMAX == 8 ? 5 : 1)>(ptr, cb, g, rows, lv, E, scr); break;
+            case 6: hier_chunk<L, (WMAX == 8 ? 6 : 1)>(ptr, cb, g, rows, lv, E, scr); break;
+            case 7: hier_chunk<L, (WMAX == 8 ? 7 : 1)>(ptr, cb, g, rows, lv, E, scr); break;
+            default: hier_chunk<L, (WMAX == 8 ? 8 : 1)>(ptr, cb, g, rows, lv, E, scr); break;
+          }
+        }
+        break;
+    }
+  }
+}
+
+// keeps the running strict-'>' argmax with lowest-p tie-break, honouring the skip bitmap
+__device__ __forceinline__ void consider(const SweepParams& sp, double val, int p, double& bestv, int& bestp) {
+  if (sp.metric_out != nullptr && (threadIdx.x & 31) == 0) sp.metric_out[p] = val;
+  const bool skipped = sp.skip != nullptr && ((sp.skip[p >> 5] >> (p & 31)) & 1u);
+  if (!skipped && (val > bestv || (val == bestv && bestp != 0 && p < bestp))) {
+    bestv = val;
+    bestp = p;
+  }
+}
+
+// One top period q and every candidate q / 2^k below it.  Non-trunc, non-orth, NORM / GAMMA.
+__device__ __forceinline__ void warp_hier_top(const SweepParams& sp, int q, double* scr, double& bestv, int& bestp) {
+  const int lane = threadIdx.x & 31;
+  const int N = sp.N;
+  int L = min(__ffs(q) - 1, 3);
+  while (L > 0 && (q >> L) < sp.pmin) --L;
+  const int g = q >> L;
+  // per-level constants, one level per lane, then broadcast
+  HierLevels lv;
+  {
+    const int l = lane & 3;
+    const int P = g << l;
+    const int M = N / P;
+    const int my_r0 = N - M * P;
+    const double my_hi = 1.0 / (double)(M + 1), my_lo = 1.0 / (double)M;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      lv.r0[i] = __shfl_sync(0xffffffffu, my_r0, i);
+      lv.inv_hi[i] = __shfl_sync(0xffffffffu, my_hi, i);
+      lv.inv_lo[i] = __shfl_sync(0xffffffffu, my_lo, i);
+    }
+  }
+  const int rows = (N + g - 1) / g;
+  const bool chain = (L == 3) && !(g & 1) && (g >> 1) >= sp.pmin;
+  double E[4] = {0.0, 0.0, 0.0, 0.0};
+  switch (L) {
+    case 0: hier_top_fold<0>(sp.xs, g, rows, lv, E, nullptr); break;
+    case 1: hier_top_fold<1>(sp.xs, g, rows, lv, E, nullptr); break;
+    case 2: hier_top_fold<2>(sp.xs, g, rows, lv, E, nullptr); break;
+    default: hier_top_fold<3>(sp.xs, g, rows, lv, E, chain ? scr : nullptr); break;
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) E[i] = warp_sum(E[i]);
+  {
+    const int l = lane & 3;
+    const double myE = l == 0 ? E[0] : (l == 1 ? E[1] : (l == 2 ? E[2] : E[3]));
+    double val = sqrt(myE) / sp.sqrtN;
+    if (sp.metric == PP_METRIC_GAMMA) val = val / sqrt((double)(g << l));
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const double vi = __shfl_sync(0xffffffffu, val, i);
+      if (i <= L) consider(sp, vi, g << i, bestv, bestp);
+    }
+  }
+  if (chain) {
+    __syncwarp();
+    double* src = scr;
+    double* dst = scr + ((g + 1) & ~1);
+    int h = g;
+    while (!(h & 1) && (h >> 1) >= sp.pmin) {
+      const int h2 = h >> 1;
+      const int M = N / h2, r0 = N - M * h2;
+      const double hi = 1.0 / (double)(M + 1), lo = 1.0 / (double)M;
+      double e = 0.0;
+      for (int r = lane; r < h2; r += 32) {
+        const double v = src[r] + src[r + h2];
+        dst[r] = v;
+        e = fma(v * v, r < r0 ? hi : lo, e);
+      }
+      __syncwarp();
+      e = warp_sum(e);
+      double val = sqrt(e) / sp.sqrtN;
+      if (sp.metric == PP_METRIC_GAMMA) val = val / sqrt((double)h2);
+      consider(sp, val, h2, bestv, bestp);
+      double* t = src;
+      src = dst;
+      dst = t;
+      h = h2;
+    }
+    __syncwarp();
+  }
+}
+
 // Shared scratch the sweep needs (one per CTA).
 struct SweepShared {
   int counter;            // next candidate index
@@ -199,7 +410,22 @@ __device__ __forceinline__ SweepResult cta_sweep(const SweepParams& sp, SweepSha
   __syncthreads();
   double bestv = 0.0;
   int bestp = 0;
-  const int ncand = sp.pmax - sp.pmin + 1;
+  const bool hier = sp.hier_scr != nullptr && !first_hit && !sp.orth && !sp.trunc &&
+                    (sp.metric == PP_METRIC_NORM || sp.metric == PP_METRIC_GAMMA);
+  if (hier) {
+    // tops: candidates p with 2p > pmax; everything else is derived from exactly one of them
+    const int top_lo = max(sp.pmin, (sp.pmax >> 1) + 1);
+    const int ntops = sp.pmax - top_lo + 1;
+    double* scr = sp.hier_scr + (size_t)wid * sp.hier_len;
+    while (true) {
+      int idx = 0;
+      if (lane == 0) idx = atomicAdd(&sh->counter, 1);
+      idx = __shfl_sync(0xffffffffu, idx, 0);
+      if (idx >= ntops) break;
+      warp_hier_top(sp, sp.pmax - idx, scr, bestv, bestp);
+    }
+  }
+  const int ncand = hier ? 0 : sp.pmax - sp.pmin + 1;
   while (true) {
     int idx = 0;
     if (lane == 0) idx = atomicAdd(&sh->counter, 1);

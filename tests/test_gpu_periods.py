@@ -108,6 +108,44 @@ def test_sweep_metrics_vs_oracle(P, trunc, orth):
         assert abs(m[0, p] - want_p) <= 1e-13, p
 
 
+@pytest.mark.parametrize("n,pmin,pmax", [(4096, 2, 1024), (2000, 2, 666), (4095, 3, 1000), (1000, 17, 500),
+                                          (8192, 2, 2730), (512, 2, 100), (4096, 600, 1024)])
+def test_sweep_hierarchical_matches_direct(P, n, pmin, pmax):
+    """The hierarchical ranking sweep (S_p from S_2p) agrees with the sequential fold to rounding."""
+    from pyperiod_b200 import _lib
+    xb = synth.synth_batch(3, n, 4242)
+    try:
+        out = {}
+        for mode in (_lib.FOLD_DIRECT, _lib.FOLD_HIERARCHICAL):
+            _lib.set_fold_mode(mode)
+            for metric in ("norm", "gamma"):
+                out[mode, metric] = P().sweep(xb, metric=metric, min_length=pmin, max_length=pmax)
+    finally:
+        _lib.set_fold_mode(_lib.FOLD_HIERARCHICAL)
+    for metric in ("norm", "gamma"):
+        md, pd_, vd = out[_lib.FOLD_DIRECT, metric]
+        mh, ph, vh = out[_lib.FOLD_HIERARCHICAL, metric]
+        assert np.all(mh[:, :pmin] == 0) and np.all(md[:, :pmin] == 0)
+        np.testing.assert_allclose(mh[:, pmin:], md[:, pmin:], rtol=1e-13, atol=0)
+        assert np.array_equal(pd_, ph)
+        np.testing.assert_allclose(vh, vd, rtol=1e-13)
+
+
+def test_mbest_fold_modes_agree(P):
+    from pyperiod_b200 import _lib
+    xb = synth.synth_batch(8, 4096, 777)
+    try:
+        _lib.set_fold_mode(_lib.FOLD_DIRECT)
+        a = P().m_best_gamma(xb, num=10, max_length=1024, return_bases=True)
+        _lib.set_fold_mode(_lib.FOLD_HIERARCHICAL)
+        b = P().m_best_gamma(xb, num=10, max_length=1024, return_bases=True)
+    finally:
+        _lib.set_fold_mode(_lib.FOLD_HIERARCHICAL)
+    assert np.array_equal(a.periods, b.periods) and np.array_equal(a.sweeps, b.sweeps)
+    np.testing.assert_allclose(a.powers, b.powers, rtol=1e-12)
+    assert np.array_equal(a.bases, b.bases)       # bases never come from the hierarchical sums
+
+
 def test_sweep_maxabs_bit_exact(P):
     x = synth.synth(2048, 40_000)
     m, bp, bv = P().sweep(x[None, :], metric="maxabs", max_length=681)
