@@ -70,6 +70,11 @@ const char *pp_last_error(void);
 int pp_set_fold_mode(int32_t mode);
 int pp_get_fold_mode(void);
 
+/* Development aid: when set to a device buffer of 8 uint64, pp_mbest adds per-window SM-cycle
+ * counts to it: [0] sweeps, [1] exact winner projections, [2] bookkeeping + residual update,
+ * [3] step 2 + outputs, [4] windows.  Pass NULL to disable (default). */
+int pp_set_profile_buffer(void *dev_u64x8);
+
 /* Device facts the host uses for grid sizing / roofline arithmetic (current device). */
 int pp_device_info(int32_t *sm_count, int32_t *smem_optin_bytes, int32_t *cc_major, int32_t *cc_minor,
                    int32_t *clock_khz);

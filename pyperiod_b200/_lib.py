@@ -29,6 +29,7 @@ SIGNATURES = {
     "pp_last_error": (C.c_char_p, []),
     "pp_set_fold_mode": (C.c_int, [_i32]),
     "pp_get_fold_mode": (C.c_int, []),
+    "pp_set_profile_buffer": (C.c_int, [_p]),
     "pp_device_info": (C.c_int, [_p, _p, _p, _p, _p]),
     "pp_grid_size": (C.c_int, [_i32, _i32, _i32, _i32]),
     "pp_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),

@@ -10,11 +10,24 @@
 
 namespace pp {
 
-constexpr int kThreads = 256;           // threads per CTA (8 warps); 2 CTAs/SM at <=128 regs
+#ifndef PP_THREADS
+#define PP_THREADS 256
+#endif
+#ifndef PP_CTAS
+#define PP_CTAS 3
+#endif
+constexpr int kThreads = PP_THREADS;    // threads per CTA
 constexpr int kWarps = kThreads / 32;
-constexpr int kResBlock = 1024;         // residues one warp pass keeps in registers (32 lanes x 32)
+constexpr int kResBlock = 512;          // residues one warp pass keeps in registers (32 lanes x 16)
+constexpr int kCtasPerSm = PP_CTAS;     // occupancy target of the sweep kernels (sets the register budget)
 constexpr int kSweepPad = 192;          // slack (samples) the register-tiled fold may read past c*p
 constexpr int kMaxFactors = 128;        // non-trivial divisors per period handled by M-best step 2
+
+// The dynamic shared memory of every kernel in this library starts with the staged window (xs).
+// Declaring the array at namespace scope lets out-of-line device functions address it as shared
+// memory (LDS with immediate offsets) instead of through a generic pointer.
+extern __shared__ __align__(128) unsigned char pp_smem[];
+__device__ __forceinline__ const double* staged_window() { return reinterpret_cast<const double*>(pp_smem); }
 
 // ------------------------------------------------------------------------------------------
 // small PTX wrappers: mbarrier + TMA bulk copy (cp.async.bulk, SASS UBLKCP)

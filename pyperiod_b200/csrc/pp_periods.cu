@@ -40,11 +40,16 @@ struct SmemPlan {
   int hier_len; // doubles per warp of hierarchical-sweep scratch (0 = none)
   __host__ __device__ size_t off_vwin() const { return (size_t)xs_len * 8; }
   __host__ __device__ size_t off_utmp() const { return off_vwin() + (size_t)pv * 8; }
-  __host__ __device__ size_t off_red() const { return off_utmp() + (size_t)pv * 8; }
+  // the hierarchical-sweep scratch is only live inside a sweep, vwin/utmp only between sweeps: they share bytes
+  __host__ __device__ size_t off_hier() const { return off_vwin(); }
+  __host__ __device__ size_t union_bytes() const {
+    const size_t a = 2 * (size_t)pv * 8, b = (size_t)kWarps * hier_len * 8;
+    return a > b ? a : b;
+  }
+  __host__ __device__ size_t off_red() const { return off_vwin() + union_bytes(); }
   __host__ __device__ size_t off_norms() const { return off_red() + 2 * kWarps * 8; }
   __host__ __device__ size_t off_fval() const { return off_norms() + (size_t)((num + 1) & ~1) * 8; }
-  __host__ __device__ size_t off_hier() const { return off_fval() + (size_t)kMaxFactors * 8; }
-  __host__ __device__ size_t off_bar() const { return off_hier() + (size_t)kWarps * hier_len * 8; }
+  __host__ __device__ size_t off_bar() const { return off_fval() + (size_t)kMaxFactors * 8; }
   __host__ __device__ size_t off_sweep() const { return off_bar() + 16; }
   __host__ __device__ size_t off_periods() const { return off_sweep() + ((sizeof(SweepShared) + 15) & ~15); }
   __host__ __device__ size_t off_slot() const { return off_periods() + (size_t)num * 4; }
@@ -116,7 +121,7 @@ struct ChainArg {
 __global__ void __launch_bounds__(kThreads, 2)
 project_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int p, int trunc, ChainArg chain,
                double* __restrict__ out, int64_t ldo, int out_len) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, p, 0, false);
   Smem sm(smem_raw, pl);
   __shared__ int32_t s_chain[16];
@@ -148,43 +153,44 @@ norm_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int p, doub
 // ------------------------------------------------------------------------------------------
 // K1: one sweep per window (parity probe and building block)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, int pmax, int metric, int trunc,
              int orth, int hier, Tables tb, double* __restrict__ metric_out, int32_t* __restrict__ best_p,
              double* __restrict__ best_val, double* __restrict__ warp_scr) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, pmax, 0, true, hier != 0);
   Smem sm(smem_raw, pl);
   WindowLoader loader;
   loader.init(sm.bar);
   zero_pad(sm.xs, N, pl.xs_len);
+  sweep_shared_init(sm.sweep);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     loader.load(sm.xs, x + (size_t)b * ldx, N);
-    SweepParams sp;
-    sp.xs = sm.xs;
-    sp.N = N;
-    sp.pmin = pmin;
-    sp.pmax = pmax;
-    sp.metric = metric;
-    sp.trunc = trunc != 0;
-    sp.orth = orth != 0;
-    sp.chain_off = tb.chain_off;
-    sp.chain_q = tb.chain_q;
-    sp.warp_scr = warp_scr ? warp_scr + (size_t)blockIdx.x * kWarps * 2 * pl.pv : nullptr;
-    sp.pv = pl.pv;
-    sp.sqrtN = sqrt((double)N);
-    sp.e_res = 0.0;
-    sp.data_norm = 1.0;
-    if (metric == PP_METRIC_IMPOSED) {
-      sp.e_res = cta_sum_sq(sm.xs, N, sm.red);
-      sp.data_norm = sqrt(sp.e_res) / sp.sqrtN;
+    double e_res = 0.0;
+    if (metric == PP_METRIC_IMPOSED) e_res = cta_sum_sq(sm.xs, N, sm.red);
+    if (threadIdx.x == 0) {
+      SweepParams& sp = sm.sweep->params;
+      sp.N = N;
+      sp.pmin = pmin;
+      sp.pmax = pmax;
+      sp.metric = metric;
+      sp.trunc = trunc;
+      sp.orth = orth;
+      sp.chain_off = tb.chain_off;
+      sp.chain_q = tb.chain_q;
+      sp.warp_scr = warp_scr ? warp_scr + (size_t)blockIdx.x * kWarps * 2 * pl.pv : nullptr;
+      sp.pv = pl.pv;
+      sp.sqrtN = sqrt((double)N);
+      sp.e_res = e_res;
+      sp.data_norm = metric == PP_METRIC_IMPOSED ? sqrt(e_res) / sp.sqrtN : 1.0;
+      sp.thresh = -1.0;
+      sp.skip = nullptr;
+      sp.hier_scr = sm.hier;
+      sp.hier_len = pl.hier_len;
+      sp.rcp = sm.sweep->rcp;
+      sp.metric_out = metric_out ? metric_out + (size_t)b * (pmax + 1) : nullptr;
     }
-    sp.thresh = -1.0;
-    sp.skip = nullptr;
-    sp.hier_scr = sm.hier;
-    sp.hier_len = pl.hier_len;
-    sp.metric_out = metric_out ? metric_out + (size_t)b * (pmax + 1) : nullptr;
-    const SweepResult r = cta_sweep(sp, sm.sweep);
+    const SweepResult r = cta_sweep(sm.sweep);
     if (threadIdx.x == 0) {
       best_p[b] = r.p;
       best_val[b] = r.val;
@@ -225,12 +231,12 @@ __device__ __forceinline__ double warp_slot_factor_norm(const double* slot, int 
   return sqrt(warp_sum(e)) / sqrtN;
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, int pmin, int pmax, int gamma,
              int trunc_i, int orth_i, int hier, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
              double* __restrict__ bases_out, int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
-             double* __restrict__ ws_slots, double* __restrict__ ws_scr) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+             double* __restrict__ ws_slots, double* __restrict__ ws_scr, unsigned long long* __restrict__ prof) {
+  unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0);
   Smem sm(smem_raw, pl);
   const bool trunc = trunc_i != 0, orth = orth_i != 0;
@@ -244,6 +250,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
   WindowLoader loader;
   loader.init(sm.bar);
   zero_pad(sm.xs, N, pl.xs_len);
+  sweep_shared_init(sm.sweep);
 
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     loader.load(sm.xs, x + (size_t)b * ldx, N);
@@ -262,34 +269,39 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     for (int i = threadIdx.x; i < pl.skip_words; i += kThreads) sm.skip[i] = 0u;
     __syncthreads();
 
-    SweepParams sp;
-    sp.xs = sm.xs;
-    sp.N = N;
-    sp.pmin = pmin;
-    sp.pmax = pmax;
-    sp.metric = gamma ? PP_METRIC_GAMMA : PP_METRIC_NORM;
-    sp.trunc = trunc;
-    sp.orth = orth;
-    sp.chain_off = tb.chain_off;
-    sp.chain_q = tb.chain_q;
-    sp.warp_scr = my_scr;
-    sp.pv = pl.pv;
-    sp.sqrtN = sqrtN;
-    sp.e_res = 0.0;
-    sp.data_norm = 1.0;
-    sp.thresh = -1.0;
-    sp.skip = sm.skip;
-    sp.metric_out = nullptr;
-    sp.hier_scr = sm.hier;
-    sp.hier_len = pl.hier_len;
+    if (threadIdx.x == 0) {
+      SweepParams& sp = sm.sweep->params;
+      sp.N = N;
+      sp.pmin = pmin;
+      sp.pmax = pmax;
+      sp.metric = gamma ? PP_METRIC_GAMMA : PP_METRIC_NORM;
+      sp.trunc = trunc;
+      sp.orth = orth;
+      sp.chain_off = tb.chain_off;
+      sp.chain_q = tb.chain_q;
+      sp.warp_scr = my_scr;
+      sp.pv = pl.pv;
+      sp.sqrtN = sqrtN;
+      sp.e_res = 0.0;
+      sp.data_norm = 1.0;
+      sp.thresh = -1.0;
+      sp.skip = sm.skip;
+      sp.metric_out = nullptr;
+      sp.hier_scr = sm.hier;
+      sp.hier_len = pl.hier_len;
+      sp.rcp = sm.sweep->rcp;
+    }
+    __syncthreads();
 
     // ---------------- step 1 (Periods.py:494-537)
+    long long t_sweep = 0, t_proj = 0, t_upd = 0, t_step2 = 0, t_mark = clock64();
     int sweeps = 0;
     const int guard = 12 * (pmax - pmin + 2) + 12 * num;
     while (true) {
       if (misc[0] >= num || misc[4] != PP_STATUS_OK) break;  // uniform: read after a barrier
-      const SweepResult top = cta_sweep(sp, sm.sweep);
+      const SweepResult top = cta_sweep(sm.sweep);
       ++sweeps;
+      { const long long t = clock64(); t_sweep += t - t_mark; t_mark = t; }
       if (top.p == 0 || sweeps > guard) {
         if (threadIdx.x == 0) misc[4] = top.p == 0 ? PP_STATUS_NO_PERIOD : PP_STATUS_GUARD;
         __syncthreads();
@@ -298,6 +310,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       const int clen = orth ? tb.chain_off[top.p + 1] - tb.chain_off[top.p] : 0;
       cta_project_exact<false>(sm.xs, 0, N, top.p, trunc, orth ? tb.chain_q + tb.chain_off[top.p] : nullptr, clen,
                                sm.vwin, sm.utmp);
+      { const long long t = clock64(); t_proj += t - t_mark; t_mark = t; }
       if (threadIdx.x == 0) {
         int found = -1;
         for (int i = 0; i < num; ++i)
@@ -333,6 +346,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       }
       cta_subtract_tiled(sm.xs, N, sm.vwin, top.p);  // always (:537)
       __syncthreads();
+      { const long long t = clock64(); t_upd += t - t_mark; t_mark = t; }
     }
 
     // ---------------- step 2 (Periods.py:540-598), one pass
@@ -429,6 +443,14 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
 
     // ---------------- outputs
     __syncthreads();
+    t_step2 = clock64() - t_mark;
+    if (prof != nullptr && threadIdx.x == 0) {
+      atomicAdd(prof + 0, (unsigned long long)t_sweep);
+      atomicAdd(prof + 1, (unsigned long long)t_proj);
+      atomicAdd(prof + 2, (unsigned long long)t_upd);
+      atomicAdd(prof + 3, (unsigned long long)t_step2);
+      atomicAdd(prof + 4, 1ull);
+    }
     const int status = misc[4];
     for (int i = threadIdx.x; i < num; i += kThreads) {
       const bool ok = status == PP_STATUS_OK;
@@ -457,12 +479,12 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
 // ------------------------------------------------------------------------------------------
 // K3: small-to-large (Periods.py:246-287): speculative sweep, restart after each acceptance
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thresh, int n_periods, int trunc_i,
            int orth_i, Tables tb, int kmax, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
            double* __restrict__ bases_out, int32_t* __restrict__ count_out, int32_t* __restrict__ status_out,
            double* __restrict__ ws_scr) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, n_periods, 0, true);
   Smem sm(smem_raw, pl);
   const bool trunc = trunc_i != 0, orth = orth_i != 0;
@@ -471,35 +493,38 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
   WindowLoader loader;
   loader.init(sm.bar);
   zero_pad(sm.xs, N, pl.xs_len);
+  sweep_shared_init(sm.sweep);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     loader.load(sm.xs, x + (size_t)b * ldx, N);
     const double e_data = cta_sum_sq(sm.xs, N, sm.red);
-    SweepParams sp;
-    sp.xs = sm.xs;
-    sp.N = N;
-    sp.pmax = n_periods;
-    sp.metric = PP_METRIC_IMPOSED;
-    sp.trunc = trunc;
-    sp.orth = orth;
-    sp.chain_off = tb.chain_off;
-    sp.chain_q = tb.chain_q;
-    sp.warp_scr = my_scr;
-    sp.pv = pl.pv;
-    sp.sqrtN = sqrtN;
-    sp.e_res = e_data;
-    sp.data_norm = sqrt(e_data) / sqrtN;
-    sp.thresh = thresh < 0.0 ? 0.0 : thresh;
-    sp.skip = nullptr;
-    sp.metric_out = nullptr;
-    sp.hier_scr = nullptr;
-    sp.hier_len = 0;
+    if (threadIdx.x == 0) {
+      SweepParams& sp = sm.sweep->params;
+      sp.N = N;
+      sp.pmax = n_periods;
+      sp.metric = PP_METRIC_IMPOSED;
+      sp.trunc = trunc;
+      sp.orth = orth;
+      sp.chain_off = tb.chain_off;
+      sp.chain_q = tb.chain_q;
+      sp.warp_scr = my_scr;
+      sp.pv = pl.pv;
+      sp.sqrtN = sqrtN;
+      sp.e_res = e_data;
+      sp.data_norm = sqrt(e_data) / sqrtN;
+      sp.thresh = thresh < 0.0 ? 0.0 : thresh;
+      sp.skip = nullptr;
+      sp.metric_out = nullptr;
+      sp.hier_scr = nullptr;
+      sp.hier_len = 0;
+      sp.rcp = sm.sweep->rcp;
+    }
     int count = 0;
     int pstart = 2;
     // thresh < 0 would accept every period in the reference; first-hit mode needs thresh >= 0,
     // the host rejects negative thresholds.
     while (pstart <= n_periods) {
-      sp.pmin = pstart;
-      const SweepResult hit = cta_sweep(sp, sm.sweep);
+      if (threadIdx.x == 0) sm.sweep->params.pmin = pstart;
+      const SweepResult hit = cta_sweep(sm.sweep);
       if (hit.p == 0) break;
       const int clen = orth ? tb.chain_off[hit.p + 1] - tb.chain_off[hit.p] : 0;
       cta_project_exact<false>(sm.xs, 0, N, hit.p, trunc, orth ? tb.chain_q + tb.chain_off[hit.p] : nullptr, clen,
@@ -514,7 +539,8 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
       }
       ++count;
       __syncthreads();
-      sp.e_res = cta_sum_sq(sm.xs, N, sm.red);
+      const double e_now = cta_sum_sq(sm.xs, N, sm.red);
+      if (threadIdx.x == 0) sm.sweep->params.e_res = e_now;
       pstart = hit.p + 1;
     }
     for (int k = count + threadIdx.x; k < kmax; k += kThreads) {
@@ -532,11 +558,11 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
 // ------------------------------------------------------------------------------------------
 // K4: best-correlation (Periods.py:289-349)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 2)
+__global__ void __launch_bounds__(kThreads, kCtasPerSm)
 bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, int max_length, double ratio,
              int trunc_i, int orth_i, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
              double* __restrict__ bases_out, int32_t* __restrict__ status_out) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
+  unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, max_length, 0, true);
   Smem sm(smem_raw, pl);
   const bool trunc = trunc_i != 0, orth = orth_i != 0;
@@ -544,38 +570,41 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
   WindowLoader loader;
   loader.init(sm.bar);
   zero_pad(sm.xs, N, pl.xs_len);
+  sweep_shared_init(sm.sweep);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     loader.load(sm.xs, x + (size_t)b * ldx, N);
     const double og = sqrt(cta_sum_sq(sm.xs, N, sm.red)) / sqrtN;
     double prev = og;
     int status = PP_STATUS_OK;
-    SweepParams sp;
-    sp.xs = sm.xs;
-    sp.N = N;
-    sp.pmin = 2;
-    sp.pmax = max_length - 1;  // range(2, max_length) excludes max_length (:324)
-    sp.metric = PP_METRIC_MAXABS;
-    sp.trunc = false;          // the correlation metric always folds all N samples
-    sp.orth = false;
-    sp.chain_off = tb.chain_off;
-    sp.chain_q = tb.chain_q;
-    sp.warp_scr = nullptr;
-    sp.pv = pl.pv;
-    sp.sqrtN = sqrtN;
-    sp.e_res = 0.0;
-    sp.data_norm = 1.0;
-    sp.thresh = -1.0;
-    sp.skip = nullptr;
-    sp.metric_out = nullptr;
-    sp.hier_scr = nullptr;
-    sp.hier_len = 0;
+    if (threadIdx.x == 0) {
+      SweepParams& sp = sm.sweep->params;
+      sp.N = N;
+      sp.pmin = 2;
+      sp.pmax = max_length - 1;  // range(2, max_length) excludes max_length (:324)
+      sp.metric = PP_METRIC_MAXABS;
+      sp.trunc = 0;              // the correlation metric always folds all N samples
+      sp.orth = 0;
+      sp.chain_off = tb.chain_off;
+      sp.chain_q = tb.chain_q;
+      sp.warp_scr = nullptr;
+      sp.pv = pl.pv;
+      sp.sqrtN = sqrtN;
+      sp.e_res = 0.0;
+      sp.data_norm = 1.0;
+      sp.thresh = -1.0;
+      sp.skip = nullptr;
+      sp.metric_out = nullptr;
+      sp.hier_scr = nullptr;
+      sp.hier_len = 0;
+      sp.rcp = sm.sweep->rcp;
+    }
     for (int i = 0; i < num; ++i) {
       uint32_t out_p = 0u;
       double out_v = 0.0;
       bool keep = false;
       int p_sel = 0;
       if (status == PP_STATUS_OK) {
-        const SweepResult top = cta_sweep(sp, sm.sweep);
+        const SweepResult top = cta_sweep(sm.sweep);
         if (top.p == 0) {
           status = PP_STATUS_NO_PERIOD;
         } else {
@@ -633,6 +662,8 @@ static int device_facts(DeviceFacts& f) {
 
 // 0 = hierarchical ranking sweeps where they apply (default), 1 = always fold every period directly
 static int g_fold_mode = 0;
+// optional device buffer of 8 uint64 phase-cycle counters (development aid; see pp_set_profile_buffer)
+static unsigned long long* g_prof = nullptr;
 
 static bool hier_applies(int metric, int trunc, int orth) {
   return g_fold_mode == 0 && !trunc && !orth && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
@@ -646,7 +677,7 @@ static int plan_for(int algo, int N, int pmax, int num, SmemPlan& pl) {
 // persistent grid: CTAs per SM limited by shared memory (<= 2 by registers)
 static int grid_for(const DeviceFacts& f, size_t smem_bytes, int B) {
   int per_sm = (int)((size_t)(f.smem_optin + 1024) / (smem_bytes + 1024));
-  if (per_sm > 2) per_sm = 2;
+  if (per_sm > kCtasPerSm) per_sm = kCtasPerSm;
   if (per_sm < 1) per_sm = 1;
   int g = f.sm_count * per_sm;
   if (B > 0 && g > B) g = B;
@@ -675,6 +706,10 @@ int pp_set_fold_mode(int32_t mode) {
   return 0;
 }
 int pp_get_fold_mode(void) { return g_fold_mode; }
+int pp_set_profile_buffer(void* dev_u64x8) {
+  g_prof = reinterpret_cast<unsigned long long*>(dev_u64x8);
+  return 0;
+}
 const char* pp_last_error(void) { return g_err; }
 
 int pp_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_major, int32_t* cc_minor,
@@ -703,7 +738,7 @@ size_t pp_workspace_bytes(int32_t algo, int32_t N, int32_t pmax, int32_t num, in
   if (device_facts(f)) return 0;
   SmemPlan pl;
   plan_for(algo, N, pmax, num, pl);
-  const size_t grid = (size_t)f.sm_count * 2;  // upper bound on the persistent grid
+  const size_t grid = (size_t)f.sm_count * kCtasPerSm;  // upper bound on the persistent grid
   size_t bytes = 1024;
   if (algo == PP_ALGO_MBEST) bytes += grid * (size_t)num * pl.pv * 8;
   if (orth && algo != PP_ALGO_BCORR) bytes += grid * kWarps * 2 * (size_t)pl.pv * 8;
@@ -814,7 +849,7 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   Tables tb{chain_off, chain_q, fac_off, fac};
   mbest_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,
                                                                      hier, tb, periods, powers, bases, sweeps, status,
-                                                                     slots, scr);
+                                                                     slots, scr, g_prof);
   return check_cuda(cudaGetLastError(), "mbest_kernel launch");
 }
 
