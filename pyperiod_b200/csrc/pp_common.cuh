@@ -14,13 +14,17 @@ namespace pp {
 #define PP_THREADS 256
 #endif
 #ifndef PP_CTAS
-#define PP_CTAS 3
+#define PP_CTAS 2
 #endif
 constexpr int kThreads = PP_THREADS;    // threads per CTA
 constexpr int kWarps = kThreads / 32;
-constexpr int kResBlock = 512;          // residues one warp pass keeps in registers (32 lanes x 16)
+#ifndef PP_RESBLOCK
+#define PP_RESBLOCK 256
+#endif
+constexpr int kResBlock = PP_RESBLOCK;  // residues one register tile covers (32 lanes x 8 columns)
 constexpr int kCtasPerSm = PP_CTAS;     // occupancy target of the sweep kernels (sets the register budget)
-constexpr int kSweepPad = 192;          // slack (samples) the register-tiled fold may read past c*p
+constexpr int kSweepPad = 192;          // zero samples after the window: the register tiles of the last,
+                                        // partial row may read up to 63 samples past N
 constexpr int kMaxFactors = 128;        // non-trivial divisors per period handled by M-best step 2
 
 // The dynamic shared memory of every kernel in this library starts with the staged window (xs).

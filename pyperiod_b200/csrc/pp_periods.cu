@@ -61,7 +61,7 @@ struct SmemPlan {
 __host__ __device__ inline SmemPlan make_plan(int N, int pmax, int num, bool sweep_pad, bool hier = false) {
   SmemPlan pl;
   pl.hier_len = hier ? hier_scratch_len(pmax) : 0;
-  pl.xs_len = sweep_pad ? ((N + pmax + kSweepPad + 1) & ~1) : ((N + 1) & ~1);
+  pl.xs_len = sweep_pad ? ((N + kSweepPad + 1) & ~1) : ((N + 1) & ~1);
   pl.pv = (pmax + 2) & ~1;
   pl.num = num;
   pl.skip_words = (pmax + 32) / 32;

@@ -1,14 +1,25 @@
 // pyperiod_b200 -- the period sweep: one warp per candidate period, residue sums in registers.
 //
-// Direct fold: for period p a warp keeps S_p[r] for r = rb + lane + 32 j (j < J <= 16) in registers
-// and walks the rows k of the (rows x p) rectangle.  Every shared-memory read is 32 consecutive
-// doubles (conflict-free, 2 wavefronts) and feeds exactly one DADD, so the sweep sits on the
-// shared-memory roofline (8 B per add).  Sums are sequential in n -- the order numpy
-// uses -- so MAXABS metrics are bit-exact; energies agree with the reference's BLAS norm to a few ulp.
+// Fold.  For period p a warp keeps S_p[r] for 32*J consecutive residues (r = ra + lane + 32 j) in
+// registers and walks the rows k of the (rows x p) rectangle: every shared-memory read is 32
+// consecutive doubles (conflict-free, 2 wavefronts) feeding exactly one DADD, so the sweep sits on
+// the shared-memory roofline (8 B per add).  Sums are sequential in n -- the order
+// numpy uses -- so MAXABS metrics are bit-exact; energies agree with the reference's BLAS norm to
+// a few ulp.
 //
-// Hierarchical fold (ranking sweeps only): only the "top" periods q in (pmax/2, pmax] are folded
-// from the window; S_p for every smaller candidate follows from S_2p[r] + S_2p[r + p].  Half the
-// shared-memory traffic; sums differ from the sequential ones by rounding only.
+// Two tiles per period.  With M = floor(N/p) and rr = N - M p, residues r < rr have M+1 terms and
+// the others M.  Register tiles never straddle rr: tile A = [0, rr) runs M+1 rows, tile B = [rr, p)
+// runs M rows (so the zero padding of the last row is never read), and the energy needs no per-lane
+// count logic:  E = T/M + (1/(M+1) - 1/M) * T_A  with T the plain sum of squares.
+//
+// Hierarchical fold (ranking sweeps only).  Only the "top" periods q in (pmax/2, pmax] are folded
+// from the window; S_p for every smaller candidate follows from S_2p[r] + S_2p[r + p].  A top
+// q = g * 2^L (L <= 3) is folded at base period g with 2^L accumulator sets selected by
+// (row mod 2^L); pairwise in-register adds give q/2 .. g, and if g is still even the chain goes on
+// through a small per-warp scratch.  Because g divides every level period, the A/B boundary in the
+// base residue (rr = N mod g) is the same for all levels; a level only differs in how many leading
+// sets count as "M+1 terms".  Half the shared-memory traffic of the direct sweep; sums differ from
+// the sequential ones by rounding only.
 //
 // Candidates are ranked by the squared metric (energy, or energy / p compared by cross
 // multiplication); the square root and divisions are taken once, for the winner.
@@ -20,6 +31,8 @@
 namespace pp {
 
 enum PassMode { kPassEnergy = 0, kPassEnergyTail = 1, kPassMaxAbs = 2, kPassStore = 3 };
+
+constexpr int kRcpTab = 256;
 
 // Lives in shared memory (one per CTA), written by thread 0 before a sweep.
 struct SweepParams {
@@ -42,13 +55,6 @@ struct SweepParams {
   int hier_len;
   const double* rcp;     // shared table rcp[m] = 1.0 / m for m < kRcpTab (energy weights without a division)
 };
-
-constexpr int kRcpTab = 256;
-
-// 1 / m: table for the small row counts every large period has, a real division otherwise
-__device__ __forceinline__ double rcp_of(const double* rcp, int m) {
-  return m < kRcpTab ? rcp[m] : 1.0 / (double)m;
-}
 
 struct SweepResult {
   double val;  // metric value of the winner (norm / gamma norm / max |S| / imposed norm)
@@ -82,11 +88,14 @@ __device__ __forceinline__ double key_to_value(int metric, double key, int p, do
 struct RankCtx {
   const uint32_t* skip;
   double* metric_out;
+  const double* rcp;
   double sqrtN;
   int metric;
+  int N;
+  int pmin;
 };
 __device__ __forceinline__ RankCtx rank_ctx(const SweepParams* sp) {
-  return RankCtx{sp->skip, sp->metric_out, sp->sqrtN, sp->metric};
+  return RankCtx{sp->skip, sp->metric_out, sp->rcp, sp->sqrtN, sp->metric, sp->N, sp->pmin};
 }
 
 __device__ __forceinline__ void consider(const RankCtx& rc, double key, int p, Best& best) {
@@ -100,132 +109,123 @@ __device__ __forceinline__ void consider(const RankCtx& rc, double key, int p, B
   }
 }
 
-// a += v*v on the lanes where x < y: one ISETP and one predicated DFMA
-__device__ __forceinline__ void fma_sq_if_lt(double& a, double v, int x, int y) {
-  asm("{\n\t.reg .pred p;\n\tsetp.lt.s32 p, %2, %3;\n\t@p fma.rn.f64 %0, %1, %1, %0;\n\t}"
-      : "+d"(a)
-      : "d"(v), "r"(x), "r"(y));
+// 1 / m: table for the small row counts every large period has, a real division otherwise
+__device__ __forceinline__ double rcp_of(const double* rcp, int m) {
+  return m < kRcpTab ? rcp[m] : 1.0 / (double)m;
 }
 
-// acc[j] += row[32 j] for j < J, with the loads of a batch issued together before the adds
-// (written out so the compiler keeps several shared-memory loads in flight per warp)
+// Register tiles are deliberately small and come in exactly two shapes -- kTileCols columns for the
+// body of a residue range, one column for what is left -- so the hot loops are a few hundred bytes
+// of code that every warp of the SM shares.  (A dispatch over 12 tile widths, tried first, lost
+// 30 % to instruction-fetch stalls; predicated partial tiles made the compiler spill.)
+constexpr int kTileCols = 4;
+
+// acc[j] += row[32 j]: the loads of a row are issued together, then the adds
 template <int J>
 __device__ __forceinline__ void add_row(double (&acc)[J], const double* __restrict__ row) {
-  constexpr int BATCH = 8;
+  double t[J];
 #pragma unroll
-  for (int j0 = 0; j0 < J; j0 += BATCH) {
-    double t[BATCH];
+  for (int j = 0; j < J; ++j) t[j] = row[32 * j];
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u)
-      if (j0 + u < J) t[u] = row[32 * (j0 + u)];
+  for (int j = 0; j < J; ++j) acc[j] += t[j];
+}
+
+// acc[j] = sum over `rows` rows (stride p) of row[32 j], added in row order; rows >= 1
+template <int J>
+__device__ __forceinline__ void fold_rows(double (&acc)[J], const double* __restrict__ ptr, int p, int rows) {
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u)
-      if (j0 + u < J) acc[j0 + u] += t[u];
+  for (int j = 0; j < J; ++j) acc[j] = ptr[32 * j];
+#pragma unroll 4
+  for (int k = 1; k < rows; ++k) {
+    ptr += p;
+    add_row<J>(acc, ptr);
   }
 }
 
 // ------------------------------------------------------------------------------------------
-// direct fold of one residue block
+// direct fold
 // ------------------------------------------------------------------------------------------
-// T = sum of S^2 over valid residues, A = the same over residues < r0 (those with one more term),
-// C = sum of S_r * x[M p + r] (trunc + IMPOSED only); for MAXABS T carries max |S_r|.
-template <int J, int MODE>
-__device__ __forceinline__ void block_pass(const double* __restrict__ xs, int p, int rb, int rows, int r0, int M,
-                                           bool trunc, double& T, double& A, double& C, double* __restrict__ gsS,
-                                           double* __restrict__ gsV) {
+// One register tile of period p: residues [ra, ra + nres), nres <= 32 J, `rows` rows.
+//   Energy / EnergyTail: T += sum S^2;  EnergyTail also C += sum S_r * x[tail_off + r]
+//   MaxAbs: T = max(T, |S_r|)
+//   Store:  gsS[r] = full-N sum, gsV[r] = S_r * inv   (orthogonalised sweeps)
+template <int J, bool PARTIAL, int MODE>
+__device__ __forceinline__ void tile_pass(const double* __restrict__ xs, int p, int ra, int nres, int rows,
+                                          int tail_off, bool add_tail, double inv, double& T, double& C,
+                                          double* __restrict__ gsS, double* __restrict__ gsV) {
   const int lane = threadIdx.x & 31;
-  const double* ptr = xs + rb + lane;
   double acc[J];
-#pragma unroll
-  for (int j = 0; j < J; ++j) acc[j] = ptr[32 * j];
-  if (J <= 4) {
-#pragma unroll 4
-    for (int k = 1; k < rows; ++k) {
-      ptr += p;
-      add_row<J>(acc, ptr);
-    }
-  } else {
-#pragma unroll 1
-    for (int k = 1; k < rows; ++k) {
-      ptr += p;
-      add_row<J>(acc, ptr);
-    }
-  }
-  const int tail_off = M * p;
+  fold_rows<J>(acc, xs + ra + lane, p, rows);
   if (MODE == kPassEnergy || MODE == kPassEnergyTail) {
-    // lanes past p hold sums of the next row's samples; only the last two registers can (J gap <= 2)
+    // lanes past the tile end hold sums of other residues (only possible in a partial tile)
+    if (PARTIAL) {
 #pragma unroll
-    for (int j = (J > 2 ? J - 2 : 0); j < J; ++j)
-      if (rb + lane + 32 * j >= p) acc[j] = 0.0;
+      for (int j = 0; j < J; ++j)
+        if (lane + 32 * j >= nres) acc[j] = 0.0;
+    }
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const double s = acc[j];
-      T = fma(s, s, T);
-      fma_sq_if_lt(A, s, lane, r0 - (rb + 32 * j));
-      if (MODE == kPassEnergyTail) C = fma(s, xs[tail_off + rb + lane + 32 * j], C);  // zero pad beyond N
+      T = fma(acc[j], acc[j], T);
+      if (MODE == kPassEnergyTail) C = fma(acc[j], xs[tail_off + ra + lane + 32 * j], C);
     }
   } else if (MODE == kPassMaxAbs) {
 #pragma unroll
     for (int j = 0; j < J; ++j)
-      if (rb + lane + 32 * j < p) T = fmax(T, fabs(acc[j]));
-  } else {  // kPassStore: full-N sums and (approximate) means to the warp scratch
-    const double invHi = 1.0 / (double)(M + 1), invLo = 1.0 / (double)M;
+      if (lane + 32 * j < nres) T = fmax(T, fabs(acc[j]));
+  } else {
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const int r = rb + lane + 32 * j;
-      if (r < p) {
-        const double s = acc[j];
-        if (trunc) {
-          gsS[r] = s + xs[tail_off + r];
-          gsV[r] = s * invLo;
-        } else {
-          gsS[r] = s;
-          gsV[r] = s * (r < r0 ? invHi : invLo);
-        }
+      if (lane + 32 * j < nres) {
+        const int r = ra + lane + 32 * j;
+        gsS[r] = add_tail ? acc[j] + xs[tail_off + r] : acc[j];
+        gsV[r] = acc[j] * inv;
       }
     }
   }
 }
 
-#define PP_J_DISPATCH(MODE, JN, ...)                              \
-  do {                                                            \
-    switch (JN) {                                                 \
-      case 1: block_pass<1, MODE>(__VA_ARGS__); break;            \
-      case 2: block_pass<2, MODE>(__VA_ARGS__); break;            \
-      case 3: block_pass<3, MODE>(__VA_ARGS__); break;            \
-      case 4: block_pass<4, MODE>(__VA_ARGS__); break;            \
-      case 5: block_pass<5, MODE>(__VA_ARGS__); break;            \
-      case 6: block_pass<6, MODE>(__VA_ARGS__); break;            \
-      case 7: block_pass<7, MODE>(__VA_ARGS__); break;            \
-      case 8: block_pass<8, MODE>(__VA_ARGS__); break;            \
-      case 9: case 10: block_pass<10, MODE>(__VA_ARGS__); break;  \
-      case 11: case 12: block_pass<12, MODE>(__VA_ARGS__); break; \
-      case 13: case 14: block_pass<14, MODE>(__VA_ARGS__); break; \
-      default: block_pass<16, MODE>(__VA_ARGS__); break;          \
-    }                                                             \
-  } while (0)
+// residues [lo, hi) of period p: tiles of kTileCols columns, then single columns (the last one masked)
+template <int MODE>
+__device__ __forceinline__ void fold_range(const double* xs, int p, int lo, int hi, int rows, int tail_off,
+                                           bool add_tail, double inv, double& T, double& C, double* gsS,
+                                           double* gsV) {
+  int ra = lo;
+  for (; ra + 32 * kTileCols <= hi; ra += 32 * kTileCols)
+    tile_pass<kTileCols, false, MODE>(xs, p, ra, 32 * kTileCols, rows, tail_off, add_tail, inv, T, C, gsS, gsV);
+  for (; ra < hi; ra += 32)
+    tile_pass<1, true, MODE>(xs, p, ra, min(hi - ra, 32), rows, tail_off, add_tail, inv, T, C, gsS, gsV);
+}
 
 // Ranking key of one period, computed by one warp; identical in all lanes.
 template <int MODE>
-__device__ __noinline__ double warp_period_key(const SweepParams* sp, int p) {
+__device__ __forceinline__ double warp_period_key(const SweepParams* sp, int p) {
   const int lane = threadIdx.x & 31;
   const int N = sp->N;
   const bool trunc = sp->trunc != 0;
   const double* xs = staged_window();
-  const int M = N / p, r0 = N - M * p;
-  const int rows = trunc ? M : (M + (r0 ? 1 : 0));
-  double T = 0.0, A = 0.0, C = 0.0;
+  const int M = N / p, rr = N - M * p;
+  const int tail_off = M * p;
+  const double m = (double)M;
+  double TA = 0.0, TB = 0.0, C = 0.0;
   double* gsS = nullptr;
   double* gsV = nullptr;
   if (MODE == kPassStore) {
     gsS = sp->warp_scr + (size_t)(threadIdx.x >> 5) * 2 * sp->pv;
     gsV = gsS + sp->pv;
   }
-  for (int rb = 0; rb < p; rb += kResBlock) {
-    const int jn = (min(p - rb, kResBlock) + 31) >> 5;
-    PP_J_DISPATCH(MODE, jn, xs, p, rb, rows, r0, M, trunc, T, A, C, gsS, gsV);
+  // tile A: residues with a sample in the last, partial row
+  if (rr > 0) {
+    if (MODE == kPassMaxAbs) {
+      fold_range<MODE>(xs, p, 0, rr, M + 1, tail_off, false, 0.0, TA, C, gsS, gsV);
+    } else {
+      fold_range<MODE>(xs, p, 0, rr, trunc ? M : M + 1, tail_off, trunc, trunc ? 1.0 / m : 1.0 / (double)(M + 1), TA,
+                       C, gsS, gsV);
+    }
   }
-  if (MODE == kPassMaxAbs) return warp_max(T);
+  // tile B never has tail samples (and must not read past the short zero pad)
+  fold_range<(MODE == kPassEnergyTail ? kPassEnergy : MODE)>(xs, p, rr, p, M, tail_off, false, 1.0 / m,
+                                                             (MODE == kPassMaxAbs ? TA : TB), C, gsS, gsV);
+  if (MODE == kPassMaxAbs) return warp_max(TA);
 
   double energy, dot;
   if (MODE == kPassStore) {
@@ -234,23 +234,21 @@ __device__ __noinline__ double warp_period_key(const SweepParams* sp, int p) {
     double e = 0.0, d = 0.0;
     for (int r = lane; r < p; r += 32) {
       const double v = gsV[r];
-      e = fma((double)(M + (r < r0 ? 1 : 0)) * v, v, e);
+      e = fma((double)(M + (r < rr ? 1 : 0)) * v, v, e);
       d = fma(v, gsS[r], d);
     }
     energy = warp_sum(e);
     dot = warp_sum(d);
     __syncwarp();
+  } else if (trunc) {
+    // mean = S / M on every residue, counts over all N:  sum cnt * mean^2 = (M (TA + TB) + TA) / M^2
+    const double T = TA + TB;
+    energy = warp_sum(fma(m, T, TA) / (m * m));
+    dot = (MODE == kPassEnergyTail) ? warp_sum((T + C) / m) : energy;
   } else {
-    const double m = (double)M;
-    if (trunc) {
-      // mean = S / M on every residue, counts over all N:  sum cnt * mean^2 = (M T + A) / M^2
-      energy = warp_sum(fma(m, T, A) / (m * m));
-      dot = (MODE == kPassEnergyTail) ? warp_sum((T + C) / m) : energy;
-    } else {
-      const double w_lo = 1.0 / m, w_diff = 1.0 / (double)(M + 1) - w_lo;
-      energy = warp_sum(fma(w_diff, A, w_lo * T));
-      dot = energy;
-    }
+    const double w_lo = 1.0 / m, w_diff = 1.0 / (double)(M + 1) - w_lo;
+    energy = warp_sum(fma(w_diff, TA, w_lo * (TA + TB)));
+    dot = energy;
   }
   if (sp->metric == PP_METRIC_IMPOSED) {
     const double e_res = sp->e_res, sqrtN = sp->sqrtN;
@@ -270,26 +268,23 @@ __device__ __forceinline__ double warp_period_key_any(const SweepParams* sp, int
 // ------------------------------------------------------------------------------------------
 // hierarchical fold
 // ------------------------------------------------------------------------------------------
-// A top q = g * 2^L (L <= 3) is folded at base period g with 2^L accumulator sets selected by
-// (row mod 2^L): set s holds S_q[r + s g].  Pairwise in-register adds then give the sums of
-// q/2, q/4, .. g.  If g is still even the chain continues through a small per-warp scratch.
 __host__ __device__ inline int hier_scratch_len(int pmax) { return ((((pmax >> 3) + 2) * 3) / 2 + 3) & ~1; }
 
 // compile-time recursion over the levels l = LV .. 0 (keeps every accumulator index static).
-// Level energy = w_lo * T + w_diff * A (T over all residues, A over residues < r0).
+// For level l the tile contributes q_s = sum_j acc[s][j]^2 of each of its 2^l sets to T[l], and to
+// A[l] when the set index is below s_in[l] (the sets whose residues have one more term).
 template <int L, int J, int LV>
 struct hier_levels {
-  static __device__ __forceinline__ void run(double (&acc)[1 << L][J], int lane, int rb, int g,
-                                             const int (&r0)[L + 1], double (&T)[L + 1], double (&A)[L + 1]) {
+  static __device__ __forceinline__ void run(double (&acc)[1 << L][J], const int (&s_in)[L + 1], double (&T)[L + 1],
+                                             double (&A)[L + 1]) {
     constexpr int sets = 1 << LV;
 #pragma unroll
     for (int s = 0; s < sets; ++s) {
+      double q = 0.0;
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        const double v = acc[s][j];
-        T[LV] = fma(v, v, T[LV]);
-        fma_sq_if_lt(A[LV], v, lane, r0[LV] - (rb + 32 * j + s * g));
-      }
+      for (int j = 0; j < J; ++j) q = fma(acc[s][j], acc[s][j], q);
+      T[LV] += q;
+      if (s < s_in[LV]) A[LV] += q;  // warp-uniform
     }
     if constexpr (LV > 0) {
       constexpr int half = sets >> 1;
@@ -297,38 +292,23 @@ struct hier_levels {
       for (int s = 0; s < half; ++s)
 #pragma unroll
         for (int j = 0; j < J; ++j) acc[s][j] += acc[s + half][j];
-      hier_levels<L, J, LV - 1>::run(acc, lane, rb, g, r0, T, A);
+      hier_levels<L, J, LV - 1>::run(acc, s_in, T, A);
     }
   }
 };
 
-// One residue block [rb, rb + 32 J) of a top q = g * 2^L: 2^L accumulator sets of J registers.
-// The caller picks the smallest available J >= needed with a gap of at most 2 registers, so only
-// the last two registers of a set can hold lanes past g.
-template <int L, int J>
-__device__ __forceinline__ void hier_pass(const double* __restrict__ xs, int rb, int g, int rows,
-                                          const int (&r0)[L + 1], double (&T)[L + 1], double (&A)[L + 1],
+// One register tile of a top q = g * 2^L: base residues [ra, ra + nres), nres <= 32 J, `rows` base
+// rows distributed over 2^L accumulator sets by (row mod 2^L).
+template <int L, int J, bool PARTIAL>
+__device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, int ra, int nres, int rows,
+                                          const int (&s_in)[L + 1], double (&T)[L + 1], double (&A)[L + 1],
                                           double* scr) {
   constexpr int S = 1 << L;
   const int lane = threadIdx.x & 31;
-  const double* ptr = xs + rb + lane;
+  const double* ptr = xs + ra + lane;
   double acc[S][J];
   if (S == 1) {
-#pragma unroll
-    for (int j = 0; j < J; ++j) acc[0][j] = ptr[32 * j];
-    if (J <= 4) {
-#pragma unroll 4
-      for (int k = 1; k < rows; ++k) {
-        ptr += g;
-        add_row<J>(acc[0], ptr);
-      }
-    } else {
-#pragma unroll 1
-      for (int k = 1; k < rows; ++k) {
-        ptr += g;
-        add_row<J>(acc[0], ptr);
-      }
-    }
+    fold_rows<J>(acc[0], ptr, g, rows);
   } else {
 #pragma unroll
     for (int s = 0; s < S; ++s)
@@ -351,81 +331,66 @@ __device__ __forceinline__ void hier_pass(const double* __restrict__ xs, int rb,
       }
     }
   }
+  if (PARTIAL) {
 #pragma unroll
-  for (int j = (J > 2 ? J - 2 : 0); j < J; ++j) {
-    if (rb + lane + 32 * j >= g) {
+    for (int j = 0; j < J; ++j) {
+      if (lane + 32 * j >= nres) {
 #pragma unroll
-      for (int s = 0; s < S; ++s) acc[s][j] = 0.0;
+        for (int s = 0; s < S; ++s) acc[s][j] = 0.0;
+      }
     }
   }
-  hier_levels<L, J, L>::run(acc, lane, rb, g, r0, T, A);
+  hier_levels<L, J, L>::run(acc, s_in, T, A);
   if (scr != nullptr) {
 #pragma unroll
     for (int j = 0; j < J; ++j)
-      if (rb + lane + 32 * j < g) scr[rb + lane + 32 * j] = acc[0][j];
+      if (lane + 32 * j < nres) scr[ra + lane + 32 * j] = acc[0][j];
   }
 }
 
-#define PP_HIER_CASE(L, J) \
-  case J: hier_pass<L, J>(xs, rb, g, rows, r0, T, A, scr); break;
-
+// register columns per accumulator set of a hierarchical tile: at most 16 accumulators per lane
 template <int L>
-__device__ __forceinline__ void hier_top_fold(const double* xs, int g, int rows, const int (&r0)[L + 1],
-                                              double (&T)[L + 1], double (&A)[L + 1], double* scr) {
-  constexpr int JMAX = (kResBlock / 32) >> L;  // 16, 8, 4, 2 registers per accumulator set
-  for (int rb = 0; rb < g; rb += 32 * JMAX) {
-    int jn = (min(g - rb, 32 * JMAX) + 31) >> 5;
-    if (jn > 8) jn = (jn + 1) & ~1;  // even sizes only above 8
-    if constexpr (JMAX == 2) {
-      switch (jn) {
-        PP_HIER_CASE(L, 1)
-        default: hier_pass<L, 2>(xs, rb, g, rows, r0, T, A, scr); break;
-      }
-    } else if constexpr (JMAX == 4) {
-      switch (jn) {
-        PP_HIER_CASE(L, 1) PP_HIER_CASE(L, 2) PP_HIER_CASE(L, 3)
-        default: hier_pass<L, 4>(xs, rb, g, rows, r0, T, A, scr); break;
-      }
-    } else if constexpr (JMAX == 8) {
-      switch (jn) {
-        PP_HIER_CASE(L, 1) PP_HIER_CASE(L, 2) PP_HIER_CASE(L, 3) PP_HIER_CASE(L, 4)
-        PP_HIER_CASE(L, 5) PP_HIER_CASE(L, 6) PP_HIER_CASE(L, 7)
-        default: hier_pass<L, 8>(xs, rb, g, rows, r0, T, A, scr); break;
-      }
-    } else {
-      switch (jn) {
-        PP_HIER_CASE(L, 1) PP_HIER_CASE(L, 2) PP_HIER_CASE(L, 3) PP_HIER_CASE(L, 4)
-        PP_HIER_CASE(L, 5) PP_HIER_CASE(L, 6) PP_HIER_CASE(L, 7) PP_HIER_CASE(L, 8)
-        PP_HIER_CASE(L, 10) PP_HIER_CASE(L, 12) PP_HIER_CASE(L, 14)
-        default: hier_pass<L, 16>(xs, rb, g, rows, r0, T, A, scr); break;
-      }
-    }
-  }
+struct hier_cols {
+  static constexpr int value = (L == 3) ? 2 : kTileCols;
+};
+
+// base residues [lo, hi) of a top: tiles of J columns, then single columns (the last one masked)
+template <int L>
+__device__ __forceinline__ void hier_range(const double* xs, int g, int lo, int hi, int rows, const int (&s_in)[L + 1],
+                                           double (&T)[L + 1], double (&A)[L + 1], double* scr) {
+  constexpr int J = hier_cols<L>::value;
+  int ra = lo;
+  for (; ra + 32 * J <= hi; ra += 32 * J) hier_tile<L, J, false>(xs, g, ra, 32 * J, rows, s_in, T, A, scr);
+  for (; ra < hi; ra += 32) hier_tile<L, 1, true>(xs, g, ra, min(hi - ra, 32), rows, s_in, T, A, scr);
 }
 
 // One top period q = g * 2^L and every candidate q / 2^k below it.  Non-trunc, non-orth, NORM / GAMMA.
 template <int L>
-__device__ __noinline__ Best warp_hier_top_L(const SweepParams* sp, int g, double* scr, Best best) {
+__device__ __forceinline__ Best warp_hier_top_L(RankCtx rc, int g, double* scr, Best best) {
   const int lane = threadIdx.x & 31;
-  const int N = sp->N;
-  const int pmin = sp->pmin;
-  const RankCtx rc = rank_ctx(sp);
-  const double* rcp = sp->rcp;
-  // rows of the level periods: floor(N / (g 2^i)) = floor(N / g) >> i
-  const int M0 = N / g;
-  int r0[L + 1];
+  const int N = rc.N;
+  const double* xs = staged_window();
+  const int M0 = N / g;        // complete base rows
+  const int rr = N - M0 * g;   // base residues below rr have one more row
+  // level l (period g 2^l): rows M0 >> l; the first s0 = M0 mod 2^l sets have one more term on every
+  // residue, set s0 only on base residues < rr
+  int s_inA[L + 1], s_inB[L + 1];
 #pragma unroll
-  for (int i = 0; i <= L; ++i) r0[i] = N - (M0 >> i) * (g << i);
-  const int rows = M0 + (r0[0] ? 1 : 0);
-  const bool chain = (L == 3) && !(g & 1) && (g >> 1) >= pmin;
+  for (int i = 0; i <= L; ++i) {
+    s_inB[i] = M0 & ((1 << i) - 1);
+    s_inA[i] = s_inB[i] + 1;
+  }
+  const bool chain = (L == 3) && !(g & 1) && (g >> 1) >= rc.pmin;
+  double* out = chain ? scr : nullptr;
   double T[L + 1], A[L + 1];
 #pragma unroll
   for (int i = 0; i <= L; ++i) T[i] = A[i] = 0.0;
-  hier_top_fold<L>(staged_window(), g, rows, r0, T, A, chain ? scr : nullptr);
+  if (rr > 0) hier_range<L>(xs, g, 0, rr, M0 + 1, s_inA, T, A, out);
+  hier_range<L>(xs, g, rr, g, M0, s_inB, T, A, out);
 #pragma unroll
   for (int i = 0; i <= L; ++i) {
     const int M = M0 >> i;
-    const double w_lo = rcp_of(rcp, M), w_diff = rcp_of(rcp, M + 1) - w_lo;
+    const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
     consider(rc, warp_sum(fma(w_diff, A[i], w_lo * T[i])), g << i, best);
   }
   if (chain) {
@@ -433,10 +398,10 @@ __device__ __noinline__ Best warp_hier_top_L(const SweepParams* sp, int g, doubl
     double* src = scr;
     double* dst = scr + ((g + 1) & ~1);
     int h = g;
-    while (!(h & 1) && (h >> 1) >= pmin) {
+    while (!(h & 1) && (h >> 1) >= rc.pmin) {
       const int h2 = h >> 1;
       const int M = N / h2, r0h = N - M * h2;
-      const double w_lo = rcp_of(rcp, M), w_diff = rcp_of(rcp, M + 1) - w_lo;
+      const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
       double t = 0.0, a = 0.0;
       for (int r = lane; r < h2; r += 32) {
         const double v = src[r] + src[r + h2];
@@ -456,15 +421,15 @@ __device__ __noinline__ Best warp_hier_top_L(const SweepParams* sp, int g, doubl
   return best;
 }
 
-__device__ __forceinline__ void warp_hier_top(const SweepParams* sp, int q, double* scr, Best& best) {
+__device__ __forceinline__ Best warp_hier_top(const RankCtx& rc, int q, double* scr, Best best) {
   int L = min(__ffs(q) - 1, 3);
-  while (L > 0 && (q >> L) < sp->pmin) --L;
+  while (L > 0 && (q >> L) < rc.pmin) --L;
   const int g = q >> L;
   switch (L) {
-    case 0: best = warp_hier_top_L<0>(sp, g, scr, best); break;
-    case 1: best = warp_hier_top_L<1>(sp, g, scr, best); break;
-    case 2: best = warp_hier_top_L<2>(sp, g, scr, best); break;
-    default: best = warp_hier_top_L<3>(sp, g, scr, best); break;
+    case 0: return warp_hier_top_L<0>(rc, g, scr, best);
+    case 1: return warp_hier_top_L<1>(rc, g, scr, best);
+    case 2: return warp_hier_top_L<2>(rc, g, scr, best);
+    default: return warp_hier_top_L<3>(rc, g, scr, best);
   }
 }
 
@@ -489,9 +454,9 @@ __device__ __forceinline__ void sweep_shared_init(SweepShared* sh) {
 //                             (Periods.py:512-515).
 //   first-hit mode (thresh >= 0): lowest p whose metric > thresh; warps stop once their next
 //                             candidate lies above the current hit (Periods.py:273-286).
-// sh->params must have been written and a CTA barrier passed.  All threads call; the result is valid
-// in all threads.  Contains CTA barriers.  Kept out of line so the caller's live state does not
-// compete with the fold's registers.
+// sh->params must have been written by thread 0.  All threads call; the result is valid in all
+// threads.  Contains CTA barriers.  Kept out of line so the caller's live state does not compete
+// with the fold's registers.
 __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   const SweepParams* sp = &sh->params;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -500,7 +465,8 @@ __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
     sh->hit_p = 0x7fffffff;
   }
   __syncthreads();  // also publishes params written by thread 0 just before the call
-  const int metric = sp->metric;
+  const RankCtx rc = rank_ctx(sp);
+  const int metric = rc.metric;
   const int pmin = sp->pmin, pmax = sp->pmax;
   const double thresh = sp->thresh;
   const bool first_hit = thresh >= 0.0;
@@ -532,10 +498,9 @@ __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
       else if ((idx -= cnt[0]) < cnt[1]) q = first[1] + idx * 4;
       else if ((idx -= cnt[1]) < cnt[2]) q = first[2] + idx * 8;
       else q = first[3] + (idx - cnt[2]) * 8;
-      warp_hier_top(sp, q, scr, best);
+      best = warp_hier_top(rc, q, scr, best);
     }
   } else {
-    const RankCtx rc = rank_ctx(sp);
     const int ncand = pmax - pmin + 1;
     while (true) {
       int idx = 0;
@@ -549,7 +514,7 @@ __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
       }
       const double key = warp_period_key_any(sp, p);
       if (first_hit) {
-        if (sp->metric_out != nullptr && lane == 0) sp->metric_out[p] = key;
+        if (rc.metric_out != nullptr && lane == 0) rc.metric_out[p] = key;
         if (key > thresh) {
           if (best.p == 0 || p < best.p) {
             best.p = p;
@@ -580,7 +545,7 @@ __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
     }
   }
   SweepResult out{0.0, res.p};
-  if (res.p != 0) out.val = key_to_value(metric, res.key, res.p, sp->sqrtN);
+  if (res.p != 0) out.val = key_to_value(metric, res.key, res.p, rc.sqrtN);
   __syncthreads();  // wkey/wp may be rewritten by the next sweep
   return out;
 }
