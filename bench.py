@@ -157,7 +157,8 @@ def workload_config(b_per_gpu: int, n_gpus: int, where: str):
     return {"workload": f"config 3: Periods.m_best(num={NUM}, max_length={PMAX}) on hop-{HOP} windows of N={N_WIN} "
                         f"cut from a synthetic multi-tone stream (3 tones + noise per 65,536-sample segment)",
             "windows_per_gpu_per_step": b_per_gpu, "windows_per_step": b_per_gpu * n_gpus, "N": N_WIN, "hop": HOP,
-            "Pmax": PMAX, "num": NUM, "sharding": f"{n_gpus} independent stream shards, no data-path collective",
+            "Pmax": PMAX, "num": NUM, "sharding": f"{n_gpus} independent stream shards, no data-path collective; compact results "
+                        f"gathered to rank 0 each step" if n_gpus > 1 else "single GPU",
             "l2": "input stream per step (>= 0.5 GB) is larger than the 126 MB L2", "inputs": where}
 
 
@@ -165,7 +166,7 @@ def workload_config(b_per_gpu: int, n_gpus: int, where: str):
 def run_b200(args, rank: int, world: int, local_rank: int):
     import torch
     import torch.distributed as dist
-    from pyperiod_b200 import Periods, _lib, synth
+    from pyperiod_b200 import Periods, _lib, sharding, synth
 
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -200,7 +201,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     algo = Periods(device=dev)
 
     def step_device():
-        return algo.m_best(dev_windows, num=NUM, max_length=PMAX)
+        r = algo.m_best(dev_windows, num=NUM, max_length=PMAX)
+        if world > 1:  # the only collective: compact periods/powers/status to rank 0 (NCCL over NVLink)
+            sharding.gather_compact(r.periods, r.powers, r.status, B * world, dst=0)
+        return r
 
     def step_e2e():
         return algo.m_best(host_windows, num=NUM, max_length=PMAX)   # H2D + kernel + D2H to numpy
