@@ -171,6 +171,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
+            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.windows
     assert B % 128 == 0, "--windows must be a multiple of 128 (segment alignment)"
