@@ -46,6 +46,8 @@ extern "C" {
 #define PP_STATUS_OVERFLOW 2    /* more accepted periods than kmax (small_to_large)            */
 #define PP_STATUS_SINGULAR 3    /* Gram matrix not positive definite (reference: LinAlgError)  */
 #define PP_STATUS_GUARD 4       /* iteration guard tripped                                     */
+#define PP_STATUS_TOO_LARGE 5   /* dictionary has more rows than rmax                          */
+#define PP_STATUS_ZERO_INPUT 6  /* sum |x| <= 1e-16: the reference returns a canned result     */
 
 /* workspace selector for pp_workspace_bytes */
 #define PP_ALGO_SWEEP 0
@@ -140,6 +142,34 @@ int pp_best_correlation(const double *x, int64_t ldx, int32_t B, int32_t N, int3
                         double ratio, int32_t trunc, int32_t orth, const int32_t *chain_off,
                         const int32_t *chain_q, int32_t table_pmax, uint32_t *periods, double *powers,
                         double *bases, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- QOPeriods.find_periods, default branch (QOPeriods.py:313-643, 743-852) ---------------
+ * Per window up to `num` rounds: gamma-norm sweep of the residual over [pmin, pmax]
+ * (trunc = the instance's trunc_to_integer_multiple, orthogonalize False, :470-478); dictionary
+ * rows per period = sum of phi over newly seen divisors (:830-840, a repeated period gets 0 and
+ * then contributes all its rows, :972); normal equations against the ORIGINAL data solved by
+ * Cholesky (reference: LU, np.linalg.solve); residual = data - reconstruction; stop when
+ * rms(reconstruction) <= rms(data) * thresh (:391), in which case the last period is not
+ * reported (:585-588).  A non-positive pivot (reference: LinAlgError) or more than rmax rows keeps
+ * the previous round's outputs (status PP_STATUS_SINGULAR / PP_STATUS_TOO_LARGE).
+ * phi: device int32 table of Euler's totient for 0..table_pmax.
+ * Outputs: periods u32[B,num] (found order, duplicates possible), norms f64[B,num], n_periods[B];
+ * dictionary dict_q/dict_keep i32[B,num] in insertion order with n_dict[B]; weights f64[B,rmax]
+ * with n_weights[B]; res f64[B,N] (nullable); status[B]. */
+size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax);
+int pp_qo_find_periods(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t num, double thresh,
+                       int32_t pmin, int32_t pmax, int32_t trunc, const int32_t *phi, int32_t table_pmax,
+                       int32_t rmax, uint32_t *periods, double *norms, int32_t *n_periods, int32_t *dict_q,
+                       int32_t *dict_keep, int32_t *n_dict, int32_t *n_weights, double *weights, double *res,
+                       int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- get_subspaces + solve_quadratic for given periods (QOPeriods.py:743-852; used by
+ *      RamanujanPeriods.find_periods_with_weights, RamanujanPeriods.py:106-112) ---------------
+ * periods i32[B,kmax] with nper[B] valid entries each, in the caller's order. */
+int pp_qo_solve(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t kmax, const int32_t *periods,
+                const int32_t *nper, int32_t pmax, const int32_t *phi, int32_t table_pmax, int32_t rmax,
+                int32_t *dict_q, int32_t *dict_keep, int32_t *n_dict, int32_t *n_weights, double *weights,
+                double *res, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- roofline denominators measured live -----------------------
  * kind 0: shared-memory load bandwidth, out_host[0] = bytes/s over the whole chip;

@@ -8,7 +8,7 @@ generators used by the tests and the benchmark.
 """
 from . import synth  # noqa: F401  (numpy only)
 
-__all__ = ["Periods", "BatchResult", "synth"]
+__all__ = ["Periods", "BatchResult", "QOPeriods", "QOBatchResult", "RamanujanPeriods", "synth"]
 
 
 def __getattr__(name):
@@ -16,4 +16,10 @@ def __getattr__(name):
     if name in ("Periods", "BatchResult"):
         from . import periods as _p
         return getattr(_p, name)
+    if name in ("QOPeriods", "QOBatchResult"):
+        from . import qoperiods as _q
+        return getattr(_q, name)
+    if name == "RamanujanPeriods":
+        from . import ramanujan as _r
+        return _r.RamanujanPeriods
     raise AttributeError(name)

@@ -15,6 +15,7 @@ ABI_VERSION = 1
 
 METRIC_NORM, METRIC_GAMMA, METRIC_MAXABS, METRIC_IMPOSED = 0, 1, 2, 3
 STATUS_OK, STATUS_NO_PERIOD, STATUS_OVERFLOW, STATUS_SINGULAR, STATUS_GUARD = 0, 1, 2, 3, 4
+STATUS_TOO_LARGE, STATUS_ZERO_INPUT = 5, 6
 ALGO_SWEEP, ALGO_MBEST, ALGO_S2L, ALGO_BCORR, ALGO_QO, ALGO_RAMANUJAN = 0, 1, 2, 3, 4, 5
 
 _p = C.c_void_p
@@ -43,6 +44,11 @@ SIGNATURES = {
     "pp_best_correlation": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _f64, _i32, _i32, _p, _p, _i32,
                                       _p, _p, _p, _p, _p, _sz, _p]),
     "pp_microbench": (C.c_int, [_i32, _i32, _p]),
+    "pp_qo_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "pp_qo_find_periods": (C.c_int, [_p, _i64, _i32, _i32, _i32, _f64, _i32, _i32, _i32, _p, _i32, _i32,
+                                     _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "pp_qo_solve": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _i32,
+                              _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 _lib = None

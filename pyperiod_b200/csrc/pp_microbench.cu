@@ -6,9 +6,9 @@
 
 #include "../../include/pyperiod_b200.h"
 
+#include "pp_host.cuh"
+
 namespace pp {
-int fail(int code, const char* fmt, const char* a);
-int check_cuda(cudaError_t e, const char* what);
 
 // Every lane streams conflict-free 16-byte shared-memory loads (4 wavefronts per warp
 // instruction = 512 B) and folds them with integer XORs, so only the LSU/crossbar is loaded.

@@ -12,6 +12,7 @@
 #include "../../include/pyperiod_b200.h"
 #include "pp_common.cuh"
 #include "pp_sweep.cuh"
+#include "pp_host.cuh"
 
 namespace pp {
 
@@ -19,7 +20,7 @@ namespace pp {
 // host-side error text
 // ------------------------------------------------------------------------------------------
 static thread_local char g_err[512] = "";
-int fail(int code, const char* fmt, const char* a = "") {
+int fail(int code, const char* fmt, const char* a) {
   snprintf(g_err, sizeof(g_err), fmt, a);
   return code;
 }
@@ -644,22 +645,6 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-struct DeviceFacts {
-  int sm_count = 0, smem_optin = 0, major = 0, minor = 0, clock_khz = 0;
-  bool ok = false;
-};
-static int device_facts(DeviceFacts& f) {
-  int dev = 0;
-  if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
-  cudaDeviceGetAttribute(&f.sm_count, cudaDevAttrMultiProcessorCount, dev);
-  cudaDeviceGetAttribute(&f.smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-  cudaDeviceGetAttribute(&f.major, cudaDevAttrComputeCapabilityMajor, dev);
-  cudaDeviceGetAttribute(&f.minor, cudaDevAttrComputeCapabilityMinor, dev);
-  cudaDeviceGetAttribute(&f.clock_khz, cudaDevAttrClockRate, dev);
-  f.ok = true;
-  return 0;
-}
-
 // 0 = hierarchical ranking sweeps where they apply (default), 1 = always fold every period directly
 static int g_fold_mode = 0;
 // optional device buffer of 8 uint64 phase-cycle counters (development aid; see pp_set_profile_buffer)
@@ -672,24 +657,6 @@ static bool hier_applies(int metric, int trunc, int orth) {
 static int plan_for(int algo, int N, int pmax, int num, SmemPlan& pl) {
   pl = make_plan(N, pmax, algo == PP_ALGO_MBEST ? num : 0, true, g_fold_mode == 0 && (algo == PP_ALGO_MBEST || algo == PP_ALGO_SWEEP));
   return 0;
-}
-
-// persistent grid: CTAs per SM limited by shared memory (<= 2 by registers)
-static int grid_for(const DeviceFacts& f, size_t smem_bytes, int B) {
-  int per_sm = (int)((size_t)(f.smem_optin + 1024) / (smem_bytes + 1024));
-  if (per_sm > kCtasPerSm) per_sm = kCtasPerSm;
-  if (per_sm < 1) per_sm = 1;
-  int g = f.sm_count * per_sm;
-  if (B > 0 && g > B) g = B;
-  return g < 1 ? 1 : g;
-}
-
-template <typename K>
-static int prep_kernel(K kernel, size_t smem_bytes, const DeviceFacts& f) {
-  if (smem_bytes > (size_t)f.smem_optin)
-    return fail(-2, "window (N + pmax) does not fit in shared memory for on-chip staging%s");
-  return check_cuda(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes),
-                    "cudaFuncSetAttribute");
 }
 
 }  // namespace pp
@@ -785,14 +752,6 @@ int pp_periodic_norm(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t
   if (grid > B) grid = B;
   norm_kernel<<<grid, kThreads, 0, (cudaStream_t)stream>>>(x, ldx, B, N, p, out);
   return check_cuda(cudaGetLastError(), "norm_kernel launch");
-}
-
-static double* carve(void* ws, size_t ws_bytes, size_t& off, size_t bytes) {
-  off = (off + 255) & ~(size_t)255;
-  if (ws == nullptr || off + bytes > ws_bytes) return nullptr;
-  double* p = reinterpret_cast<double*>(reinterpret_cast<char*>(ws) + off);
-  off += bytes;
-  return p;
 }
 
 int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, int32_t pmax, int32_t metric,

@@ -457,7 +457,7 @@ __device__ __forceinline__ void sweep_shared_init(SweepShared* sh) {
 // sh->params must have been written by thread 0.  All threads call; the result is valid in all
 // threads.  Contains CTA barriers.  Kept out of line so the caller's live state does not compete
 // with the fold's registers.
-__device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
+static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   const SweepParams* sp = &sh->params;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   if (threadIdx.x == 0) {

@@ -1,0 +1,253 @@
+"""`QOPeriods` -- drop-in for pyPeriod.QOPeriods (pyPeriod/QOPeriods.py:148-1310), default path on the B200.
+
+`find_periods(data, num, thresh, ...)` runs the whole residualisation loop of QOPeriods.py:313-596 in
+one persistent kernel per batch (csrc/pp_qo.cu): gamma sweep -> dictionary layout -> Gram + Cholesky
+-> reconstruction / residual -> stop test.  1-D input returns the reference's `(dict, res)`; a
+(B, N) batch returns a QOBatchResult whose `.window(b)` rebuilds that pair for one window.
+
+Supported: the reference's DEFAULT branch (`_orthogonalize=False`, `update_weights=True`,
+`basis_type="natural"`, default `test_function`).  The other branches are out of scope
+ and raise NotImplementedError instead of silently doing something else.
+Deviation from the reference: the stray `print(nonzero_periods)` at QOPeriods.py:488 is not reproduced.
+"""
+from __future__ import annotations
+
+import itertools
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._device import Workspace, ptr, stage_windows, stream_ptr, to_host
+from .periods import Periods, _export
+from .tables import get_tables
+
+MAX_ROUNDS = 64  # device-side cap on `num` (the reference's default num = len(data) is "way too many", :377)
+
+
+def indicator_rows(q: int, n: int, keep) -> np.ndarray:
+    """Natural-basis rows 1[(m - i) % q == 0], i < keep; keep == 0/None keeps all q rows (QOPeriods.py:940-974)."""
+    m = np.arange(int(n))
+    rows = ((m[None, :] - np.arange(int(q))[:, None]) % int(q) == 0).astype(np.float64)
+    return rows[:keep] if keep else rows
+
+
+def build_subspaces(dict_q, dict_keep, n: int) -> np.ndarray:
+    """The stacked dictionary matrix the reference returns under 'subspaces' (an output structure, 0/1 valued)."""
+    blocks = [np.zeros((0, n))] + [indicator_rows(q, n, k) for q, k in zip(dict_q, dict_keep)]
+    return np.vstack(blocks)
+
+
+@dataclass
+class QOBatchResult:
+    """Padded batch outputs of find_periods; numpy for host input, torch (device) otherwise."""
+    periods: object      # (B, num) uint32, first n_periods[b] valid
+    norms: object        # (B, num) float64
+    n_periods: object    # (B,)
+    dict_q: object       # (B, num) int32: dictionary keys in insertion order
+    dict_keep: object    # (B, num) int32: rows kept per key (0 = repeated period)
+    n_dict: object       # (B,)
+    weights: object      # (B, rmax) float64, first n_weights[b] valid
+    n_weights: object    # (B,)
+    res: object          # (B, N) float64 or None
+    status: object       # (B,) int32
+    n: int = 0
+
+    def window(self, b: int, data_row=None):
+        """(dict, res) of window b in the reference's form."""
+        g = (lambda t: t.cpu().numpy() if isinstance(t, torch.Tensor) else t)
+        st = int(g(self.status)[b])
+        res = None if self.res is None else np.array(g(self.res)[b])
+        if st == _lib.STATUS_ZERO_INPUT:  # QOPeriods.py:394-406
+            out = {"periods": np.array([1]), "norms": np.array([0]), "subspaces": np.ones((1, self.n)),
+                   "weights": np.array([0]), "basis_dictionary": {"1": self.n}}
+            return out, np.zeros(self.n)
+        nd, nw, npd = int(g(self.n_dict)[b]), int(g(self.n_weights)[b]), int(g(self.n_periods)[b])
+        if nd == 0:  # nothing was ever solved: the reference still holds its initial lists (:409-415)
+            return ({"periods": [], "norms": [], "subspaces": [], "weights": [], "basis_dictionary": {}}, res)
+        dq, dk = g(self.dict_q)[b, :nd], g(self.dict_keep)[b, :nd]
+        per = np.array(g(self.periods)[b, :npd]).view(np.uint32) if g(self.periods).dtype != np.uint32 \
+            else np.array(g(self.periods)[b, :npd])
+        out = {"periods": per, "norms": np.array(g(self.norms)[b, :npd]),
+               "subspaces": build_subspaces(dq, dk, self.n), "weights": np.array(g(self.weights)[b, :nw]),
+               "basis_dictionary": {str(int(q)): int(k) for q, k in zip(dq, dk)}}
+        return out, res
+
+
+class QOPeriods(Periods):
+    """Quadratic-program periodicity decomposition (default path), B200-native."""
+
+    def __init__(self, basis_type="natural", trunc_to_integer_multiple=False, orthogonalize=False, device=None):
+        super().__init__(trunc_to_integer_multiple, orthogonalize, device=device)
+        self._output = None
+        self._basis_type = basis_type
+        self._verbose = False
+        self._k = 0
+        self._window = False
+        self._output_bases = None
+        self._container = []
+
+    # ------------------------------------------------------------------ detection
+    def find_periods(self, data, num=None, thresh=None, min_length=2, max_length=None, update_weights=True,
+                     return_res=True, rmax=None, **kwargs):
+        """QOPeriods.find_periods (QOPeriods.py:313-596)."""
+        if "test_function" in kwargs:
+            raise NotImplementedError("custom test_function is evaluated on the device only in its default form")
+        if kwargs:
+            raise TypeError(f"unexpected arguments {sorted(kwargs)}")
+        if self._orthogonalize or not update_weights or self._basis_type != "natural":
+            raise NotImplementedError("only the reference's default branch (orthogonalize=False, "
+                                      "update_weights=True, basis_type='natural') is implemented")
+        lib = _lib.load()
+        w = stage_windows(data, self._device)
+        n = w.n
+        if max_length is None:
+            max_length = int(np.floor(n / 3))
+        num = min(n, MAX_ROUNDS) if num is None else int(num)
+        if num > MAX_ROUNDS:
+            raise ValueError(f"num > {MAX_ROUNDS} is not supported on the device")
+        if thresh is None:
+            if num > 1:
+                raise TypeError("thresh is None: the reference's default test multiplies it (QOPeriods.py:391)")
+            thresh = 0.0
+        if rmax is None:
+            rmax = min(n, 1024)
+        tb = get_tables(max_length)
+        phi = tb.phi_device(w.device)
+        ws = Workspace.get(w.device, lib.pp_qo_workspace_bytes(n, max_length, num, rmax))
+        dev = w.device
+        i32 = dict(dtype=torch.int32, device=dev)
+        f64 = dict(dtype=torch.float64, device=dev)
+        periods = torch.zeros((w.b, num), **i32)
+        norms = torch.zeros((w.b, num), **f64)
+        n_periods, n_dict, n_weights, status = (torch.zeros((w.b,), **i32) for _ in range(4))
+        dict_q, dict_keep = torch.zeros((w.b, num), **i32), torch.zeros((w.b, num), **i32)
+        weights = torch.zeros((w.b, (rmax + 1) & ~1), **f64)
+        res = torch.empty((w.b, n), **f64) if return_res else None
+        _lib.check(lib.pp_qo_find_periods(ptr(w.tensor), w.ldx, w.b, n, num, float(thresh), int(min_length),
+                                          int(max_length), int(self._trunc_to_integer_multiple), ptr(phi), tb.pmax,
+                                          int(rmax), ptr(periods), ptr(norms), ptr(n_periods), ptr(dict_q),
+                                          ptr(dict_keep), ptr(n_dict), ptr(n_weights), ptr(weights), ptr(res),
+                                          ptr(status), ptr(ws), ws.numel(), stream_ptr(dev)), "pp_qo_find_periods")
+        out = QOBatchResult(_export(w, periods, True), _export(w, norms), _export(w, n_periods), _export(w, dict_q),
+                            _export(w, dict_keep), _export(w, n_dict), _export(w, weights), _export(w, n_weights),
+                            _export(w, res), _export(w, status), n=n)
+        if w.was_1d:
+            pair = out.window(0)
+            self._output = self._output_bases = pair[0]
+            return pair
+        return out
+
+    # ------------------------------------------------------------------ extraction (QOPeriods.py:719-741)
+    def get_periods(self, weights, dictionary, decomp_type="row reduction"):
+        """Redistribute shared-GCD energy between the found periods; returns a tuple of per-period waveforms.
+
+        A small dense problem (sum of the periods unknowns); it runs on the device through torch.linalg.
+        """
+        dev = torch.device("cuda", torch.cuda.current_device()) if self._device is None else torch.device(self._device)
+        periods = [int(p) for p in dictionary.keys()]
+        cat = torch.as_tensor(self.concatenate_periods(weights, dictionary), dtype=torch.float64, device=dev)
+        a = torch.as_tensor(self.stack_pairwise_gcd_subspaces(periods), dtype=torch.float64, device=dev)
+        if decomp_type == "row reduction":
+            a = _reduce_rows(a)
+            kind = "solve"
+        elif decomp_type == "lu":
+            _, _, a = torch.linalg.lu(a)
+            kind = "solve"
+        elif decomp_type == "qr":
+            _, a = torch.linalg.qr(a, mode="complete")
+            kind = "solve"
+        else:
+            kind = "lstsq"
+        _, rec = self.solve_quadratic(cat, a, kind)
+        actual = (cat - rec).cpu().numpy()
+        out, start = [], 0
+        for p in periods:
+            out.append(actual[start:start + p])
+            start += p
+        return tuple(out)
+
+    @staticmethod
+    def solve_quadratic(x, A, type="solve", window=None, k=0):
+        """Normal equations (A A^T) w = A x and reconstruction A^T w (QOPeriods.py:743-805), on torch tensors."""
+        x = torch.as_tensor(x, dtype=torch.float64, device=A.device if isinstance(A, torch.Tensor) else None)
+        A = torch.as_tensor(A, dtype=torch.float64, device=x.device)
+        gram, rhs = A @ A.T, A @ x
+        if type == "solve":
+            w = torch.linalg.solve(gram, rhs)  # raises torch.linalg.LinAlgError on a singular matrix
+        else:
+            w = torch.linalg.lstsq(gram, rhs.unsqueeze(1)).solution.squeeze(1)
+        return w, A.T @ w
+
+    @staticmethod
+    def concatenate_periods(weights, dictionary):
+        """QOPeriods.py:854-887."""
+        pos, parts = 0, []
+        for q, r in dictionary.items():
+            v = np.zeros(int(q))
+            v[0:r] = np.asarray(weights)[pos:pos + r]
+            pos += r
+            parts.append(v)
+        return np.concatenate(parts) if parts else np.zeros(0)
+
+    @staticmethod
+    def stack_pairwise_gcd_subspaces(periods):
+        """QOPeriods.py:889-938: +/- combs of every pair's gcd, all shifts."""
+        periods = [int(p) for p in periods]
+        if len(periods) > 1:
+            rows = []
+            for a, b in itertools.combinations(periods, 2):
+                g = int(np.gcd(a, b))
+                segs = []
+                for p in periods:
+                    if p in (a, b):
+                        comb = np.tile((np.arange(g) == 0).astype(np.float64), p // g)
+                        segs.append(-comb if p == a else comb)
+                    else:
+                        segs.append(np.zeros(p))
+                row = np.concatenate(segs)
+                rows.append(row)
+                for s in range(1, g):
+                    rows.append(np.roll(row, s))
+            return np.vstack(rows)
+        if len(periods) == 1:
+            return np.ones((1, periods[0]))
+        return np.ones((1, 1))
+
+    @staticmethod
+    def Pp(p, N=1, keep=None, type="natural"):
+        """QOPeriods.py:940-974 (natural basis)."""
+        if type != "natural":
+            raise NotImplementedError("only the natural basis is implemented")
+        return indicator_rows(p, N, keep)
+
+    def get_subspaces(self, Q, N):
+        """QOPeriods.py:807-852: (A, {str(q): rows kept}); layout rule identical to the device kernel's."""
+        phi = get_tables(max([int(q) for q in Q] + [2])).phi
+        seen, dim_before, layout = set(), 0, {}
+        for q in Q:
+            q = int(q)
+            seen |= {d for d in range(1, q + 1) if q % d == 0}
+            dim = int(sum(int(phi[r]) for r in seen))
+            layout[str(q)] = dim - dim_before
+            dim_before = dim
+        return build_subspaces([int(q) for q in layout], list(layout.values()), N), layout
+
+    # ------------------------------------------------------------------ properties (QOPeriods.py:1237-1310)
+    basis_type = property(lambda s: s._basis_type, lambda s, v: setattr(s, "_basis_type", v))
+    verbose = property(lambda s: s._verbose, lambda s, v: setattr(s, "_verbose", v))
+    k = property(lambda s: s._k, lambda s, v: setattr(s, "_k", v))
+    output_bases = property(lambda s: s._output_bases, lambda s, v: setattr(s, "_output_bases", v))
+
+
+def _reduce_rows(a: torch.Tensor) -> torch.Tensor:
+    """Greedy rank-increasing row selection (QOPeriods.py:86-94)."""
+    kept = a[0:1]
+    rank = int(torch.linalg.matrix_rank(kept))
+    for i in range(1, a.shape[0]):
+        trial = torch.cat((kept, a[i:i + 1]))
+        r = int(torch.linalg.matrix_rank(trial))
+        if r > rank:
+            kept, rank = trial, r
+    return kept

@@ -49,6 +49,16 @@ def orth_chain(p: int) -> list:
     return [int(p / f) for f in nontrivial_factors(p) if f in pr]
 
 
+def euler_phi_table(nmax: int) -> np.ndarray:
+    """phi[0..nmax] by a sieve (values equal the reference's gcd-count phi, QOPeriods.py:16-43)."""
+    phi = np.arange(nmax + 1, dtype=np.int64)
+    for p in range(2, nmax + 1):
+        if phi[p] == p:  # prime
+            phi[p::p] -= phi[p::p] // p
+    phi[0] = 0
+    return phi.astype(np.int32)
+
+
 class PeriodTables:
     """CSR tables for all periods 0..pmax, as numpy int32 (host) and cached device tensors."""
 
@@ -69,13 +79,23 @@ class PeriodTables:
         self.fac_off = fac_off
         self.chain_q = np.asarray(chain if chain else [0], dtype=np.int32)
         self.fac = np.asarray(fac if fac else [0], dtype=np.int32)
+        self.phi = euler_phi_table(self.pmax)
         self._dev = {}
+        self._dev_phi = {}
 
     def chain_of(self, p: int) -> np.ndarray:
         return self.chain_q[self.chain_off[p]: self.chain_off[p + 1]]
 
     def factors_of(self, p: int) -> np.ndarray:
         return self.fac[self.fac_off[p]: self.fac_off[p + 1]]
+
+    def phi_device(self, device):
+        """Euler phi table as a torch int32 tensor on `device` (cached)."""
+        import torch
+        key = str(device)
+        if key not in self._dev_phi:
+            self._dev_phi[key] = torch.from_numpy(self.phi).to(device)
+        return self._dev_phi[key]
 
     def device(self, device):
         """Tuple of torch int32 tensors (chain_off, chain_q, fac_off, fac) on `device` (cached)."""

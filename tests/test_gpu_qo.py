@@ -1,0 +1,97 @@
+"""GPU parity tests for QOPeriods.find_periods / get_periods (default branch) against the golden
+fixtures generated from the reference and against the oracle."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import qo as oq
+from pyperiod_b200 import synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def QO():
+    from pyperiod_b200 import QOPeriods
+    return QOPeriods
+
+
+def _check(d, res, g, pre):
+    assert np.array_equal(np.asarray(d["periods"]), g[pre + "periods"])
+    np.testing.assert_allclose(d["norms"], g[pre + "norms"], rtol=1e-10)
+    assert [int(k) for k in d["basis_dictionary"]] == g[pre + "dict_keys"].tolist()
+    assert list(d["basis_dictionary"].values()) == g[pre + "dict_vals"].tolist()
+    np.testing.assert_allclose(d["weights"], g[pre + "weights"], rtol=1e-8, atol=1e-11)
+    np.testing.assert_allclose(res, g[pre + "res"], rtol=0, atol=1e-11)
+    assert d["subspaces"].shape == (len(d["weights"]), len(res))
+
+
+def test_qo_readme_vs_golden(QO):
+    g = load_golden("readme_qo_ram")
+    c = synth.readme_signal(0)
+    d, res = QO().find_periods(c, num=2, thresh=0.05)
+    _check(d, res, g, "qo_")
+    assert d["periods"].tolist() == [59, 100] and d["basis_dictionary"] == {"59": 59, "100": 99}
+    d3, res3 = QO().find_periods(c, num=3, thresh=0.05)
+    _check(d3, res3, g, "qo3_")
+    # reconstruction from the returned dictionary reproduces data - res
+    np.testing.assert_allclose(d3["subspaces"].T @ d3["weights"], c - res3, rtol=0, atol=1e-12)
+
+
+def test_qo_synth_4096_vs_golden_and_batch(QO):
+    g = load_golden("qo_ram_synth")
+    xb = synth.synth_batch(2, 4096, 50_000)
+    out = QO().find_periods(xb, num=4, thresh=0.05)
+    assert out.status.tolist() == [0, 0]
+    for b in range(2):
+        d, res = out.window(b)
+        _check(d, res, g, f"qo_{b}_")
+        d1, res1 = QO().find_periods(xb[b], num=4, thresh=0.05)      # 1-D call == batch row
+        assert np.array_equal(d1["weights"], d["weights"]) and np.array_equal(res1, res)
+
+
+def test_qo_vs_oracle_modes(QO):
+    xb = synth.synth_batch(3, 1500, 8800)
+    for trunc in (False, True):
+        for num, thresh in ((1, 0.5), (3, 0.05), (4, 0.6)):
+            out = QO(trunc_to_integer_multiple=trunc).find_periods(xb, num=num, thresh=thresh, max_length=300)
+            for b in range(3):
+                d, res = out.window(b)
+                d0, res0 = oq.find_periods(xb[b], num=num, thresh=thresh, max_length=300, trunc=trunc)
+                assert np.array_equal(np.asarray(d["periods"]), np.asarray(d0["periods"])), (trunc, num, b)
+                assert d["basis_dictionary"] == d0["basis_dictionary"]
+                np.testing.assert_allclose(d["norms"], d0["norms"], rtol=1e-10)
+                np.testing.assert_allclose(d["weights"], d0["weights"], rtol=1e-8, atol=1e-11)
+                np.testing.assert_allclose(res, res0, rtol=0, atol=1e-11)
+
+
+def test_qo_zero_input(QO):
+    d, res = QO().find_periods(np.zeros(600), num=2, thresh=0.05)
+    assert d["periods"].tolist() == [1] and d["basis_dictionary"] == {"1": 600} and not res.any()
+
+
+def test_get_periods_vs_golden(QO):
+    g = load_golden("readme_qo_ram")
+    c = synth.readme_signal(0)
+    q = QO()
+    d, _ = q.find_periods(c, num=2, thresh=0.05)
+    gp = q.get_periods(d["weights"], d["basis_dictionary"], "lstsq")
+    for i, v in enumerate(gp):
+        np.testing.assert_allclose(v, g[f"qo_getp_lstsq_{i}"], rtol=0, atol=1e-9)
+    d3, _ = q.find_periods(c, num=3, thresh=0.05)
+    for kind, key in (("row reduction", "rowreduction"), ("lstsq", "lstsq")):
+        if f"qo3_getp_{key}_linalgerror" in g.files:
+            continue
+        gp = q.get_periods(d3["weights"], d3["basis_dictionary"], kind)
+        for i, v in enumerate(gp):
+            np.testing.assert_allclose(v, g[f"qo3_getp_{key}_{i}"], rtol=0, atol=1e-8)
+
+
+def test_unsupported_branches_raise(QO):
+    x = synth.synth(512, 1)
+    with pytest.raises(NotImplementedError):
+        QO(orthogonalize=True).find_periods(x, num=1, thresh=0.1)
+    with pytest.raises(NotImplementedError):
+        QO().find_periods(x, num=1, thresh=0.1, update_weights=False)
+    with pytest.raises(TypeError):
+        QO().find_periods(x, num=2)
