@@ -171,6 +171,23 @@ int pp_qo_solve(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t kmax
                 int32_t *dict_q, int32_t *dict_keep, int32_t *n_dict, int32_t *n_weights, double *weights,
                 double *res, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- RamanujanPeriods.find_periods (RamanujanPeriods.py:67-86, 124-169) ------------------
+ * norms[b, q] = sum_n (sum_i <x, r_i> r_i)[n]^2 over the q-row Ramanujan dictionary of period q,
+ * evaluated in fp64 as the dense contraction (q / phi(q)^2) * circ(c_q) * S_q on the FP64 tensor
+ * cores (DMMA), S_q = residue-class fold of the window, followed by the count-weighted column
+ * norms.  (The reference stores its projection in float32, :127, so its own norms carry ~1e-7
+ * relative noise; this path is the fp64 value.)  mu / phi: device int32 tables (Moebius, totient)
+ * for 0..table_qmax.  Only columns qmin..qmax of norms[B, ld_norms] are written. */
+size_t pp_ramanujan_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32_t tile_windows);
+int pp_ramanujan_norms(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
+                       const int32_t *mu, const int32_t *phi, int32_t table_qmax, int32_t tile_windows,
+                       double *norms, int32_t ld_norms, void *workspace, size_t workspace_bytes, void *stream);
+
+/* periods[b, 0:nper[b]] = ascending q in [0, qlen) with norms[b,q] / |max_q norms[b,q]| > thresh
+ * (RamanujanPeriods.py:97-101); nper[b] may exceed kmax, only the first kmax are stored. */
+int pp_ramanujan_select(const double *norms, int32_t B, int32_t ld_norms, int32_t qlen, double thresh,
+                        int32_t kmax, int32_t *periods, int32_t *nper, void *stream);
+
 /* ---- roofline denominators measured live -----------------------
  * kind 0: shared-memory load bandwidth, out_host[0] = bytes/s over the whole chip;
  * kind 1: FP64 add throughput,           out_host[0] = adds/s  over the whole chip;

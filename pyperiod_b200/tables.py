@@ -59,6 +59,19 @@ def euler_phi_table(nmax: int) -> np.ndarray:
     return phi.astype(np.int32)
 
 
+def moebius_table(nmax: int) -> np.ndarray:
+    """mu[0..nmax] (mu[0] = 0) by a linear sieve."""
+    mu = np.ones(nmax + 1, dtype=np.int32)
+    mu[0] = 0
+    is_comp = np.zeros(nmax + 1, dtype=bool)
+    for p in range(2, nmax + 1):
+        if not is_comp[p]:
+            is_comp[2 * p:: p] = True
+            mu[p:: p] *= -1
+            mu[p * p:: p * p] = 0
+    return mu
+
+
 class PeriodTables:
     """CSR tables for all periods 0..pmax, as numpy int32 (host) and cached device tensors."""
 
@@ -80,6 +93,7 @@ class PeriodTables:
         self.chain_q = np.asarray(chain if chain else [0], dtype=np.int32)
         self.fac = np.asarray(fac if fac else [0], dtype=np.int32)
         self.phi = euler_phi_table(self.pmax)
+        self.mu = moebius_table(self.pmax)
         self._dev = {}
         self._dev_phi = {}
 
@@ -95,6 +109,14 @@ class PeriodTables:
         key = str(device)
         if key not in self._dev_phi:
             self._dev_phi[key] = torch.from_numpy(self.phi).to(device)
+        return self._dev_phi[key]
+
+    def mu_device(self, device):
+        """Moebius table as a torch int32 tensor on `device` (cached)."""
+        import torch
+        key = "mu:" + str(device)
+        if key not in self._dev_phi:
+            self._dev_phi[key] = torch.from_numpy(self.mu).to(device)
         return self._dev_phi[key]
 
     def device(self, device):
