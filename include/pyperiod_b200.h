@@ -74,8 +74,11 @@ int pp_get_fold_mode(void);
 
 /* Development aid: when set to a device buffer of 8 uint64, pp_mbest adds per-window SM-cycle
  * counts to it: [0] sweeps, [1] exact winner projections, [2] bookkeeping + residual update,
- * [3] step 2 + outputs, [4] windows.  Pass NULL to disable (default). */
+ * [3] step 2 + outputs, [4] windows.  pp_qo_find_periods adds: [0] sweeps, [1] dictionary layout,
+ * [2] W + Gram build, [3] Cholesky, [5] solves + reconstruction, [4] windows.
+ * Pass NULL to disable (default). */
 int pp_set_profile_buffer(void *dev_u64x8);
+void *pp_get_profile_buffer(void);
 
 /* Device facts the host uses for grid sizing / roofline arithmetic (current device). */
 int pp_device_info(int32_t *sm_count, int32_t *smem_optin_bytes, int32_t *cc_major, int32_t *cc_minor,

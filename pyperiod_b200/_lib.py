@@ -31,6 +31,7 @@ SIGNATURES = {
     "pp_set_fold_mode": (C.c_int, [_i32]),
     "pp_get_fold_mode": (C.c_int, []),
     "pp_set_profile_buffer": (C.c_int, [_p]),
+    "pp_get_profile_buffer": (C.c_void_p, []),
     "pp_device_info": (C.c_int, [_p, _p, _p, _p, _p]),
     "pp_grid_size": (C.c_int, [_i32, _i32, _i32, _i32]),
     "pp_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),

@@ -677,6 +677,7 @@ int pp_set_profile_buffer(void* dev_u64x8) {
   g_prof = reinterpret_cast<unsigned long long*>(dev_u64x8);
   return 0;
 }
+void* pp_get_profile_buffer(void) { return g_prof; }
 const char* pp_last_error(void) { return g_err; }
 
 int pp_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_major, int32_t* cc_minor,

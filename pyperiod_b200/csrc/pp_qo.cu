@@ -21,7 +21,7 @@
 namespace pp {
 
 constexpr int kCholNb = 32;    // Cholesky block size
-constexpr int kCholTile = 64;  // trailing-update tile (64 x 64 outputs per CTA step, 4 x 4 per thread)
+constexpr int kCholTile = 32;  // trailing-update tile: 32 x 32 outputs per warp, 4 x 8 per lane
 
 struct QoPlan {
   int xs_len, n_even, rmax, num, seen_words, hier_len;
@@ -30,7 +30,7 @@ struct QoPlan {
   __host__ __device__ size_t off_chol() const { return off_wv() + (size_t)rmax * 8; }
   // Cholesky tiles and the hierarchical-sweep scratch are never live together
   __host__ __device__ size_t chol_bytes() const {
-    const size_t a = (size_t)(kCholNb * (kCholNb + 1) + kCholNb + 2 * kCholNb * kCholTile) * 8;
+    const size_t a = (size_t)(kCholNb * (kCholNb + 1) + kCholNb) * 8;
     const size_t b = (size_t)kWarps * hier_len * 8;
     return a > b ? a : b;
   }
@@ -61,8 +61,6 @@ __host__ __device__ inline QoPlan make_qo_plan(int N, int pmax, int num, int rma
 struct CholSmem {
   double* D;    // [32][33] diagonal block
   double* rD;   // [32] reciprocals of its diagonal
-  double* Pi;   // [32][64] k-major tile of the panel (rows ti..)
-  double* Pj;   // [32][64]
 };
 
 __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __restrict__ Pt, const CholSmem& cs,
@@ -131,71 +129,95 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
       }
     }
     __syncthreads();
-    // (3) trailing update  A[i][j] -= sum_k P[i][k] P[j][k]   (j <= i), 64 x 64 tiles, 4 x 4 per thread
-    const int ty = tid >> 4, tx = tid & 15;
-    const int base = kb + nb;
-    for (int ti = base; ti < R; ti += kCholTile) {
-      for (int idx = tid; idx < kCholNb * kCholTile; idx += kThreads) {
-        const int k = idx >> 6, ii = idx & 63;
-        cs.Pi[idx] = (ti + ii < R) ? Pt[(size_t)k * ld + ti + ii] : 0.0;
-      }
-      for (int tj = base; tj <= ti; tj += kCholTile) {
-        const bool diag = tj == ti;
-        if (!diag) {
-          for (int idx = tid; idx < kCholNb * kCholTile; idx += kThreads) {
-            const int k = idx >> 6, jj = idx & 63;
-            cs.Pj[idx] = (tj + jj < R) ? Pt[(size_t)k * ld + tj + jj] : 0.0;
-          }
-        }
-        __syncthreads();
-        const double* pj = diag ? cs.Pi : cs.Pj;
-        double acc[4][4];
+    // (3) trailing update  A[i][j] -= sum_k P[i][k] P[j][k]  (j <= i).  Each warp owns 32 x 32 output
+    // tiles (round-robin over the lower-triangular tile pairs) and streams the transposed panel Pt
+    // straight from L1/L2 into registers: no shared-memory staging, no CTA barrier inside the update.
+    {
+      const int base = kb + nb;
+      const int nt = (R - base + kCholTile - 1) / kCholTile;
+      const int npairs = nt * (nt + 1) / 2;
+      const int ty = lane >> 2, tx = lane & 3;  // lane's 4 rows x 8 columns of the tile
+      for (int pr = wid; pr < npairs; pr += kWarps) {
+        // pr -> (it, jt) with jt <= it
+        int it = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
+        while (it * (it + 1) / 2 > pr) --it;
+        while ((it + 1) * (it + 2) / 2 <= pr) ++it;
+        const int jt = pr - it * (it + 1) / 2;
+        const int ti = base + it * kCholTile, tj = base + jt * kCholTile;
+        const int i0 = ti + ty * 4, j0 = tj + tx * 8;
+        double acc[4][8];
 #pragma unroll
         for (int r = 0; r < 4; ++r)
 #pragma unroll
-          for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
-#pragma unroll 8
+          for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
+        const bool full = (ti + kCholTile <= R) && (tj + kCholTile <= R);
+#pragma unroll 4
         for (int k = 0; k < kCholNb; ++k) {
-          const double2 a01 = *reinterpret_cast<const double2*>(cs.Pi + k * kCholTile + ty * 4);
-          const double2 a23 = *reinterpret_cast<const double2*>(cs.Pi + k * kCholTile + ty * 4 + 2);
-          const double2 b01 = *reinterpret_cast<const double2*>(pj + k * kCholTile + tx * 4);
-          const double2 b23 = *reinterpret_cast<const double2*>(pj + k * kCholTile + tx * 4 + 2);
-          const double av[4] = {a01.x, a01.y, a23.x, a23.y}, bv[4] = {b01.x, b01.y, b23.x, b23.y};
+          const double* pk = Pt + (size_t)k * ld;
+          double av[4], bv[8];
+          if (full) {
+            const double2 a01 = *reinterpret_cast<const double2*>(pk + i0);
+            const double2 a23 = *reinterpret_cast<const double2*>(pk + i0 + 2);
+            av[0] = a01.x; av[1] = a01.y; av[2] = a23.x; av[3] = a23.y;
+#pragma unroll
+            for (int c = 0; c < 8; c += 2) {
+              const double2 b2 = *reinterpret_cast<const double2*>(pk + j0 + c);
+              bv[c] = b2.x;
+              bv[c + 1] = b2.y;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < 4; ++r) av[r] = (i0 + r < R) ? pk[i0 + r] : 0.0;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) bv[c] = (j0 + c < R) ? pk[j0 + c] : 0.0;
+          }
 #pragma unroll
           for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+            for (int c = 0; c < 8; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
         }
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
-          const int i = ti + ty * 4 + r;
+          const int i = i0 + r;
           if (i < R) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
-              const int j = tj + tx * 4 + c;
+            for (int c = 0; c < 8; ++c) {
+              const int j = j0 + c;
               if (j <= i) A[(size_t)i * ld + j] -= acc[r][c];
             }
           }
         }
-        __syncthreads();
       }
     }
+    __syncthreads();
   }
   return true;
 }
 
 // Solve L L^T w = b in place (b in shared memory, length R) with the factor from cta_cholesky.
+// Each 32 x 32 diagonal block is staged in shared memory so the serial substitution of warp 0 never
+// waits on global memory; the rectangular updates are spread over the CTA.
 __device__ void cta_chol_solve(const double* __restrict__ A, int R, int ld, double* b, const CholSmem& cs) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  auto stage = [&](int kb, int nb) {
+    for (int idx = tid; idx < kCholNb * kCholNb; idx += kThreads) {
+      const int r = idx >> 5, c = idx & 31;
+      double v = (r == c) ? 1.0 : 0.0;
+      if (r < nb && c <= r) v = A[(size_t)(kb + r) * ld + kb + c];
+      cs.D[r * (kCholNb + 1) + c] = v;
+    }
+    __syncthreads();
+  };
   // forward: L y = b
   for (int kb = 0; kb < R; kb += kCholNb) {
     const int nb = min(kCholNb, R - kb);
+    stage(kb, nb);
     if (wid == 0) {
       for (int k = 0; k < nb; ++k) {
-        const double yk = b[kb + k] / A[(size_t)(kb + k) * ld + kb + k];
+        const double yk = b[kb + k] / cs.D[k * (kCholNb + 1) + k];
         __syncwarp();
         if (lane == k) b[kb + k] = yk;
-        if (lane > k && lane < nb) b[kb + lane] -= A[(size_t)(kb + lane) * ld + kb + k] * yk;
+        if (lane > k && lane < nb) b[kb + lane] -= cs.D[lane * (kCholNb + 1) + k] * yk;
         __syncwarp();
       }
     }
@@ -211,12 +233,13 @@ __device__ void cta_chol_solve(const double* __restrict__ A, int R, int ld, doub
   // backward: L^T w = y
   for (int kb = ((R - 1) / kCholNb) * kCholNb; kb >= 0; kb -= kCholNb) {
     const int nb = min(kCholNb, R - kb);
+    stage(kb, nb);
     if (wid == 0) {
       for (int k = nb - 1; k >= 0; --k) {
-        const double wk = b[kb + k] / A[(size_t)(kb + k) * ld + kb + k];
+        const double wk = b[kb + k] / cs.D[k * (kCholNb + 1) + k];
         __syncwarp();
         if (lane == k) b[kb + k] = wk;
-        if (lane < k) b[kb + lane] -= A[(size_t)(kb + k) * ld + kb + lane] * wk;
+        if (lane < k) b[kb + lane] -= cs.D[k * (kCholNb + 1) + lane] * wk;
         __syncwarp();
       }
     }
@@ -251,37 +274,51 @@ struct QoCtx {
   double* G;            // global, rmax*rmax
   double* Pt;           // global, 32*rmax
   CholSmem cs;
+  long long* t;         // per-thread phase timers (development aid): [0] layout [1] build [2] cholesky [3] solve
 };
 
-// QOPeriods.get_subspaces (QOPeriods.py:830-840) for `found[0..nfound)`; thread 0 only.
+// QOPeriods.get_subspaces (QOPeriods.py:830-840) for `found[0..nfound)`.  All threads call (contains
+// barriers): the divisor scan of each period is spread over the CTA, the bookkeeping is thread 0's.
 __device__ void qo_layout(const QoCtx& c, int nfound) {
-  for (int i = 0; i < c.seen_words; ++i) c.seen[i] = 0u;
-  int ndict = 0;
+  const int tid = threadIdx.x;
+  for (int i = tid; i < c.seen_words; i += kThreads) c.seen[i] = 0u;
+  if (tid == 0) c.misc[0] = 0;
+  __syncthreads();
   for (int f = 0; f < nfound; ++f) {
     const int q = c.found[f];
+    if (tid == 0) c.misc[3] = 0;
+    __syncthreads();
     int fresh = 0;
-    for (int d = 1; d <= q; ++d) {
+    for (int d = 1 + tid; d <= q; d += kThreads) {
       if (q % d == 0 && !((c.seen[d >> 5] >> (d & 31)) & 1u)) {
         fresh += c.phi[d];
-        c.seen[d >> 5] |= 1u << (d & 31);
+        atomicOr(&c.seen[d >> 5], 1u << (d & 31));
       }
     }
-    int slot = -1;
-    for (int k = 0; k < ndict; ++k)
-      if (c.dict_q[k] == q) slot = k;
-    if (slot < 0) slot = ndict++;
-    c.dict_q[slot] = q;
-    c.dict_keep[slot] = fresh;   // a repeated period overwrites its entry with 0 new dimensions
+    if (fresh) atomicAdd(&c.misc[3], fresh);
+    __syncthreads();
+    if (tid == 0) {
+      int ndict = c.misc[0], slot = -1;
+      for (int k = 0; k < ndict; ++k)
+        if (c.dict_q[k] == q) slot = k;
+      if (slot < 0) slot = ndict++;
+      c.dict_q[slot] = q;
+      c.dict_keep[slot] = c.misc[3];   // a repeated period overwrites its entry with 0 new dimensions
+      c.misc[0] = ndict;
+    }
+    __syncthreads();
   }
-  int off = 0;
-  for (int k = 0; k < ndict; ++k) {
-    c.dict_rows[k] = c.dict_keep[k] ? c.dict_keep[k] : c.dict_q[k];
-    c.dict_off[k] = off;
-    off += c.dict_rows[k];
+  if (tid == 0) {
+    const int ndict = c.misc[0];
+    int off = 0;
+    for (int k = 0; k < ndict; ++k) {
+      c.dict_rows[k] = c.dict_keep[k] ? c.dict_keep[k] : c.dict_q[k];
+      c.dict_off[k] = off;
+      off += c.dict_rows[k];
+    }
+    c.dict_off[ndict] = off;
+    c.misc[1] = off;
   }
-  c.dict_off[ndict] = off;
-  c.misc[0] = ndict;
-  c.misc[1] = off;
 }
 
 // Returns 0 ok, PP_STATUS_SINGULAR, PP_STATUS_TOO_LARGE.  On success wv holds the weights, xs the residual,
@@ -289,8 +326,10 @@ __device__ void qo_layout(const QoCtx& c, int nfound) {
 __device__ int cta_qo_solve(const QoCtx& c, int nfound, double* e_recon) {
   const int tid = threadIdx.x;
   const int N = c.N;
-  if (tid == 0) qo_layout(c, nfound);
+  long long tm = clock64();
+  qo_layout(c, nfound);
   __syncthreads();
+  { const long long now = clock64(); c.t[0] += now - tm; tm = now; }
   const int ndict = c.misc[0], R = c.misc[1];
   if (R > c.rmax) return PP_STATUS_TOO_LARGE;
   if (R == 0) {
@@ -327,7 +366,9 @@ __device__ int cta_qo_solve(const QoCtx& c, int nfound, double* e_recon) {
     }
   }
   __syncthreads();
+  { const long long now = clock64(); c.t[1] += now - tm; tm = now; }
   if (!cta_cholesky(c.G, R, ld, c.Pt, c.cs, &c.misc[2])) return PP_STATUS_SINGULAR;
+  { const long long now = clock64(); c.t[2] += now - tm; tm = now; }
   cta_chol_solve(c.G, R, ld, c.wv, c.cs);
   // reconstruction A^T w and residual
   double e = 0.0;
@@ -347,6 +388,7 @@ __device__ int cta_qo_solve(const QoCtx& c, int nfound, double* e_recon) {
   double t = 0.0;
   for (int w = 0; w < kWarps; ++w) t += c.red[w];
   __syncthreads();
+  c.t[3] += clock64() - tm;
   *e_recon = t;
   return PP_STATUS_OK;
 }
@@ -396,8 +438,6 @@ __device__ __forceinline__ QoCtx make_ctx(unsigned char* smem, const QoPlan& pl,
   double* chol = reinterpret_cast<double*>(smem + pl.off_chol());
   c.cs.D = chol;
   c.cs.rD = chol + kCholNb * (kCholNb + 1);
-  c.cs.Pi = c.cs.rD + kCholNb;
-  c.cs.Pj = c.cs.Pi + kCholNb * kCholTile;
   c.red = reinterpret_cast<double*>(smem + pl.off_red());
   int* ints = reinterpret_cast<int*>(smem + pl.off_ints());
   c.found = ints;
@@ -410,16 +450,17 @@ __device__ __forceinline__ QoCtx make_ctx(unsigned char* smem, const QoPlan& pl,
   c.misc = ints + 5 * num + 1 + pl.seen_words;
   c.G = G;
   c.Pt = Pt;
+  c.t = nullptr;
   return c;
 }
 
 // ------------------------------------------------------------------------------------------
 // QOPeriods.find_periods, default branch (QOPeriods.py:313-596)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, double thresh, int pmin, int pmax,
                int trunc, int hier, const int32_t* __restrict__ phi, int rmax, QoOut out, double* __restrict__ ws_G,
-               double* __restrict__ ws_Pt, double* __restrict__ ws_norms) {
+               double* __restrict__ ws_Pt, double* __restrict__ ws_norms, unsigned long long* __restrict__ prof) {
   unsigned char* smem = pp_smem;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0);
   const size_t ldg = (size_t)pl.rmax;
@@ -431,6 +472,8 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
   double* x0 = const_cast<double*>(c.x0);
   const double sqrtN = sqrt((double)N);
   const int tid = threadIdx.x;
+  long long timers[4] = {0, 0, 0, 0}, t_sweep = 0;
+  c.t = timers;
 
   WindowLoader loader;
   loader.init(bar);
@@ -505,7 +548,9 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
           break;
         }
       }
+      const long long t0 = clock64();
       const SweepResult top = cta_sweep(sweep);
+      t_sweep += clock64() - t0;
       if (tid == 0) {
         round_norms[i] = top.val;
         if (top.p > 0) c.found[nfound] = top.p;
@@ -529,12 +574,20 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
     }
     __syncthreads();
   }
+  if (prof != nullptr && tid == 0) {
+    atomicAdd(prof + 0, (unsigned long long)t_sweep);
+    atomicAdd(prof + 1, (unsigned long long)timers[0]);
+    atomicAdd(prof + 2, (unsigned long long)timers[1]);
+    atomicAdd(prof + 3, (unsigned long long)timers[2]);
+    atomicAdd(prof + 5, (unsigned long long)timers[3]);
+    atomicAdd(prof + 4, (unsigned long long)((B - blockIdx.x + gridDim.x - 1) / gridDim.x));
+  }
 }
 
 // ------------------------------------------------------------------------------------------
 // solve stage alone, for given periods (RamanujanPeriods.find_periods_with_weights :106-112)
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 qo_solve_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int kmax, const int32_t* __restrict__ periods,
                 const int32_t* __restrict__ nper, int pmax, const int32_t* __restrict__ phi, int rmax, QoOut out,
                 double* __restrict__ ws_G, double* __restrict__ ws_Pt) {
@@ -546,6 +599,8 @@ qo_solve_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int kma
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + pl.off_bar());
   double* x0 = const_cast<double*>(c.x0);
   const int tid = threadIdx.x;
+  long long timers[4] = {0, 0, 0, 0};
+  c.t = timers;
   WindowLoader loader;
   loader.init(bar);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
@@ -588,7 +643,7 @@ size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax)
   DeviceFacts f;
   if (device_facts(f)) return 0;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, true);
-  const size_t grid = (size_t)f.sm_count;
+  const size_t grid = (size_t)f.sm_count * 2;
   return 4096 + grid * ((size_t)pl.rmax * pl.rmax + (size_t)kCholNb * pl.rmax + (size_t)num + 64) * 8;
 }
 
@@ -617,7 +672,7 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   const int hier = (pp_get_fold_mode() == PP_FOLD_HIERARCHICAL && !trunc) ? 1 : 0;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0);
   if (int rc = prep_kernel(qo_find_kernel, pl.bytes(), f)) return rc;
-  const int grid = grid_for(f, pl.bytes(), B, 1);
+  const int grid = grid_for(f, pl.bytes(), B, 2);
   size_t off = 0;
   double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.rmax * 8);
   double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.rmax * 8);
@@ -625,7 +680,8 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   if (!G || !Pt || !nr) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
   QoOut o{periods, norms, n_periods, dict_q, dict_keep, n_dict, n_weights, weights, res, status};
   qo_find_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, thresh, pmin, pmax, trunc,
-                                                                       hier, phi, pl.rmax, o, G, Pt, nr);
+                                                                       hier, phi, pl.rmax, o, G, Pt, nr,
+                                                                       reinterpret_cast<unsigned long long*>(pp_get_profile_buffer()));
   return check_cuda(cudaGetLastError(), "qo_find_kernel launch");
 }
 
@@ -641,7 +697,7 @@ int pp_qo_solve(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t kmax
   if (int rc = device_facts(f)) return rc;
   const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
   if (int rc = prep_kernel(qo_solve_kernel, pl.bytes(), f)) return rc;
-  const int grid = grid_for(f, pl.bytes(), B, 1);
+  const int grid = grid_for(f, pl.bytes(), B, 2);
   size_t off = 0;
   double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.rmax * 8);
   double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.rmax * 8);

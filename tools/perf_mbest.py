@@ -16,14 +16,15 @@ for mode in modes:
     _lib.set_fold_mode(_lib.FOLD_DIRECT if mode == "direct" else _lib.FOLD_HIERARCHICAL)
     for name, fn in (("m_best", P.m_best), ("m_best_gamma", P.m_best_gamma)):
         fn(win, num=10, max_length=1024)
+        fn(win, num=10, max_length=1024)
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(3):
+        for _ in range(5):
             r = fn(win, num=10, max_length=1024)
         e1.record()
         torch.cuda.synchronize()
-        ms = e0.elapsed_time(e1) / 3
+        ms = e0.elapsed_time(e1) / 5
         pr = prof.cpu().numpy().astype(float); prof.zero_()
         print("   cycles/window: sweep %.0f  project %.0f  update %.0f  step2+out %.0f" % tuple(pr[:4] / pr[4]))
         print(f"{mode:7s} {name:13s} B={B} {ms:9.2f} ms  {B / ms * 1e3:10.0f} win/s  sweeps/win={float(r.sweeps.float().mean()):.3f}", flush=True)
