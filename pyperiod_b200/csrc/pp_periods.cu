@@ -157,7 +157,7 @@ norm_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int p, doub
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, int pmax, int metric, int trunc,
              int orth, int hier, Tables tb, double* __restrict__ metric_out, int32_t* __restrict__ best_p,
-             double* __restrict__ best_val, double* __restrict__ warp_scr) {
+             double* __restrict__ best_val, double* __restrict__ warp_scr, const uint2* __restrict__ tops, int ntops) {
   unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, pmax, 0, true, hier != 0);
   Smem sm(smem_raw, pl);
@@ -189,6 +189,8 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
       sp.hier_scr = sm.hier;
       sp.hier_len = pl.hier_len;
       sp.rcp = sm.sweep->rcp;
+      sp.tops = tops;
+      sp.ntops = ntops;
       sp.metric_out = metric_out ? metric_out + (size_t)b * (pmax + 1) : nullptr;
     }
     const SweepResult r = cta_sweep(sm.sweep);
@@ -236,7 +238,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, int pmin, int pmax, int gamma,
              int trunc_i, int orth_i, int hier, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
              double* __restrict__ bases_out, int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
-             double* __restrict__ ws_slots, double* __restrict__ ws_scr, unsigned long long* __restrict__ prof) {
+             double* __restrict__ ws_slots, double* __restrict__ ws_scr, const uint2* __restrict__ tops, int ntops,
+             unsigned long long* __restrict__ prof) {
   unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0);
   Smem sm(smem_raw, pl);
@@ -291,6 +294,8 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.hier_scr = sm.hier;
       sp.hier_len = pl.hier_len;
       sp.rcp = sm.sweep->rcp;
+      sp.tops = tops;
+      sp.ntops = ntops;
     }
     __syncthreads();
 
@@ -518,6 +523,8 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
       sp.hier_scr = nullptr;
       sp.hier_len = 0;
       sp.rcp = sm.sweep->rcp;
+      sp.tops = nullptr;
+      sp.ntops = 0;
     }
     int count = 0;
     int pstart = 2;
@@ -598,6 +605,8 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.hier_scr = nullptr;
       sp.hier_len = 0;
       sp.rcp = sm.sweep->rcp;
+      sp.tops = nullptr;
+      sp.ntops = 0;
     }
     for (int i = 0; i < num; ++i) {
       uint32_t out_p = 0u;
@@ -707,7 +716,7 @@ size_t pp_workspace_bytes(int32_t algo, int32_t N, int32_t pmax, int32_t num, in
   SmemPlan pl;
   plan_for(algo, N, pmax, num, pl);
   const size_t grid = (size_t)f.sm_count * kCtasPerSm;  // upper bound on the persistent grid
-  size_t bytes = 1024;
+  size_t bytes = 1024 + 256 + (size_t)(pmax + 2) * sizeof(uint2);
   if (algo == PP_ALGO_MBEST) bytes += grid * (size_t)num * pl.pv * 8;
   if (orth && algo != PP_ALGO_BCORR) bytes += grid * kWarps * 2 * (size_t)pl.pv * 8;
   return bytes;
@@ -778,9 +787,16 @@ int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, i
     scr = carve(workspace, workspace_bytes, off, (size_t)grid * kWarps * 2 * pl.pv * 8);
     if (!scr) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
   }
+  uint2* tops = nullptr;
+  const int ntops = hier ? hier_top_count(pmin, pmax) : 0;
+  if (ntops > 0) {
+    tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)ntops * sizeof(uint2)));
+    if (!tops) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
+    tops_kernel<<<(ntops + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, pmin, pmax, tops);
+  }
   Tables tb{chain_off, chain_q, nullptr, nullptr};
   sweep_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, pmin, pmax, metric, trunc, orth, hier,
-                                                                     tb, metric_out, best_p, best_val, scr);
+                                                                     tb, metric_out, best_p, best_val, scr, tops, ntops);
   return check_cuda(cudaGetLastError(), "sweep_kernel launch");
 }
 
@@ -806,10 +822,17 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   double* slots = carve(workspace, workspace_bytes, off, (size_t)grid * num * pl.pv * 8);
   double* scr = orth ? carve(workspace, workspace_bytes, off, (size_t)grid * kWarps * 2 * pl.pv * 8) : nullptr;
   if (!slots || (orth && !scr)) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
+  uint2* tops = nullptr;
+  const int ntops = hier ? hier_top_count(pmin, pmax) : 0;
+  if (ntops > 0) {
+    tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)ntops * sizeof(uint2)));
+    if (!tops) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
+    tops_kernel<<<(ntops + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, pmin, pmax, tops);
+  }
   Tables tb{chain_off, chain_q, fac_off, fac};
   mbest_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,
                                                                      hier, tb, periods, powers, bases, sweeps, status,
-                                                                     slots, scr, g_prof);
+                                                                     slots, scr, tops, ntops, g_prof);
   return check_cuda(cudaGetLastError(), "mbest_kernel launch");
 }
 

@@ -460,7 +460,8 @@ __device__ __forceinline__ QoCtx make_ctx(unsigned char* smem, const QoPlan& pl,
 __global__ void __launch_bounds__(kThreads, 2)
 qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, double thresh, int pmin, int pmax,
                int trunc, int hier, const int32_t* __restrict__ phi, int rmax, QoOut out, double* __restrict__ ws_G,
-               double* __restrict__ ws_Pt, double* __restrict__ ws_norms, unsigned long long* __restrict__ prof) {
+               double* __restrict__ ws_Pt, double* __restrict__ ws_norms, const uint2* __restrict__ tops, int ntops,
+               unsigned long long* __restrict__ prof) {
   unsigned char* smem = pp_smem;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0);
   const size_t ldg = (size_t)pl.rmax;
@@ -531,6 +532,8 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
       sp.hier_scr = pl.hier_len ? reinterpret_cast<double*>(smem + pl.off_chol()) : nullptr;
       sp.hier_len = pl.hier_len;
       sp.rcp = sweep->rcp;
+      sp.tops = tops;
+      sp.ntops = ntops;
     }
     __syncthreads();
     int nfound = 0;
@@ -644,7 +647,8 @@ size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax)
   if (device_facts(f)) return 0;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, true);
   const size_t grid = (size_t)f.sm_count * 2;
-  return 4096 + grid * ((size_t)pl.rmax * pl.rmax + (size_t)kCholNb * pl.rmax + (size_t)num + 64) * 8;
+  return 8192 + (size_t)(pmax + 2) * sizeof(uint2) +
+         grid * ((size_t)pl.rmax * pl.rmax + (size_t)kCholNb * pl.rmax + (size_t)num + 64) * 8;
 }
 
 static int qo_check(const void* x, int64_t ldx, int B, int N, int num, int pmax, int rmax, const void* phi,
@@ -678,9 +682,16 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.rmax * 8);
   double* nr = carve(workspace, workspace_bytes, off, (size_t)grid * num * 8);
   if (!G || !Pt || !nr) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
+  uint2* tops = nullptr;
+  const int ntops = hier ? hier_top_count(pmin, pmax) : 0;
+  if (ntops > 0) {
+    tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)ntops * sizeof(uint2)));
+    if (!tops) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
+    tops_kernel<<<(ntops + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, pmin, pmax, tops);
+  }
   QoOut o{periods, norms, n_periods, dict_q, dict_keep, n_dict, n_weights, weights, res, status};
   qo_find_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, thresh, pmin, pmax, trunc,
-                                                                       hier, phi, pl.rmax, o, G, Pt, nr,
+                                                                       hier, phi, pl.rmax, o, G, Pt, nr, tops, ntops,
                                                                        reinterpret_cast<unsigned long long*>(pp_get_profile_buffer()));
   return check_cuda(cudaGetLastError(), "qo_find_kernel launch");
 }

@@ -54,6 +54,8 @@ struct SweepParams {
   double* hier_scr;      // shared scratch of the hierarchical sweep: kWarps * hier_len doubles (nullable => direct)
   int hier_len;
   const double* rcp;     // shared table rcp[m] = 1.0 / m for m < kRcpTab (energy weights without a division)
+  const uint2* tops;     // global: descriptors of the hierarchical tops in hand-out order (tops_kernel)
+  int ntops;
 };
 
 struct SweepResult {
@@ -192,6 +194,8 @@ __device__ __forceinline__ void fold_range(const double* xs, int p, int lo, int 
   int ra = lo;
   for (; ra + 32 * kTileCols <= hi; ra += 32 * kTileCols)
     tile_pass<kTileCols, false, MODE>(xs, p, ra, 32 * kTileCols, rows, tail_off, add_tail, inv, T, C, gsS, gsV);
+  for (; ra + 64 <= hi; ra += 64)
+    tile_pass<2, false, MODE>(xs, p, ra, 64, rows, tail_off, add_tail, inv, T, C, gsS, gsV);
   for (; ra < hi; ra += 32)
     tile_pass<1, true, MODE>(xs, p, ra, min(hi - ra, 32), rows, tail_off, add_tail, inv, T, C, gsS, gsV);
 }
@@ -361,17 +365,18 @@ __device__ __forceinline__ void hier_range(const double* xs, int g, int lo, int 
   constexpr int J = hier_cols<L>::value;
   int ra = lo;
   for (; ra + 32 * J <= hi; ra += 32 * J) hier_tile<L, J, false>(xs, g, ra, 32 * J, rows, s_in, T, A, scr);
+  if (J > 2)
+    for (; ra + 64 <= hi; ra += 64) hier_tile<L, 2, false>(xs, g, ra, 64, rows, s_in, T, A, scr);
   for (; ra < hi; ra += 32) hier_tile<L, 1, true>(xs, g, ra, min(hi - ra, 32), rows, s_in, T, A, scr);
 }
 
 // One top period q = g * 2^L and every candidate q / 2^k below it.  Non-trunc, non-orth, NORM / GAMMA.
 template <int L>
-__device__ __forceinline__ Best warp_hier_top_L(RankCtx rc, int g, double* scr, Best best) {
+__device__ __forceinline__ Best warp_hier_top_L(RankCtx rc, int g, int M0, int rr, double* scr, Best best) {
+  // M0 = floor(N / g) complete base rows; base residues below rr = N - M0 g have one more row
   const int lane = threadIdx.x & 31;
   const int N = rc.N;
   const double* xs = staged_window();
-  const int M0 = N / g;        // complete base rows
-  const int rr = N - M0 * g;   // base residues below rr have one more row
   // level l (period g 2^l): rows M0 >> l; the first s0 = M0 mod 2^l sets have one more term on every
   // residue, set s0 only on base residues < rr
   int s_inA[L + 1], s_inB[L + 1];
@@ -421,15 +426,42 @@ __device__ __forceinline__ Best warp_hier_top_L(RankCtx rc, int g, double* scr, 
   return best;
 }
 
-__device__ __forceinline__ Best warp_hier_top(const RankCtx& rc, int q, double* scr, Best best) {
-  int L = min(__ffs(q) - 1, 3);
-  while (L > 0 && (q >> L) < rc.pmin) --L;
-  const int g = q >> L;
+// Descriptor of one top q = g 2^L: x = g | L << 16, y = floor(N / g) | (N mod g) << 16.
+// Built once per launch in the order the tops are handed out: grouped by L = min(ctz(q), 3) (capped so
+// that g >= pmin) so that all warps of the SM run the same specialisation at the same time, ascending
+// q inside a group.
+__host__ __device__ inline int hier_top_count(int pmin, int pmax) {
+  const int top_lo = pmin > (pmax >> 1) + 1 ? pmin : (pmax >> 1) + 1;
+  return pmax >= top_lo ? pmax - top_lo + 1 : 0;
+}
+
+static __global__ void tops_kernel(int N, int pmin, int pmax, uint2* __restrict__ tops) {
+  const int top_lo = max(pmin, (pmax >> 1) + 1);
+  const int q = top_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (q > pmax) return;
+  auto level = [&](int t) {
+    int L = min(__ffs(t) - 1, 3);
+    while (L > 0 && (t >> L) < pmin) --L;
+    return L;
+  };
+  const int L = level(q);
+  // rank = tops with a smaller level + tops of the same level below q
+  int rank = 0;
+  for (int t = top_lo; t <= pmax; ++t) {
+    const int lt = level(t);
+    rank += (lt < L) || (lt == L && t < q);
+  }
+  const int g = q >> L, M0 = N / g, rr = N - M0 * g;
+  tops[rank] = make_uint2((unsigned)g | ((unsigned)L << 16), (unsigned)M0 | ((unsigned)rr << 16));
+}
+
+__device__ __forceinline__ Best warp_hier_top(const RankCtx& rc, uint2 e, double* scr, Best best) {
+  const int g = e.x & 0xffff, L = e.x >> 16, M0 = e.y & 0xffff, rr = e.y >> 16;
   switch (L) {
-    case 0: return warp_hier_top_L<0>(rc, g, scr, best);
-    case 1: return warp_hier_top_L<1>(rc, g, scr, best);
-    case 2: return warp_hier_top_L<2>(rc, g, scr, best);
-    default: return warp_hier_top_L<3>(rc, g, scr, best);
+    case 0: return warp_hier_top_L<0>(rc, g, M0, rr, scr, best);
+    case 1: return warp_hier_top_L<1>(rc, g, M0, rr, scr, best);
+    case 2: return warp_hier_top_L<2>(rc, g, M0, rr, scr, best);
+    default: return warp_hier_top_L<3>(rc, g, M0, rr, scr, best);
   }
 }
 
@@ -471,34 +503,19 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   const double thresh = sp->thresh;
   const bool first_hit = thresh >= 0.0;
   Best best{0.0, 0};
-  const bool hier = sp->hier_scr != nullptr && !first_hit && !sp->orth && !sp->trunc &&
+  const bool hier = sp->hier_scr != nullptr && sp->tops != nullptr && !first_hit && !sp->orth && !sp->trunc &&
                     (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
   if (hier) {
-    // tops: candidates p with 2p > pmax; everything else is derived from exactly one of them.
-    // They are handed out grouped by L = min(ctz(q), 3) so that all warps of the SM run the same
-    // specialisation at the same time (the per-(L, J) code does not fit the instruction cache together).
-    const int top_lo = max(pmin, (pmax >> 1) + 1);
-    int first[4], cnt[4], total = 0;
-#pragma unroll
-    for (int l = 0; l < 4; ++l) {
-      const int mod = (l < 3) ? (2 << l) : 8, rem = (l < 3) ? (1 << l) : 0;
-      const int f = top_lo + ((rem - top_lo) % mod + mod) % mod;  // smallest q >= top_lo, q = rem (mod mod)
-      first[l] = f;
-      cnt[l] = f <= pmax ? (pmax - f) / mod + 1 : 0;
-      total += cnt[l];
-    }
+    // tops: candidates p with 2p > pmax; everything else is derived from exactly one of them
+    const uint2* __restrict__ tops = sp->tops;
+    const int total = sp->ntops;
     double* scr = sp->hier_scr + (size_t)wid * sp->hier_len;
     while (true) {
       int idx = 0;
       if (lane == 0) idx = atomicAdd(&sh->counter, 1);
       idx = __shfl_sync(0xffffffffu, idx, 0);
       if (idx >= total) break;
-      int q;
-      if (idx < cnt[0]) q = first[0] + idx * 2;
-      else if ((idx -= cnt[0]) < cnt[1]) q = first[1] + idx * 4;
-      else if ((idx -= cnt[1]) < cnt[2]) q = first[2] + idx * 8;
-      else q = first[3] + (idx - cnt[2]) * 8;
-      best = warp_hier_top(rc, q, scr, best);
+      best = warp_hier_top(rc, __ldg(tops + idx), scr, best);
     }
   } else {
     const int ncand = pmax - pmin + 1;
