@@ -72,7 +72,7 @@ class RamanujanPeriods(QOPeriods):
             nper = torch.zeros((w.b,), **i32)
             _lib.check(lib.pp_ramanujan_select(ptr(norms), w.b, max_length + 1, max_length + 1, float(thresh), kmax,
                                                ptr(periods), ptr(nper), stream_ptr(dev)), "pp_ramanujan_select")
-            need = int(nper.max())
+            need = int(nper.max()) if w.b else 0
             if need <= kmax:
                 break
             kmax = need

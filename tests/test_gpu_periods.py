@@ -294,3 +294,45 @@ def test_device_tensor_io(P):
     host = P().m_best(x.cpu().numpy(), num=4, max_length=300)
     assert np.array_equal(res.periods.cpu().numpy().view(np.uint32), host.periods)
     assert np.array_equal(res.powers.cpu().numpy(), host.powers)
+
+
+# ---------------------------------------------------------------- edge cases
+def test_empty_batch_and_minimal_sizes(P):
+    empty = np.zeros((0, 512))
+    res = P().m_best(empty, num=3, max_length=100)
+    assert res.periods.shape == (0, 3) and res.powers.shape == (0, 3)
+    r2 = P().small_to_large(empty, thresh=0.1)
+    assert r2.count.shape == (0,)
+    assert P.project(empty, 5).shape == (0, 512)
+    # smallest useful window, period equal to the window length, odd length (no TMA alignment)
+    x = synth.synth(7, 1)
+    for p in (1, 2, 3, 7):
+        got = P.project(x, p)
+        if p > 1:   # p = 1 is numpy's pairwise-summation case
+            assert np.array_equal(got, op.project(x, p)), p
+        else:
+            np.testing.assert_allclose(got, op.project(x, p), rtol=1e-15)
+    with pytest.raises(ValueError):
+        P.project(x, 8)
+
+
+def test_scaled_and_offset_windows(P):
+    """Amplitude and DC offset do not change which periods are found (ranking is scale-free), and the
+    batch path treats every row independently."""
+    x = synth.synth(2048, 77)
+    xb = np.stack([x, 1e6 * x, 1e-6 * x, x + 3.0])
+    res = P().m_best_gamma(xb, num=5, max_length=500)
+    for b in range(4):
+        per, pw, _ = op.m_best_gamma(xb[b], 5, 500)
+        assert np.array_equal(res.periods[b], per), b
+        np.testing.assert_allclose(res.powers[b], pw, rtol=RTOL)
+    assert np.array_equal(res.periods[0], res.periods[1]) and np.array_equal(res.periods[0], res.periods[2])
+
+
+def test_large_window_n8192_mbest(P):
+    x = synth.synth(8192, 40_001)
+    per, pw, bs = P().m_best(x, num=4)                # default max_length = 2730: multi-tile tops
+    per0, pw0, bs0 = op.m_best(x, 4)
+    assert np.array_equal(per, per0)
+    np.testing.assert_allclose(pw, pw0, rtol=RTOL)
+    assert np.array_equal(bs, bs0)
