@@ -732,6 +732,7 @@ static int check_common(const void* x, int64_t ldx, int B, int N) {
 int pp_project(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t p, int32_t trunc,
                const int32_t* chain_q_host, int32_t chain_len, double* out, int64_t ldo, int32_t out_len,
                void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (int rc = check_common(x, ldx, B, N)) return rc;
   if (p < 1 || p > N) return fail(-1, "period must satisfy 1 <= p <= N%s");
   if (chain_len < 0 || chain_len > 16) return fail(-1, "chain_len must be in [0,16]%s");
@@ -754,6 +755,7 @@ int pp_project(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t p, in
 }
 
 int pp_periodic_norm(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t p, double* out, void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (x == nullptr || out == nullptr || B < 0 || N < 1 || ldx < 1 || p < 0) return fail(-1, "bad arguments%s");
   if (B == 0) return 0;
   DeviceFacts f;
@@ -768,6 +770,7 @@ int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, i
              int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q, int32_t table_pmax,
              double* metric_out, int32_t* best_p, double* best_val, void* workspace, size_t workspace_bytes,
              void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (int rc = check_common(x, ldx, B, N)) return rc;
   if (pmin < 1 || pmax < pmin || pmax > N) return fail(-1, "need 1 <= pmin <= pmax <= N%s");
   if (metric < 0 || metric > 3) return fail(-1, "unknown metric%s");
@@ -804,6 +807,7 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
              int32_t gamma, int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q,
              const int32_t* fac_off, const int32_t* fac, int32_t table_pmax, uint32_t* periods, double* powers,
              double* bases, int32_t* sweeps, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (int rc = check_common(x, ldx, B, N)) return rc;
   if (num < 1 || num > 4096) return fail(-1, "need 1 <= num <= 4096%s");
   if (pmin < 2 || pmax < pmin || pmax > N) return fail(-1, "need 2 <= pmin <= pmax <= N%s");
@@ -840,6 +844,7 @@ int pp_small_to_large(const double* x, int64_t ldx, int32_t B, int32_t N, double
                       int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q,
                       int32_t table_pmax, int32_t kmax, uint32_t* periods, double* powers, double* bases,
                       int32_t* count, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (int rc = check_common(x, ldx, B, N)) return rc;
   if (!(thresh >= 0.0)) return fail(-1, "thresh must be >= 0%s");
   if (n_periods < 2 || n_periods > N) return fail(-1, "need 2 <= n_periods <= N%s");
@@ -868,6 +873,7 @@ int pp_best_correlation(const double* x, int64_t ldx, int32_t B, int32_t N, int3
                         double ratio, int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q,
                         int32_t table_pmax, uint32_t* periods, double* powers, double* bases, int32_t* status,
                         void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
   (void)workspace;
   (void)workspace_bytes;
   if (int rc = check_common(x, ldx, B, N)) return rc;

@@ -666,6 +666,7 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
                        uint32_t* periods, double* norms, int32_t* n_periods, int32_t* dict_q, int32_t* dict_keep,
                        int32_t* n_dict, int32_t* n_weights, double* weights, double* res, int32_t* status,
                        void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (int rc = qo_check(x, ldx, B, N, num, pmax, rmax, phi, table_pmax)) return rc;
   if (pmin < 1 || pmin > pmax) return fail(-1, "need 1 <= pmin <= pmax%s");
   if (!periods || !norms || !n_periods || !dict_q || !dict_keep || !n_dict || !n_weights || !weights || !status)
@@ -700,6 +701,7 @@ int pp_qo_solve(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t kmax
                 const int32_t* nper, int32_t pmax, const int32_t* phi, int32_t table_pmax, int32_t rmax,
                 int32_t* dict_q, int32_t* dict_keep, int32_t* n_dict, int32_t* n_weights, double* weights,
                 double* res, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (int rc = qo_check(x, ldx, B, N, kmax, pmax, rmax, phi, table_pmax)) return rc;
   if (!periods || !nper || !dict_q || !dict_keep || !n_dict || !n_weights || !weights || !status)
     return fail(-1, "pointers are null%s");

@@ -257,6 +257,7 @@ size_t pp_ramanujan_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32
 int pp_ramanujan_norms(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
                        const int32_t* mu, const int32_t* phi, int32_t table_qmax, int32_t tile_windows,
                        double* norms, int32_t ld_norms, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (x == nullptr || norms == nullptr || B < 0 || N < 2 || ldx < 1) return fail(-1, "bad window arguments%s");
   if (qmin < 1 || qmax < qmin || qmax > N) return fail(-1, "need 1 <= qmin <= qmax <= N%s");
   if (mu == nullptr || phi == nullptr || table_qmax < qmax) return fail(-1, "mu/phi tables must cover qmax%s");
@@ -292,6 +293,7 @@ int pp_ramanujan_norms(const double* x, int64_t ldx, int32_t B, int32_t N, int32
 // (RamanujanPeriods.py:97-101).  nper[b] may exceed kmax; only the first kmax are stored.
 int pp_ramanujan_select(const double* norms, int32_t B, int32_t ld_norms, int32_t qlen, double thresh, int32_t kmax,
                         int32_t* periods, int32_t* nper, void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (!norms || !periods || !nper || B < 0 || qlen < 1 || ld_norms < qlen || kmax < 1)
     return fail(-1, "bad select arguments%s");
   if (B == 0) return 0;
