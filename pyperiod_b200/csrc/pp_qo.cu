@@ -30,7 +30,7 @@ struct QoPlan {
   __host__ __device__ size_t off_chol() const { return off_wv() + (size_t)rmax * 8; }
   // Cholesky tiles and the hierarchical-sweep scratch are never live together
   __host__ __device__ size_t chol_bytes() const {
-    const size_t a = (size_t)(kCholNb * (kCholNb + 1) + kCholNb) * 8;
+    const size_t a = (size_t)(2 * kCholNb * (kCholNb + 1) + kCholNb) * 8;
     const size_t b = (size_t)kWarps * hier_len * 8;
     return a > b ? a : b;
   }
@@ -59,8 +59,9 @@ __host__ __device__ inline QoPlan make_qo_plan(int N, int pmax, int num, int rma
 // Returns false (uniformly) when a pivot is not positive: the reference raises LinAlgError there.
 // ------------------------------------------------------------------------------------------
 struct CholSmem {
-  double* D;    // [32][33] diagonal block
-  double* rD;   // [32] reciprocals of its diagonal
+  double* D;    // [32][33] diagonal block (factor L after step 1)
+  double* rD;   // [32] column broadcast buffer
+  double* Li;   // [32][33] inverse of the factored block
 };
 
 __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __restrict__ Pt, const CholSmem& cs,
@@ -78,27 +79,41 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
     }
     __syncthreads();
     if (wid == 0) {
+      // lane owns row `lane` of the block in registers; column k is broadcast through cs.rD each step
+      double r[kCholNb];
+#pragma unroll
+      for (int c = 0; c < kCholNb; ++c) r[c] = cs.D[lane * (kCholNb + 1) + c];
       bool ok = true;
-      for (int k = 0; k < nb; ++k) {
-        double d = cs.D[k * (kCholNb + 1) + k];
-        if (!(d > 1e-8)) {
-          ok = false;
-          break;
-        }
-        d = sqrt(d);
-        double l = 0.0;
-        if (lane > k && lane < nb) {
-          l = cs.D[lane * (kCholNb + 1) + k] / d;
-          cs.D[lane * (kCholNb + 1) + k] = l;
-        }
-        if (lane == k) cs.D[k * (kCholNb + 1) + k] = d;
+#pragma unroll
+      for (int k = 0; k < kCholNb; ++k) {
+        const double dkk = __shfl_sync(0xffffffffu, r[k], k);
+        if (k < nb && !(dkk > 1e-8)) ok = false;   // uniform: every lane sees the same pivot
+        const double d = sqrt(ok ? dkk : 1.0);
+        const double l = (lane > k) ? r[k] / d : (lane == k ? d : 0.0);
+        r[k] = l;
+        cs.rD[lane] = l;
         __syncwarp();
-        if (lane > k && lane < nb)
-          for (int j = k + 1; j <= lane; ++j) cs.D[lane * (kCholNb + 1) + j] -= l * cs.D[j * (kCholNb + 1) + k];
+#pragma unroll
+        for (int j = k + 1; j < kCholNb; ++j) r[j] = fma(-l, cs.rD[j], r[j]);   // only j <= lane is ever used
         __syncwarp();
       }
       if (!ok && lane == 0) *flag = 1;
-      if (ok) cs.rD[lane] = 1.0 / cs.D[lane * (kCholNb + 1) + lane];
+#pragma unroll
+      for (int c = 0; c < kCholNb; ++c) cs.D[lane * (kCholNb + 1) + c] = (c <= lane) ? r[c] : 0.0;
+      __syncwarp();
+      // inverse of the block, X = L^-1 (lower triangular): lane c solves column c by forward substitution
+      double xcol[kCholNb];
+#pragma unroll
+      for (int rr = 0; rr < kCholNb; ++rr) {
+        double v = (rr == lane) ? 1.0 : 0.0;
+#pragma unroll
+        for (int m = 0; m < rr; ++m) v = fma(-cs.D[rr * (kCholNb + 1) + m], xcol[m], v);
+        xcol[rr] = (rr >= lane) ? v / cs.D[rr * (kCholNb + 1) + rr] : 0.0;
+      }
+      __syncwarp();
+      // store transposed: cs.Li[c][m] = X[c][m] is what the panel needs (out[c] = sum_m row[m] X[c][m])
+#pragma unroll
+      for (int rr = 0; rr < kCholNb; ++rr) cs.Li[rr * (kCholNb + 1) + lane] = xcol[rr];
     }
     __syncthreads();
     if (*flag) return false;
@@ -115,13 +130,16 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
       double* a = A + (size_t)i * ld + kb;
 #pragma unroll
       for (int c = 0; c < kCholNb; ++c) row[c] = (c < nb) ? a[c] : 0.0;
+      double outv[kCholNb];
 #pragma unroll
       for (int c = 0; c < kCholNb; ++c) {
-        double v = row[c];
+        double v = 0.0;
 #pragma unroll
-        for (int m = 0; m < c; ++m) v = fma(-row[m], cs.D[c * (kCholNb + 1) + m], v);
-        row[c] = v * cs.rD[c];
+        for (int m = 0; m <= c; ++m) v = fma(row[m], cs.Li[c * (kCholNb + 1) + m], v);
+        outv[c] = v;
       }
+#pragma unroll
+      for (int c = 0; c < kCholNb; ++c) row[c] = outv[c];
 #pragma unroll
       for (int c = 0; c < kCholNb; ++c) {
         if (c < nb) a[c] = row[c];
@@ -438,6 +456,7 @@ __device__ __forceinline__ QoCtx make_ctx(unsigned char* smem, const QoPlan& pl,
   double* chol = reinterpret_cast<double*>(smem + pl.off_chol());
   c.cs.D = chol;
   c.cs.rD = chol + kCholNb * (kCholNb + 1);
+  c.cs.Li = c.cs.rD + kCholNb;
   c.red = reinterpret_cast<double*>(smem + pl.off_red());
   int* ints = reinterpret_cast<int*>(smem + pl.off_ints());
   c.found = ints;
