@@ -124,6 +124,25 @@ def best_correlation(x: np.ndarray, num: int = 5, max_length=None, ratio: float 
     return periods, norms, bases
 
 
+def best_frequency(x: np.ndarray, win_size=None, num: int = 5, trunc: bool = False, orth: bool = False):
+    """Periods.py:351-398 (FFT peak -> period -> projection).  Listed as "next" in SURVEY.md 8f."""
+    if win_size is None:
+        win_size = len(x)
+    periods = np.zeros(num, dtype=np.uint32)
+    norms = np.zeros(num)
+    bases = np.zeros((num, len(x)))
+    work = x.copy()
+    for i in range(num):
+        mags = np.abs(np.fft.rfft(work, win_size))
+        p = int(np.round((2 * win_size) / np.argmax(mags)))
+        base = project(work, p, trunc, orth)
+        periods[i] = p
+        norms[i] = periodic_norm(base)
+        bases[i] = base
+        work = work - base
+    return periods, norms / periodic_norm(x), bases
+
+
 def m_best_meta(x: np.ndarray, gamma: bool, num: int = 5, max_length=None, min_length: int = 2,
                 trunc: bool = False, orth: bool = False, stats: dict | None = None):
     """M-best / M-best-gamma.  Periods.py:456-601.

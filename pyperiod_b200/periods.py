@@ -292,6 +292,52 @@ class Periods:
             return res.periods[0], res.powers[0], (None if res.bases is None else res.bases[0])
         return res
 
+    # ------------------------------------------------------------------ best frequency
+    def best_frequency(self, *args, **kw):
+        """Best-frequency (Periods.py:351-398).  best_frequency([data,] win_size=None, num=5).
+
+        Not on the north-star hot path: the spectrum comes from torch.fft (cuFFT), the
+        projection and residual update from this library's exact projection kernel.  1-D or (B, N).
+        Like the reference, a window whose DC bin is the largest gives p = round(2*win/0) -> error.
+        """
+        data, pos = self._split(args, ["win_size", "num"])
+        kw = {**pos, **kw}
+        win_size = kw.pop("win_size", None)
+        num = int(kw.pop("num", 5))
+        if kw:
+            raise TypeError(f"unexpected arguments {sorted(kw)}")
+        w = stage_windows(data, self._device)
+        n = w.n
+        if win_size is None:
+            win_size = n
+        elif win_size < n:
+            warn("win_size is smaller than the input signal length. It will be truncated and information will be lost.")
+        x = torch.as_strided(w.tensor, (w.b, n), (w.ldx, 1)).clone()
+        data_norm = Periods.periodic_norm(x, device=w.device)
+        periods = torch.zeros((w.b, num), dtype=torch.int32, device=w.device)
+        norms = torch.zeros((w.b, num), dtype=torch.float64, device=w.device)
+        bases = torch.zeros((w.b, num, n), dtype=torch.float64, device=w.device)
+        for i in range(num):
+            mags = torch.abs(torch.fft.rfft(x, win_size, dim=1))
+            peak = torch.argmax(mags, dim=1)
+            if bool((peak == 0).any()):
+                raise ZeroDivisionError("best_frequency: the DC bin is the spectral peak (p = 2*win/0), as in the reference")
+            p = torch.round((2.0 * win_size) / peak.double()).to(torch.int32)
+            # windows sharing a period are projected together (one kernel launch per distinct period)
+            for pv in torch.unique(p).tolist():
+                rows = torch.nonzero(p == pv).flatten()
+                base = Periods.project(x[rows], int(pv), self._trunc_to_integer_multiple, self._orthogonalize)
+                bases[rows, i] = base
+                norms[rows, i] = Periods.periodic_norm(base, device=w.device)
+                x[rows] = x[rows] - base
+            periods[:, i] = p
+        powers = norms / data_norm[:, None]
+        res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases),
+                          _export(w, torch.zeros((w.b,), dtype=torch.int32, device=w.device)))
+        if w.was_1d:
+            return res.periods[0], res.powers[0], res.bases[0]
+        return res
+
     # ------------------------------------------------------------------ properties (Periods.py:606-644)
     @property
     def trunc_to_integer_multiple(self):

@@ -336,3 +336,20 @@ def test_large_window_n8192_mbest(P):
     assert np.array_equal(per, per0)
     np.testing.assert_allclose(pw, pw0, rtol=RTOL)
     assert np.array_equal(bs, bs0)
+
+
+def test_best_frequency_vs_oracle(P):
+    """Periods.best_frequency (SURVEY.md 8f 'next' #1): cuFFT spectrum + this library's exact projection."""
+    for seed, (trunc, orth) in ((901, (False, False)), (902, (True, True))):
+        x = synth.synth(2000, seed)
+        per, pw, bs = P(trunc, orth).best_frequency(x, num=4)
+        per0, pw0, bs0 = op.best_frequency(x, None, 4, trunc, orth)
+        assert np.array_equal(per, per0)
+        np.testing.assert_allclose(pw, pw0, rtol=RTOL)
+        np.testing.assert_allclose(bs, bs0, rtol=RTOL, atol=1e-14)
+    xb = synth.synth_batch(3, 1024, 950)
+    res = P().best_frequency(xb, num=3)
+    for b in range(3):
+        per0, pw0, _ = op.best_frequency(xb[b], None, 3)
+        assert np.array_equal(res.periods[b], per0)
+        np.testing.assert_allclose(res.powers[b], pw0, rtol=RTOL)
