@@ -127,7 +127,7 @@ def run_reference(args, rank: int):
         return
     from pyperiod_b200 import synth
     cores = host_cores()
-    per_step = max(16, 4 * cores)
+    per_step = 16 * cores
     stream = synth.synth_stream(per_step, N_WIN, HOP, 30_000)
     wins = sample_windows(stream, per_step)
     pool = OraclePool(cores)
@@ -145,7 +145,7 @@ def run_reference(args, rank: int):
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(per_step, 1, "host"),
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": f"{per_step} windows per step (4 per core), oracle numpy port of Periods.m_best, "
+                         "sample": f"{per_step} windows per step (16 per core), oracle numpy port of Periods.m_best, "
                                    f"one process per core"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -184,12 +184,12 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     stream = synth.synth_stream(B, N_WIN, HOP, 30_000, first_segment=first_seg)
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cores = host_cores()
-        n_s = max(16, 2 * cores)
+        n_s = 64 * cores   # ~10-20 s of CPU work at ~0.16 s per window per core
         pool = OraclePool(cores)
         oracle_out, dt = pool.run(sample_windows(stream, n_s))
         pool.close()
         cpu = {"value": n_s / dt, "unit": UNIT, "cores": cores, "kind": "port",
-               "sample": f"first {n_s} windows of the GPU run's own stream (2 per core), oracle numpy port of "
+               "sample": f"first {n_s} windows of the GPU run's own stream (64 per core), oracle numpy port of "
                          f"Periods.m_best, one process per core, {dt:.1f} s wall"}
 
     # ---- measured roofline denominators (outside any timed region)
@@ -300,7 +300,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "ms_per_step": ms_e2e / e2e_steps,
                     "api": "Periods().m_best(pinned host (B,4096) hop-512 view, num=10, max_length=1024) -> numpy"},
-            "gpu_launches": args.steps,  # one pp::mbest_kernel launch per step
+            "gpu_launches": 2 * args.steps,  # per step: pp::tops_kernel (descriptor table, ~2 us) + pp::mbest_kernel
             "roofline": {
                 "kernel": "pp::mbest_kernel", "bound": "smem",
                 "achieved": smem_bps / 1e9, "peak": smem_peak["per_s"] / 1e9, "unit": "GB/s",
