@@ -120,7 +120,10 @@ __device__ __forceinline__ double rcp_of(const double* rcp, int m) {
 // body of a residue range, one column for what is left -- so the hot loops are a few hundred bytes
 // of code that every warp of the SM shares.  (A dispatch over 12 tile widths, tried first, lost
 // 30 % to instruction-fetch stalls; predicated partial tiles made the compiler spill.)
-constexpr int kTileCols = 4;
+#ifndef PP_TILECOLS
+#define PP_TILECOLS 4
+#endif
+constexpr int kTileCols = PP_TILECOLS;
 
 // acc[j] += row[32 j]: the loads of a row are issued together, then the adds
 template <int J>
@@ -355,7 +358,7 @@ __device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, 
 // register columns per accumulator set of a hierarchical tile: at most 16 accumulators per lane
 template <int L>
 struct hier_cols {
-  static constexpr int value = (L == 3) ? 2 : kTileCols;
+  static constexpr int value = (16 >> L) < kTileCols ? (16 >> L) : kTileCols;  // 2^L sets x J columns <= 16
 };
 
 // base residues [lo, hi) of a top: tiles of J columns, then single columns (the last one masked)

@@ -353,3 +353,29 @@ def test_best_frequency_vs_oracle(P):
         per0, pw0, _ = op.best_frequency(xb[b], None, 3)
         assert np.array_equal(res.periods[b], per0)
         np.testing.assert_allclose(res.powers[b], pw0, rtol=RTOL)
+
+
+# ---------------------------------------------------------------- randomized differential sweep
+@pytest.mark.parametrize("trunc", [False, True])
+def test_differential_many_windows(P, trunc):
+    """48 random windows x 4 algorithms against the oracle: period lists exact, powers <= 1e-10."""
+    xb = synth.synth_batch(48, 1024, 777_000 + int(trunc))
+    inst = P(trunc, False)
+    mb = inst.m_best(xb, num=6, max_length=300)
+    mg = inst.m_best_gamma(xb, num=6, max_length=300)
+    sl = inst.small_to_large(xb, thresh=0.08)
+    bc = inst.best_correlation(xb, num=4, max_length=300)
+    for b in range(48):
+        per, pw, _ = op.m_best(xb[b], 6, 300, 2, trunc)
+        assert np.array_equal(mb.periods[b], per), ("m_best", b)
+        np.testing.assert_allclose(mb.powers[b], pw, rtol=RTOL)
+        per, pw, _ = op.m_best_gamma(xb[b], 6, 300, 2, trunc)
+        assert np.array_equal(mg.periods[b], per), ("gamma", b)
+        np.testing.assert_allclose(mg.powers[b], pw, rtol=RTOL)
+        per, pw, _ = op.small_to_large(xb[b], 0.08, None, trunc)
+        k = int(sl.count[b])
+        assert sl.periods[b, :k].tolist() == per, ("s2l", b)
+        np.testing.assert_allclose(sl.powers[b, :k], pw, rtol=1e-9)
+        per, pw, _ = op.best_correlation(xb[b], 4, 300, 0.01, trunc)
+        assert np.array_equal(bc.periods[b], per), ("bcorr", b)
+        np.testing.assert_allclose(bc.powers[b], pw, rtol=RTOL, atol=1e-15)
