@@ -186,6 +186,7 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
       sp.data_norm = metric == PP_METRIC_IMPOSED ? sqrt(e_res) / sp.sqrtN : 1.0;
       sp.thresh = -1.0;
       sp.skip = nullptr;
+      sp.nskip = 0;
       sp.hier_scr = sm.hier;
       sp.hier_len = pl.hier_len;
       sp.rcp = sm.sweep->rcp;
@@ -290,6 +291,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.data_norm = 1.0;
       sp.thresh = -1.0;
       sp.skip = sm.skip;
+      sp.nskip = 0;
       sp.metric_out = nullptr;
       sp.hier_scr = sm.hier;
       sp.hier_len = pl.hier_len;
@@ -328,6 +330,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
           misc[3] = sm.slot[found];
         } else if (found >= 0) {                   // blacklist it (:525-529)
           sm.skip[top.p >> 5] |= 1u << (top.p & 31);
+          sm.sweep->params.nskip += 1;
           misc[1] = 0;
           misc[2] = 1;
         } else {                                   // new slot (:530-535)
@@ -519,6 +522,7 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
       sp.data_norm = sqrt(e_data) / sqrtN;
       sp.thresh = thresh < 0.0 ? 0.0 : thresh;
       sp.skip = nullptr;
+      sp.nskip = 0;
       sp.metric_out = nullptr;
       sp.hier_scr = nullptr;
       sp.hier_len = 0;
@@ -601,6 +605,7 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.data_norm = 1.0;
       sp.thresh = -1.0;
       sp.skip = nullptr;
+      sp.nskip = 0;
       sp.metric_out = nullptr;
       sp.hier_scr = nullptr;
       sp.hier_len = 0;

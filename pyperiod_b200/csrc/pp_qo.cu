@@ -547,6 +547,7 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
       sp.data_norm = 1.0;
       sp.thresh = -1.0;
       sp.skip = nullptr;
+      sp.nskip = 0;
       sp.metric_out = nullptr;
       sp.hier_scr = pl.hier_len ? reinterpret_cast<double*>(smem + pl.off_chol()) : nullptr;
       sp.hier_len = pl.hier_len;

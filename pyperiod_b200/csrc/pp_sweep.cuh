@@ -50,6 +50,7 @@ struct SweepParams {
   double data_norm;   // ||x||/sqrt(N)    (IMPOSED)
   double thresh;      // IMPOSED early-stop threshold; <0 disables first-hit mode
   const uint32_t* skip;  // bitmap of periods to ignore (M-best), nullable
+  int nskip;             // number of bits set in skip (0 => the bitmap is not consulted)
   double* metric_out;    // global [pmax+1], nullable
   double* hier_scr;      // shared scratch of the hierarchical sweep: kWarps * hier_len doubles (nullable => direct)
   int hier_len;
@@ -97,7 +98,7 @@ struct RankCtx {
   int pmin;
 };
 __device__ __forceinline__ RankCtx rank_ctx(const SweepParams* sp) {
-  return RankCtx{sp->skip, sp->metric_out, sp->rcp, sp->sqrtN, sp->metric, sp->N, sp->pmin};
+  return RankCtx{sp->nskip > 0 ? sp->skip : nullptr, sp->metric_out, sp->rcp, sp->sqrtN, sp->metric, sp->N, sp->pmin};
 }
 
 __device__ __forceinline__ void consider(const RankCtx& rc, double key, int p, Best& best) {
@@ -124,6 +125,24 @@ __device__ __forceinline__ double rcp_of(const double* rcp, int m) {
 #define PP_TILECOLS 4
 #endif
 constexpr int kTileCols = PP_TILECOLS;
+
+// sum of squares of J values as a short tree (no J-long dependent FMA chain)
+template <int J>
+__device__ __forceinline__ double sum_sq(const double (&v)[J]) {
+  if constexpr (J == 1) {
+    return v[0] * v[0];
+  } else if constexpr (J == 2) {
+    return fma(v[1], v[1], v[0] * v[0]);
+  } else {
+    double lo = v[0] * v[0], hi = v[1] * v[1];
+#pragma unroll
+    for (int j = 2; j < J; j += 2) {
+      lo = fma(v[j], v[j], lo);
+      if (j + 1 < J) hi = fma(v[j + 1], v[j + 1], hi);
+    }
+    return lo + hi;
+  }
+}
 
 // acc[j] += row[32 j]: the loads of a row are issued together, then the adds
 template <int J>
@@ -168,10 +187,10 @@ __device__ __forceinline__ void tile_pass(const double* __restrict__ xs, int p, 
       for (int j = 0; j < J; ++j)
         if (lane + 32 * j >= nres) acc[j] = 0.0;
     }
+    T += sum_sq<J>(acc);
+    if (MODE == kPassEnergyTail) {
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      T = fma(acc[j], acc[j], T);
-      if (MODE == kPassEnergyTail) C = fma(acc[j], xs[tail_off + ra + lane + 32 * j], C);
+      for (int j = 0; j < J; ++j) C = fma(acc[j], xs[tail_off + ra + lane + 32 * j], C);
     }
   } else if (MODE == kPassMaxAbs) {
 #pragma unroll
@@ -287,9 +306,7 @@ struct hier_levels {
     constexpr int sets = 1 << LV;
 #pragma unroll
     for (int s = 0; s < sets; ++s) {
-      double q = 0.0;
-#pragma unroll
-      for (int j = 0; j < J; ++j) q = fma(acc[s][j], acc[s][j], q);
+      double q = sum_sq<J>(acc[s]);
       T[LV] += q;
       if (s < s_in[LV]) A[LV] += q;  // warp-uniform
     }
