@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpyperiod_b200.so")
+# PYPERIOD_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
+LIB_PATH = os.environ.get("PYPERIOD_B200_LIB") or os.path.join(HERE, "libpyperiod_b200.so")
 
 ABI_VERSION = 1
 

@@ -42,20 +42,26 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > built for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False, defines=()) -> str:
-    """Build libpyperiod_b200.so if missing or older than its sources; return its path."""
+def build(force: bool = False, verbose: bool = False, defines=(), out: str | None = None) -> str:
+    """Build libpyperiod_b200.so if missing or older than its sources; return its path.
+
+    `out` names an alternative output file (tuning variants built with `-D...`; load one by
+    setting PYPERIOD_B200_LIB)."""
+    if out is not None:
+        force = True
     if not force and not _stale():
         return LIB_PATH
     cmd = [_nvcc()] + NVCC_FLAGS + [f"-D{d}" for d in defines] + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
+          ["-o", out or LIB_PATH] + [os.path.join(CSRC, s) for s in SOURCES]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if verbose or proc.returncode != 0:
         sys.stderr.write(proc.stdout + proc.stderr)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed building " + LIB_NAME)
-    return LIB_PATH
+    return out or LIB_PATH
 
 
 if __name__ == "__main__":
+    outs = [a[6:] for a in sys.argv if a.startswith("--out=")]
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv,
-                defines=[a[2:] for a in sys.argv if a.startswith("-D")]))
+                defines=[a[2:] for a in sys.argv if a.startswith("-D")], out=outs[0] if outs else None))

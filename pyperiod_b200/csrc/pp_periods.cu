@@ -214,14 +214,31 @@ __device__ __forceinline__ double warp_slot_factor_norm(const double* slot, int 
   const int t = P / f;
   const int Mf = N / f, r0f = N - Mf * f;
   double e = 0.0;
-  for (int r = lane; r < f; r += 32) {
-    const int K = trunc ? Mf : (Mf + (r < r0f ? 1 : 0));
-    const int base = K / t, rem = K - base * t;
-    double s = 0.0;
-    for (int j = 0; j < t; ++j) s = fma((double)(base + (j < rem ? 1 : 0)), slot[r + j * f], s);
-    const double mean = s / (double)K;
-    if (orth) scr[r] = mean;
-    else e = fma((double)(Mf + (r < r0f ? 1 : 0)) * mean, mean, e);
+  if (f < 32) {
+    // few residues, long sums: the lanes split the t terms of one residue and reduce (fixed tree order)
+    for (int r = 0; r < f; ++r) {
+      const int K = trunc ? Mf : (Mf + (r < r0f ? 1 : 0));
+      const int base = K / t, rem = K - base * t;
+      double s = 0.0;
+      for (int j = lane; j < t; j += 32) s = fma((double)(base + (j < rem ? 1 : 0)), slot[r + j * f], s);
+      s = warp_sum(s);
+      const double mean = s / (double)K;
+      if (orth) {
+        if (lane == 0) scr[r] = mean;
+      } else if (lane == 0) {
+        e = fma((double)(Mf + (r < r0f ? 1 : 0)) * mean, mean, e);
+      }
+    }
+  } else {
+    for (int r = lane; r < f; r += 32) {
+      const int K = trunc ? Mf : (Mf + (r < r0f ? 1 : 0));
+      const int base = K / t, rem = K - base * t;
+      double s = 0.0;
+      for (int j = 0; j < t; ++j) s = fma((double)(base + (j < rem ? 1 : 0)), slot[r + j * f], s);
+      const double mean = s / (double)K;
+      if (orth) scr[r] = mean;
+      else e = fma((double)(Mf + (r < r0f ? 1 : 0)) * mean, mean, e);
+    }
   }
   if (orth) {
     __syncwarp();

@@ -123,7 +123,10 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
       if (c <= r) A[(size_t)(kb + r) * ld + kb + c] = cs.D[r * (kCholNb + 1) + c];
     }
     const int below = R - kb - nb;
-    if (below <= 0) break;
+    if (below <= 0) {
+      __syncthreads();  // cs.D is restaged by the caller's next step: every write-back read must be done
+      break;
+    }
     // (2) panel: one thread per row, forward substitution against the diagonal block
     for (int i = kb + nb + tid; i < R; i += kThreads) {
       double row[kCholNb];

@@ -16,10 +16,10 @@
 // from the window; S_p for every smaller candidate follows from S_2p[r] + S_2p[r + p].  A top
 // q = g * 2^L (L <= 3) is folded at base period g with 2^L accumulator sets selected by
 // (row mod 2^L); pairwise in-register adds give q/2 .. g, and if g is still even the chain goes on
-// through a small per-warp scratch.  Because g divides every level period, the A/B boundary in the
-// base residue (rr = N mod g) is the same for all levels; a level only differs in how many leading
-// sets count as "M+1 terms".  Half the shared-memory traffic of the direct sweep; sums differ from
-// the sequential ones by rounding only.
+// through a small per-warp scratch.  Because g divides every level period, the boundary in the base
+// residue (rr = N mod g) below which a residue has one more term is the same for all levels; a level
+// only differs in how many sets hold one more complete row.  Half the shared-memory traffic of the
+// direct sweep; sums differ from the sequential ones by rounding only.
 //
 // Candidates are ranked by the squared metric (energy, or energy / p compared by cross
 // multiplication); the square root and divisions are taken once, for the winner.
@@ -296,122 +296,133 @@ __device__ __forceinline__ double warp_period_key_any(const SweepParams* sp, int
 // ------------------------------------------------------------------------------------------
 __host__ __device__ inline int hier_scratch_len(int pmax) { return ((((pmax >> 3) + 2) * 3) / 2 + 3) & ~1; }
 
+// Rows are assigned to the 2^L accumulator sets by (row - M0) mod 2^L, M0 = floor(N / g): the partial
+// tail row (row M0, base residues < rr = N mod g) always lands in set 0, the complete rows fill the
+// sets cyclically, and at level l (period g 2^l, 2^l sets) the sets with index >= 2^l - (M0 mod 2^l)
+// hold one more term on every residue.  A tile therefore covers the whole residue range [0, g) with
+// one code path: no split at rr, the tail row is a predicated load.
+//
 // compile-time recursion over the levels l = LV .. 0 (keeps every accumulator index static).
-// For level l the tile contributes q_s = sum_j acc[s][j]^2 of each of its 2^l sets to T[l], and to
-// A[l] when the set index is below s_in[l] (the sets whose residues have one more term).
+// For level l the tile contributes q_s = sum_j acc[s][j]^2 of each of its 2^l sets to T[l], and to A[l]
+// (residues with one more term) for the warp-uniform top sets and, lane by lane, for set 0 under the tail.
 template <int L, int J, int LV>
 struct hier_levels {
-  static __device__ __forceinline__ void run(double (&acc)[1 << L][J], const int (&s_in)[L + 1], double (&T)[L + 1],
-                                             double (&A)[L + 1]) {
+  static __device__ __forceinline__ void run(double (&acc)[1 << L][J], int M0, const bool (&tail)[J],
+                                             double (&T)[L + 1], double (&A)[L + 1]) {
     constexpr int sets = 1 << LV;
+    const int extra = M0 & (sets - 1);
 #pragma unroll
     for (int s = 0; s < sets; ++s) {
-      double q = sum_sq<J>(acc[s]);
+      const double q = sum_sq<J>(acc[s]);
       T[LV] += q;
-      if (s < s_in[LV]) A[LV] += q;  // warp-uniform
+      if (s >= sets - extra) A[LV] += q;  // warp-uniform
     }
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+      if (tail[j]) A[LV] = fma(acc[0][j], acc[0][j], A[LV]);
     if constexpr (LV > 0) {
       constexpr int half = sets >> 1;
 #pragma unroll
       for (int s = 0; s < half; ++s)
 #pragma unroll
         for (int j = 0; j < J; ++j) acc[s][j] += acc[s + half][j];
-      hier_levels<L, J, LV - 1>::run(acc, s_in, T, A);
+      hier_levels<L, J, LV - 1>::run(acc, M0, tail, T, A);
     }
   }
 };
 
-// One register tile of a top q = g * 2^L: base residues [ra, ra + nres), nres <= 32 J, `rows` base
-// rows distributed over 2^L accumulator sets by (row mod 2^L).
-template <int L, int J, bool PARTIAL>
-__device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, int ra, int nres, int rows,
-                                          const int (&s_in)[L + 1], double (&T)[L + 1], double (&A)[L + 1],
-                                          double* scr) {
+// One register tile of a top q = g * 2^L: base residues ra + lane + 32 j (j < J), all M0 complete base
+// rows plus the tail row.  MASK: the tile may run past g (lanes beyond it are zeroed before the energies).
+template <int L, int J, bool MASK>
+__device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, int ra, int M0, int rr,
+                                          double (&T)[L + 1], double (&A)[L + 1], double* scr) {
   constexpr int S = 1 << L;
   const int lane = threadIdx.x & 31;
   const double* ptr = xs + ra + lane;
   double acc[S][J];
-  if (S == 1) {
-    fold_rows<J>(acc[0], ptr, g, rows);
+  if constexpr (S == 1) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[0][j] = ptr[32 * j];
+    ptr += g;
+#pragma unroll 2
+    for (int k = 1; k < M0; ++k) {
+      add_row<J>(acc[0], ptr);
+      ptr += g;
+    }
   } else {
 #pragma unroll
     for (int s = 0; s < S; ++s)
 #pragma unroll
       for (int j = 0; j < J; ++j) acc[s][j] = 0.0;
-    int k = 0;
+    const int head = M0 & (S - 1);  // rows before the first complete group of S
+#pragma unroll
+    for (int s = 1; s < S; ++s) {
+      if (s >= S - head) {
+        add_row<J>(acc[s], ptr);
+        ptr += g;
+      }
+    }
 #pragma unroll 1
-    for (; k + S <= rows; k += S) {
+    for (int i = M0 >> L; i > 0; --i) {
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         add_row<J>(acc[s], ptr);
         ptr += g;
       }
     }
-#pragma unroll
-    for (int s = 0; s < S - 1; ++s) {
-      if (k + s < rows) {
-        add_row<J>(acc[s], ptr);
-        ptr += g;
-      }
-    }
   }
-  if (PARTIAL) {
+  bool tail[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    tail[j] = ra + lane + 32 * j < rr;
+    double t = 0.0;
+    if (tail[j]) t = ptr[32 * j];
+    acc[0][j] += t;
+  }
+  if (MASK) {
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      if (lane + 32 * j >= nres) {
+      if (ra + lane + 32 * j >= g) {
 #pragma unroll
         for (int s = 0; s < S; ++s) acc[s][j] = 0.0;
       }
     }
   }
-  hier_levels<L, J, L>::run(acc, s_in, T, A);
+  hier_levels<L, J, L>::run(acc, M0, tail, T, A);
   if (scr != nullptr) {
 #pragma unroll
     for (int j = 0; j < J; ++j)
-      if (lane + 32 * j < nres) scr[ra + lane + 32 * j] = acc[0][j];
+      if (!MASK || ra + lane + 32 * j < g) scr[ra + lane + 32 * j] = acc[0][j];
   }
 }
 
-// register columns per accumulator set of a hierarchical tile: at most 16 accumulators per lane
+// register columns per accumulator set of a hierarchical tile: 16 accumulators per lane, at most 8 columns
+#ifndef PP_HIER_ACCS
+#define PP_HIER_ACCS 16
+#endif
 template <int L>
 struct hier_cols {
-  static constexpr int value = (16 >> L) < kTileCols ? (16 >> L) : kTileCols;  // 2^L sets x J columns <= 16
+  static constexpr int value = (PP_HIER_ACCS >> L) < 8 ? (PP_HIER_ACCS >> L) : 8;
 };
-
-// base residues [lo, hi) of a top: tiles of J columns, then single columns (the last one masked)
-template <int L>
-__device__ __forceinline__ void hier_range(const double* xs, int g, int lo, int hi, int rows, const int (&s_in)[L + 1],
-                                           double (&T)[L + 1], double (&A)[L + 1], double* scr) {
-  constexpr int J = hier_cols<L>::value;
-  int ra = lo;
-  for (; ra + 32 * J <= hi; ra += 32 * J) hier_tile<L, J, false>(xs, g, ra, 32 * J, rows, s_in, T, A, scr);
-  if (J > 2)
-    for (; ra + 64 <= hi; ra += 64) hier_tile<L, 2, false>(xs, g, ra, 64, rows, s_in, T, A, scr);
-  for (; ra < hi; ra += 32) hier_tile<L, 1, true>(xs, g, ra, min(hi - ra, 32), rows, s_in, T, A, scr);
-}
 
 // One top period q = g * 2^L and every candidate q / 2^k below it.  Non-trunc, non-orth, NORM / GAMMA.
 template <int L>
 __device__ __forceinline__ Best warp_hier_top_L(RankCtx rc, int g, int M0, int rr, double* scr, Best best) {
-  // M0 = floor(N / g) complete base rows; base residues below rr = N - M0 g have one more row
+  // M0 = floor(N / g) complete base rows; base residues below rr = N - M0 g have one more (tail) row
+  constexpr int J = hier_cols<L>::value;
   const int lane = threadIdx.x & 31;
   const int N = rc.N;
   const double* xs = staged_window();
-  // level l (period g 2^l): rows M0 >> l; the first s0 = M0 mod 2^l sets have one more term on every
-  // residue, set s0 only on base residues < rr
-  int s_inA[L + 1], s_inB[L + 1];
-#pragma unroll
-  for (int i = 0; i <= L; ++i) {
-    s_inB[i] = M0 & ((1 << i) - 1);
-    s_inA[i] = s_inB[i] + 1;
-  }
   const bool chain = (L == 3) && !(g & 1) && (g >> 1) >= rc.pmin;
   double* out = chain ? scr : nullptr;
   double T[L + 1], A[L + 1];
 #pragma unroll
   for (int i = 0; i <= L; ++i) T[i] = A[i] = 0.0;
-  if (rr > 0) hier_range<L>(xs, g, 0, rr, M0 + 1, s_inA, T, A, out);
-  hier_range<L>(xs, g, rr, g, M0, s_inB, T, A, out);
+  int ra = 0;
+  for (; ra + 32 * J <= g; ra += 32 * J) hier_tile<L, J, false>(xs, g, ra, M0, rr, T, A, out);
+  if constexpr (J > 2)
+    for (; ra + 64 <= g; ra += 64) hier_tile<L, 2, false>(xs, g, ra, M0, rr, T, A, out);
+  for (; ra < g; ra += 32) hier_tile<L, 1, true>(xs, g, ra, M0, rr, T, A, out);
 #pragma unroll
   for (int i = 0; i <= L; ++i) {
     const int M = M0 >> i;
