@@ -50,7 +50,8 @@ struct SmemPlan {
   __host__ __device__ size_t off_red() const { return off_vwin() + union_bytes(); }
   __host__ __device__ size_t off_norms() const { return off_red() + 2 * kWarps * 8; }
   __host__ __device__ size_t off_fval() const { return off_norms() + (size_t)((num + 1) & ~1) * 8; }
-  __host__ __device__ size_t off_bar() const { return off_fval() + (size_t)kMaxFactors * 8; }
+  __host__ __device__ size_t off_facs() const { return off_fval() + (size_t)kMaxFactors * 8; }
+  __host__ __device__ size_t off_bar() const { return off_facs() + (size_t)kMaxFactors * 4; }
   __host__ __device__ size_t off_sweep() const { return off_bar() + 16; }
   __host__ __device__ size_t off_periods() const { return off_sweep() + ((sizeof(SweepShared) + 15) & ~15); }
   __host__ __device__ size_t off_slot() const { return off_periods() + (size_t)num * 4; }
@@ -76,6 +77,7 @@ struct Smem {
   double* red;
   double* norms;
   double* fval;
+  int* facs;
   double* hier;
   uint64_t* bar;
   SweepShared* sweep;
@@ -90,6 +92,7 @@ struct Smem {
     red = reinterpret_cast<double*>(base + pl.off_red());
     norms = reinterpret_cast<double*>(base + pl.off_norms());
     fval = reinterpret_cast<double*>(base + pl.off_fval());
+    facs = reinterpret_cast<int*>(base + pl.off_facs());
     hier = pl.hier_len ? reinterpret_cast<double*>(base + pl.off_hier()) : nullptr;
     bar = reinterpret_cast<uint64_t*>(base + pl.off_bar());
     sweep = reinterpret_cast<SweepShared*>(base + pl.off_sweep());
@@ -209,33 +212,41 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
 // Ranking only (multiplicity sums instead of N sequential adds).
 __device__ __forceinline__ double warp_slot_factor_norm(const double* slot, int P, int f, int N,
                                                         bool trunc, bool orth, const Tables& tb, double* scr,
-                                                        double sqrtN) {
+                                                        double sqrtN, double* wscr) {
+  // slot: the P-periodic basis (shared memory); wscr: 32 doubles of per-warp shared scratch
   const int lane = threadIdx.x & 31;
   const int t = P / f;
   const int Mf = N / f, r0f = N - Mf * f;
+  // the mean of residue r divides by K_r in {Mf, Mf + 1}: two reciprocals instead of a division per residue
+  const double rcp_lo = 1.0 / (double)Mf, rcp_hi = 1.0 / (double)(Mf + 1);
   double e = 0.0;
   if (f < 32) {
-    // few residues, long sums: the lanes split the t terms of one residue and reduce (fixed tree order)
-    for (int r = 0; r < f; ++r) {
-      const int K = trunc ? Mf : (Mf + (r < r0f ? 1 : 0));
-      const int base = K / t, rem = K - base * t;
-      double s = 0.0;
-      for (int j = lane; j < t; j += 32) s = fma((double)(base + (j < rem ? 1 : 0)), slot[r + j * f], s);
-      s = warp_sum(s);
-      const double mean = s / (double)K;
-      if (orth) {
-        if (lane == 0) scr[r] = mean;
-      } else if (lane == 0) {
-        e = fma((double)(Mf + (r < r0f ? 1 : 0)) * mean, mean, e);
-      }
+    // few residues, long sums: lane = (group, residue); the groups split the t terms of a residue and meet in
+    // the scratch.  (One reduction per divisor: dependent shuffles queue behind the co-resident CTA's sweep.)
+    const int g = 32 / f;
+    const int r = lane % f, grp = lane / f;
+    const int K = trunc ? Mf : (Mf + (r < r0f ? 1 : 0));
+    const int base = K / t, rem = K - base * t;
+    double s = 0.0;
+    if (grp < g)
+      for (int j = grp; j < t; j += g) s = fma((double)(base + (j < rem ? 1 : 0)), slot[r + j * f], s);
+    wscr[lane] = s;
+    __syncwarp();
+    if (lane < f) {
+      double tot = wscr[lane];
+      for (int k = 1; k < g; ++k) tot += wscr[lane + k * f];
+      const double mean = tot * (K == Mf ? rcp_lo : rcp_hi);
+      if (orth) scr[lane] = mean;
+      else e = (double)(Mf + (lane < r0f ? 1 : 0)) * mean * mean;
     }
+    __syncwarp();
   } else {
     for (int r = lane; r < f; r += 32) {
       const int K = trunc ? Mf : (Mf + (r < r0f ? 1 : 0));
       const int base = K / t, rem = K - base * t;
       double s = 0.0;
       for (int j = 0; j < t; ++j) s = fma((double)(base + (j < rem ? 1 : 0)), slot[r + j * f], s);
-      const double mean = s / (double)K;
+      const double mean = s * (K == Mf ? rcp_lo : rcp_hi);
       if (orth) scr[r] = mean;
       else e = fma((double)(Mf + (r < r0f ? 1 : 0)) * mean, mean, e);
     }
@@ -319,7 +330,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     __syncthreads();
 
     // ---------------- step 1 (Periods.py:494-537)
-    long long t_sweep = 0, t_proj = 0, t_upd = 0, t_step2 = 0, t_mark = clock64();
+    long long t_sweep = 0, t_proj = 0, t_upd = 0, t_step2 = 0, t_fac = 0, t_swap = 0, t_copy = 0, t_dec = 0, t_blk = 0, t_mark = clock64();
     int sweeps = 0;
     const int guard = 12 * (pmax - pmin + 2) + 12 * num;
     while (true) {
@@ -337,9 +348,17 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
                                sm.vwin, sm.utmp);
       { const long long t = clock64(); t_proj += t - t_mark; t_mark = t; }
       if (threadIdx.x == 0) {
+        // (independent shared-memory loads issued as a batch: a lone thread's dependent loads queue behind
+        // the other CTA's sweep traffic, ~200 cycles each)
         int found = -1;
-        for (int i = 0; i < num; ++i)
-          if (sm.periods[i] == top.p) found = i;
+        for (int i0 = 0; i0 < num; i0 += 16) {
+          int pk[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) pk[k] = (i0 + k < num) ? sm.periods[i0 + k] : -1;
+#pragma unroll
+          for (int k = 0; k < 16; ++k)
+            if (pk[k] == top.p) found = i0 + k;
+        }
         if (found >= 0 && misc[1] < 10) {          // strengthen an existing slot (:518-524)
           sm.norms[found] += top.val;
           misc[1] += 1;
@@ -376,6 +395,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     }
 
     // ---------------- step 2 (Periods.py:540-598), one pass
+    int changes_total = 0;
     if (misc[4] == PP_STATUS_OK) {
       const double stale_div = sqrt((double)pmax);  // gamma norms divide by sqrt(max_length) (:559,:572)
       int i = 0;
@@ -389,34 +409,76 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
           __syncthreads();
           break;
         }
-        __threadfence_block();
+        // the residual is dead after step 1: stage the slot basis (one period) and its divisor list on chip
+        double* sl_s = sm.xs;
+        const long long t_c0 = clock64();
+        for (int r = threadIdx.x; r < P; r += kThreads) sl_s[r] = sl[r];
+        for (int fi = threadIdx.x; fi < nf; fi += kThreads) sm.facs[fi] = tb.fac[f0 + fi];
+        __syncthreads();
+        const long long t_f0 = clock64();
+        t_copy += t_f0 - t_c0;
+        // every warp ranks its own divisors (ascending fi, strict '>' keeps the first maximum, Periods.py:561-565)
+        double w_top = 0.0;
+        int w_fi = -1;
         for (int fi = wid; fi < nf; fi += kWarps) {
-          const int f = tb.fac[f0 + fi];
-          double v = warp_slot_factor_norm(sl, P, f, N, trunc, orth, tb, my_scr ? my_scr + (size_t)wid * 2 * pl.pv : nullptr,
-                                           sqrtN);
+          const int f = sm.facs[fi];
+          double v = warp_slot_factor_norm(sl_s, P, f, N, trunc, orth, tb, my_scr ? my_scr + (size_t)wid * 2 * pl.pv : nullptr,
+                                           sqrtN, sm.vwin + wid * 32);
           if (gamma) v = v / stale_div;
-          if (lane == 0) sm.fval[fi] = v;
+          if (v > w_top) {
+            w_top = v;
+            w_fi = fi;
+          }
+          if (fi == nf - 1 && lane == 0) sm.fval[0] = v;  // norm of the LAST factor's projection (:570-572)
+        }
+        if (lane == 0) {
+          sm.sweep->wkey[wid] = w_top;
+          sm.sweep->wp[wid] = w_fi;
         }
         __syncthreads();
+        t_fac += clock64() - t_f0;
         if (threadIdx.x == 0) {
+          const long long t_b0 = clock64();
           double top = 0.0;
-          int top_f = 0;
-          for (int fi = 0; fi < nf; ++fi) {
-            if (sm.fval[fi] > top) {
-              top = sm.fval[fi];
-              top_f = tb.fac[f0 + fi];
+          int top_fi = -1;
+          {
+            double wk[kWarps];
+            int wf[kWarps];
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+              wk[w] = sm.sweep->wkey[w];
+              wf[w] = sm.sweep->wp[w];
             }
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w)
+              if (wf[w] >= 0 && (wk[w] > top || (wk[w] == top && top_fi >= 0 && wf[w] < top_fi))) {
+                top = wk[w];
+                top_fi = wf[w];
+              }
           }
+          const int top_f = top_fi >= 0 ? sm.facs[top_fi] : 0;
           int decision = 0;
           if (top_f != 0) {
             bool present = false;
-            for (int k = 0; k < num; ++k) present |= (sm.periods[k] == top_f);
+            double floor_n = sm.norms[0];
+            const double n_weak = sm.fval[0], n_last = sm.norms[num - 1], n_i = sm.norms[i];
+            for (int k0 = 0; k0 < num; k0 += 16) {  // batched loads, see step 1
+              int pk[16];
+              double nk[16];
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                pk[k] = (k0 + k < num) ? sm.periods[k0 + k] : -1;
+                nk[k] = (k0 + k < num) ? sm.norms[k0 + k] : floor_n;
+              }
+#pragma unroll
+              for (int k = 0; k < 16; ++k) {
+                present |= (pk[k] == top_f);
+                if (k0 + k < num) floor_n = fmin(floor_n, nk[k]);
+              }
+            }
             if (!present) {
               const double n_strong = top;
-              const double n_weak = sm.fval[nf - 1];  // norm of the LAST factor's projection (:570-572)
-              double floor_n = sm.norms[0];
-              for (int k = 1; k < num; ++k) floor_n = fmin(floor_n, sm.norms[k]);
-              if ((n_weak + n_strong) > (sm.norms[num - 1] + sm.norms[i]) && n_weak > floor_n && n_strong > floor_n) {
+              if ((n_weak + n_strong) > (n_last + n_i) && n_weak > floor_n && n_strong > floor_n) {
                 decision = 1;
                 // slot i keeps its period with the weakened basis; the strong factor is inserted before it
                 const int freed = sm.slot[num - 1];
@@ -436,13 +498,16 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
           }
           misc[5] = decision;
           misc[6] = top_f;
+          t_blk += clock64() - t_b0;
         }
         __syncthreads();
+        t_dec += clock64() - t_f0;
         if (misc[5]) {
+          const long long t_s0 = clock64();
           const int f = misc[6];
           const int clen = orth ? tb.chain_off[f + 1] - tb.chain_off[f] : 0;
           // exact xQ = project(bases[i], f) from the (still unmodified) old slot storage
-          cta_project_exact<true>(sl, P, N, f, trunc, orth ? tb.chain_q + tb.chain_off[f] : nullptr, clen, sm.vwin,
+          cta_project_exact<true>(sl_s, P, N, f, trunc, orth ? tb.chain_q + tb.chain_off[f] : nullptr, clen, sm.vwin,
                                   sm.utmp);
           double* old_sl = const_cast<double*>(sl);
           double* new_sl = my_slots + (size_t)misc[3] * pl.pv;
@@ -452,7 +517,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
             int rq = threadIdx.x % f;
             const int step = kThreads % f;
             for (int r = threadIdx.x; r < P; r += kThreads) {
-              old_sl[r] = old_sl[r] - sm.vwin[rq];
+              old_sl[r] = sl_s[r] - sm.vwin[rq];
               rq += step;
               if (rq >= f) rq -= f;
             }
@@ -460,7 +525,9 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
           __syncthreads();  // old_sl may alias new_sl when the old slot was dropped
           for (int r = threadIdx.x; r < f; r += kThreads) new_sl[r] = sm.vwin[r];
           ++changes;
+          ++changes_total;
           __syncthreads();
+          t_swap += clock64() - t_s0;
         } else {
           ++i;
         }
@@ -476,6 +543,9 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       atomicAdd(prof + 2, (unsigned long long)t_upd);
       atomicAdd(prof + 3, (unsigned long long)t_step2);
       atomicAdd(prof + 4, 1ull);
+      atomicAdd(prof + 5, (unsigned long long)t_fac);
+      atomicAdd(prof + 6, (unsigned long long)t_dec);
+      atomicAdd(prof + 7, (unsigned long long)t_blk);
     }
     const int status = misc[4];
     for (int i = threadIdx.x; i < num; i += kThreads) {

@@ -112,6 +112,69 @@ __device__ __forceinline__ void consider(const RankCtx& rc, double key, int p, B
   }
 }
 
+// Per-lane variant: every lane ranks its own candidate (p == 0: none); `writer` lanes record the metric.
+__device__ __forceinline__ void consider_lane(const RankCtx& rc, double key, int p, bool writer, Best& best) {
+  if (p == 0) return;
+  const int metric = rc.metric;
+  if (rc.metric_out != nullptr && writer) rc.metric_out[p] = key_to_value(metric, key, p, rc.sqrtN);
+  const uint32_t* skip = rc.skip;
+  if (skip != nullptr && ((skip[p >> 5] >> (p & 31)) & 1u)) return;
+  if (better(metric, key, p, best)) {
+    best.key = key;
+    best.p = p;
+  }
+}
+
+// Warp totals of K per-lane values with a transposed butterfly: K/2 + ... exchanges instead of 5 K.
+// On return lane l holds the total of value l >> (5 - log2 K).  (Shuffles share the shared-memory data
+// pipe the fold is bound by, so they are worth saving.)
+template <int K>
+__device__ __forceinline__ double warp_sum_multi(const double (&v)[K]) {
+  static_assert(K == 1 || K == 2 || K == 4, "K must be 1, 2 or 4");
+  const int lane = threadIdx.x & 31;
+  if constexpr (K == 1) {
+    return warp_sum(v[0]);
+  } else if constexpr (K == 2) {
+    const bool hi = (lane & 16) != 0;
+    double keep = hi ? v[1] : v[0];
+    keep += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[1], 16);
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    return keep;
+  } else {
+    const bool hi = (lane & 16) != 0;
+    double k0 = hi ? v[2] : v[0], k1 = hi ? v[3] : v[1];
+    k0 += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 16);
+    k1 += __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 16);
+    const bool hi8 = (lane & 8) != 0;
+    double keep = hi8 ? k1 : k0;
+    keep += __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8);
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    return keep;
+  }
+}
+
+// Ranking state of one warp during a hierarchical sweep: per-lane best, plus the per-lane partial energy
+// of an odd top waiting for a partner so that two tops share one reduction.
+struct WarpRank {
+  Best best;
+  double pend;
+  int pend_p;  // warp-uniform; 0 = nothing pending
+};
+
+// all lanes end up with the warp's best candidate (total order: `better`)
+__device__ __forceinline__ Best warp_best(int metric, Best b) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    Best other;
+    other.key = __shfl_xor_sync(0xffffffffu, b.key, o);
+    other.p = __shfl_xor_sync(0xffffffffu, b.p, o);
+    if (other.p != 0 && better(metric, other.key, other.p, b)) b = other;
+  }
+  return b;
+}
+
 // 1 / m: table for the small row counts every large period has, a real division otherwise
 __device__ __forceinline__ double rcp_of(const double* rcp, int m) {
   return m < kRcpTab ? rcp[m] : 1.0 / (double)m;
@@ -373,11 +436,14 @@ __device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, 
   }
   bool tail[J];
 #pragma unroll
-  for (int j = 0; j < J; ++j) {
-    tail[j] = ra + lane + 32 * j < rr;
-    double t = 0.0;
-    if (tail[j]) t = ptr[32 * j];
-    acc[0][j] += t;
+  for (int j = 0; j < J; ++j) tail[j] = ra + lane + 32 * j < rr;
+  if (ra < rr) {  // warp-uniform: most tiles of a top lie entirely past the tail row
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      double t = 0.0;
+      if (tail[j]) t = ptr[32 * j];
+      acc[0][j] += t;
+    }
   }
   if (MASK) {
 #pragma unroll
@@ -407,7 +473,7 @@ struct hier_cols {
 
 // One top period q = g * 2^L and every candidate q / 2^k below it.  Non-trunc, non-orth, NORM / GAMMA.
 template <int L>
-__device__ __forceinline__ Best warp_hier_top_L(RankCtx rc, int g, int M0, int rr, double* scr, Best best) {
+__device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int rr, double* scr, WarpRank& wr) {
   // M0 = floor(N / g) complete base rows; base residues below rr = N - M0 g have one more (tail) row
   constexpr int J = hier_cols<L>::value;
   const int lane = threadIdx.x & 31;
@@ -423,12 +489,36 @@ __device__ __forceinline__ Best warp_hier_top_L(RankCtx rc, int g, int M0, int r
   if constexpr (J > 2)
     for (; ra + 64 <= g; ra += 64) hier_tile<L, 2, false>(xs, g, ra, M0, rr, T, A, out);
   for (; ra < g; ra += 32) hier_tile<L, 1, true>(xs, g, ra, M0, rr, T, A, out);
+  // per-lane partial energies of the L + 1 levels, reduced together
+  constexpr int KP = L == 0 ? 1 : (L == 1 ? 2 : 4);
+  double e[KP];
 #pragma unroll
-  for (int i = 0; i <= L; ++i) {
-    const int M = M0 >> i;
-    const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
-    consider(rc, warp_sum(fma(w_diff, A[i], w_lo * T[i])), g << i, best);
+  for (int i = 0; i < KP; ++i) {
+    if (i <= L) {
+      const int M = M0 >> i;
+      const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+      e[i] = fma(w_diff, A[i], w_lo * T[i]);
+    } else {
+      e[i] = 0.0;
+    }
   }
+  if constexpr (L == 0) {
+    if (wr.pend_p == 0) {  // wait for the next odd top
+      wr.pend = e[0];
+      wr.pend_p = g;
+    } else {
+      const double pair[2] = {wr.pend, e[0]};
+      const double key = warp_sum_multi<2>(pair);
+      consider_lane(rc, key, (lane & 16) ? g : wr.pend_p, (lane & 15) == 0, wr.best);
+      wr.pend_p = 0;
+    }
+  } else {
+    const double key = warp_sum_multi<KP>(e);
+    constexpr int shift = KP == 2 ? 4 : 3;
+    const int k = lane >> shift;
+    consider_lane(rc, key, k <= L ? (g << k) : 0, (lane & ((1 << shift) - 1)) == 0, wr.best);
+  }
+  Best& best = wr.best;
   if (chain) {
     __syncwarp();
     double* src = scr;
@@ -454,7 +544,6 @@ __device__ __forceinline__ Best warp_hier_top_L(RankCtx rc, int g, int M0, int r
     }
     __syncwarp();
   }
-  return best;
 }
 
 // Descriptor of one top q = g 2^L: x = g | L << 16, y = floor(N / g) | (N mod g) << 16.
@@ -486,13 +575,13 @@ static __global__ void tops_kernel(int N, int pmin, int pmax, uint2* __restrict_
   tops[rank] = make_uint2((unsigned)g | ((unsigned)L << 16), (unsigned)M0 | ((unsigned)rr << 16));
 }
 
-__device__ __forceinline__ Best warp_hier_top(const RankCtx& rc, uint2 e, double* scr, Best best) {
+__device__ __forceinline__ void warp_hier_top(const RankCtx& rc, uint2 e, double* scr, WarpRank& wr) {
   const int g = e.x & 0xffff, L = e.x >> 16, M0 = e.y & 0xffff, rr = e.y >> 16;
   switch (L) {
-    case 0: return warp_hier_top_L<0>(rc, g, M0, rr, scr, best);
-    case 1: return warp_hier_top_L<1>(rc, g, M0, rr, scr, best);
-    case 2: return warp_hier_top_L<2>(rc, g, M0, rr, scr, best);
-    default: return warp_hier_top_L<3>(rc, g, M0, rr, scr, best);
+    case 0: warp_hier_top_L<0>(rc, g, M0, rr, scr, wr); break;
+    case 1: warp_hier_top_L<1>(rc, g, M0, rr, scr, wr); break;
+    case 2: warp_hier_top_L<2>(rc, g, M0, rr, scr, wr); break;
+    default: warp_hier_top_L<3>(rc, g, M0, rr, scr, wr); break;
   }
 }
 
@@ -541,13 +630,16 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
     const uint2* __restrict__ tops = sp->tops;
     const int total = sp->ntops;
     double* scr = sp->hier_scr + (size_t)wid * sp->hier_len;
+    WarpRank wr{best, 0.0, 0};
     while (true) {
       int idx = 0;
       if (lane == 0) idx = atomicAdd(&sh->counter, 1);
       idx = __shfl_sync(0xffffffffu, idx, 0);
       if (idx >= total) break;
-      best = warp_hier_top(rc, __ldg(tops + idx), scr, best);
+      warp_hier_top(rc, __ldg(tops + idx), scr, wr);
     }
+    if (wr.pend_p != 0) consider(rc, warp_sum(wr.pend), wr.pend_p, wr.best);  // odd top left without a partner
+    best = warp_best(metric, wr.best);
   } else {
     const int ncand = pmax - pmin + 1;
     while (true) {

@@ -210,6 +210,14 @@ int main(int argc, char** argv) {
   int N = 4096, pmax = 1024, iters = 20, sms = 0;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
   cudaMalloc(&g_en, 2048 * 8); cudaMemset(g_en, 0, 2048 * 8);
+  if (argc > 3) {
+    const int l = atoi(argv[2]), j = atoi(argv[3]);
+    if (l == 0 && j == 8) run<0, 8>(N, pmax, iters, sms);
+    if (l == 1 && j == 8) run<1, 8>(N, pmax, iters, sms);
+    if (l == 2 && j == 4) run<2, 4>(N, pmax, iters, sms);
+    if (l == 3 && j == 2) run<3, 2>(N, pmax, iters, sms);
+    return 0;
+  }
   run<0, 4>(N, pmax, iters, sms);
   run<0, 8>(N, pmax, iters, sms);
   run<0, 16>(N, pmax, iters, sms);

@@ -26,5 +26,5 @@ for mode in modes:
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / 5
         pr = prof.cpu().numpy().astype(float); prof.zero_()
-        print("   cycles/window: sweep %.0f  project %.0f  update %.0f  step2+out %.0f" % tuple(pr[:4] / pr[4]))
+        print("   cycles/window: sweep %.0f  project %.0f  update %.0f  step2+out %.0f (factor norms %.0f, norms+decision %.0f, thread-0 block %.0f)" % (tuple(pr[:4] / pr[4]) + tuple(pr[5:8] / pr[4])))
         print(f"{mode:7s} {name:13s} B={B} {ms:9.2f} ms  {B / ms * 1e3:10.0f} win/s  sweeps/win={float(r.sweeps.float().mean()):.3f}", flush=True)
