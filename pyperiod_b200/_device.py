@@ -2,6 +2,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import warnings
 from dataclasses import dataclass
 
 import numpy as np
@@ -32,6 +33,18 @@ class Windows:
     ldx: int
     was_1d: bool
     from_host: bool        # results go back to numpy
+    # pipelined upload (stage_windows(..., pipeline=True)): generator factory of (first window, end window, event)
+    plan: object = None
+
+    def launch_plan(self):
+        """Yields (b0, b1, event-or-None), one entry per kernel launch: windows [b0, b1) are complete on the
+        device once `event` has fired.  With a pipelined upload the copy of the NEXT piece is issued just
+        before a chunk is yielded, so it overlaps the kernel the caller launches for this chunk (also for
+        pageable host memory, whose copies block the host thread)."""
+        if self.plan is None:
+            yield (0, self.b, None)
+        else:
+            yield from self.plan()
 
     @property
     def ptr(self) -> int:
@@ -42,12 +55,73 @@ class Windows:
         return self.tensor.device
 
 
-def stage_windows(data, device=None) -> Windows:
+PIPELINE_MIN_WINDOWS = 16384   # below this a single upload + launch is cheaper than the extra launches
+PIPELINE_PIECES = 8
+_copy_streams: dict = {}
+
+
+def _pipelined_upload(host_flat: torch.Tensor, b: int, n: int, hop: int, dev: torch.device) -> Windows:
+    """Upload a host sample stream in pieces on a side stream; window chunk k may be launched as soon as
+    its piece has landed, so the PCIe copy of piece k+1 overlaps the kernel on piece k."""
+    span = host_flat.numel()
+    dflat = torch.empty((span,), dtype=torch.float64, device=dev)
+    cur = torch.cuda.current_stream(dev)
+    cs = _copy_streams.get(str(dev))
+    if cs is None:
+        cs = _copy_streams[str(dev)] = torch.cuda.Stream(dev)
+    cs.wait_stream(cur)              # the allocation point of dflat is on the current stream
+    dflat.record_stream(cs)
+    per = -(-b // PIPELINE_PIECES)
+    bounds = [(b0, min(b, b0 + per)) for b0 in range(0, b, per)]
+
+    def copy_piece(k):
+        b0, b1 = bounds[k]
+        s0 = 0 if k == 0 else (bounds[k - 1][1] - 1) * hop + n
+        s1 = (b1 - 1) * hop + n          # one past the last sample window b1-1 reads
+        with torch.cuda.stream(cs):
+            dflat[s0:s1].copy_(host_flat[s0:s1], non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        return ev
+
+    def plan():
+        ev = copy_piece(0)
+        for k, (b0, b1) in enumerate(bounds):
+            yield (b0, b1, ev)           # the caller launches the kernel for this chunk ...
+            if k + 1 < len(bounds):
+                ev = copy_piece(k + 1)   # ... and the next copy is issued behind it
+
+    view = torch.as_strided(dflat, (b, n), (hop, 1))
+    return Windows(view, b, n, hop, False, True, plan)
+
+
+def stage_windows(data, device=None, pipeline: bool = False) -> Windows:
     """Accept a 1-D signal or a (B, N) batch (numpy / torch, host / device) and put it on the GPU.
 
     Overlapping row-strided views (stride0 < N, e.g. hop-512 frames of one stream) are uploaded
-    once as the underlying stream and read in place by the kernels (ldx = hop).
+    once as the underlying stream and read in place by the kernels (ldx = hop).  With
+    `pipeline=True` a large host batch is uploaded in pieces on a side stream and the returned
+    Windows carries a launch plan (see Windows.launch_plan).
     """
+    if pipeline:
+        flat = None
+        if isinstance(data, torch.Tensor) and data.device.type != "cuda" and data.dtype == torch.float64 \
+                and data.dim() == 2 and data.shape[0] >= PIPELINE_MIN_WINDOWS and data.stride(1) == 1 \
+                and 0 < data.stride(0) <= data.shape[1]:
+            b, n = data.shape
+            hop = data.stride(0)
+            flat = torch.as_strided(data, ((b - 1) * hop + n,), (1,))
+        elif isinstance(data, np.ndarray) and data.dtype == np.float64 and data.ndim == 2 \
+                and data.shape[0] >= PIPELINE_MIN_WINDOWS and data.strides[1] == 8 and data.strides[0] % 8 == 0 \
+                and 0 < data.strides[0] <= data.shape[1] * 8:
+            b, n = data.shape
+            hop = data.strides[0] // 8
+            flat_np = np.lib.stride_tricks.as_strided(data, shape=((b - 1) * hop + n,), strides=(8,), writeable=False)
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")   # read-only view: we only read from it
+                flat = torch.from_numpy(flat_np)
+        if flat is not None:
+            return _pipelined_upload(flat, b, n, hop, require_cuda(device))
     if isinstance(data, torch.Tensor):
         t = data
         if t.dtype != torch.float64:

@@ -268,7 +268,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
              int trunc_i, int orth_i, int hier, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
              double* __restrict__ bases_out, int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
              double* __restrict__ ws_slots, double* __restrict__ ws_scr, const uint2* __restrict__ tops, int ntops,
-             unsigned long long* __restrict__ prof) {
+             int* __restrict__ next_window, unsigned long long* __restrict__ prof) {
   unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0);
   Smem sm(smem_raw, pl);
@@ -285,7 +285,12 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
   zero_pad(sm.xs, N, pl.xs_len);
   sweep_shared_init(sm.sweep);
 
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  // windows are handed out dynamically (global counter, zeroed per launch): per-window cost varies with the
+  // number of sweeps and step-2 work, and a static stride leaves a tail of idle CTAs at the end of a launch
+  int b = blockIdx.x;
+  while (b < B) {
+    int b_next = 0;
+    if (threadIdx.x == 0) b_next = gridDim.x + atomicAdd(next_window, 1);  // consumed at the end of this window
     loader.load(sm.xs, x + (size_t)b * ldx, N);
     const double e_data = cta_sum_sq(sm.xs, N, sm.red);
     const double data_norm = sqrt(e_data) / sqrtN;  // periodic_norm(data), Periods.py:600
@@ -568,7 +573,9 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
         }
       }
     }
+    if (threadIdx.x == 0) misc[7] = b_next;
     __syncthreads();
+    b = misc[7];
   }
 }
 
@@ -808,7 +815,7 @@ size_t pp_workspace_bytes(int32_t algo, int32_t N, int32_t pmax, int32_t num, in
   SmemPlan pl;
   plan_for(algo, N, pmax, num, pl);
   const size_t grid = (size_t)f.sm_count * kCtasPerSm;  // upper bound on the persistent grid
-  size_t bytes = 1024 + 256 + (size_t)(pmax + 2) * sizeof(uint2);
+  size_t bytes = 1024 + 1024 + (size_t)(pmax + 2) * sizeof(uint2);
   if (algo == PP_ALGO_MBEST) bytes += grid * (size_t)num * pl.pv * 8;
   if (orth && algo != PP_ALGO_BCORR) bytes += grid * kWarps * 2 * (size_t)pl.pv * 8;
   return bytes;
@@ -918,6 +925,9 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   double* slots = carve(workspace, workspace_bytes, off, (size_t)grid * num * pl.pv * 8);
   double* scr = orth ? carve(workspace, workspace_bytes, off, (size_t)grid * kWarps * 2 * pl.pv * 8) : nullptr;
   if (!slots || (orth && !scr)) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
+  int* next_window = reinterpret_cast<int*>(carve(workspace, workspace_bytes, off, 256));
+  if (!next_window) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
+  if (int rc = check_cuda(cudaMemsetAsync(next_window, 0, sizeof(int), (cudaStream_t)stream), "cudaMemsetAsync")) return rc;
   uint2* tops = nullptr;
   const int ntops = hier ? hier_top_count(pmin, pmax) : 0;
   if (ntops > 0) {
@@ -928,7 +938,7 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   Tables tb{chain_off, chain_q, fac_off, fac};
   mbest_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,
                                                                      hier, tb, periods, powers, bases, sweeps, status,
-                                                                     slots, scr, tops, ntops, g_prof);
+                                                                     slots, scr, tops, ntops, next_window, g_prof);
   return check_cuda(cudaGetLastError(), "mbest_kernel launch");
 }
 

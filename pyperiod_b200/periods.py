@@ -191,7 +191,9 @@ class Periods:
         if self._orthogonalize:
             warn("`Orthogonalize = True` has no effect in M-best.")  # Periods.py:482-483 (HEAD still applies it)
         lib = _lib.load()
-        w = stage_windows(data, self._device)
+        # a large host batch is uploaded in pieces on a side stream; each piece gets its own launch so the
+        # PCIe copy overlaps the kernels (the results are compact: one read-back at the end)
+        w = stage_windows(data, self._device, pipeline=True)
         if return_bases is None:
             return_bases = w.was_1d
         pmax = math.floor(w.n / 3) if max_length is None else int(max_length)
@@ -205,10 +207,15 @@ class Periods:
         bases = torch.empty((w.b, num, w.n), dtype=torch.float64, device=w.device) if return_bases else None
         sweeps = torch.empty((w.b,), dtype=torch.int32, device=w.device)
         status = torch.empty((w.b,), dtype=torch.int32, device=w.device)
-        _lib.check(lib.pp_mbest(ptr(w.tensor), w.ldx, w.b, w.n, num, min_length, pmax, int(gamma),
-                                int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq), ptr(fo), ptr(fc),
-                                tb.pmax, ptr(periods), ptr(powers), ptr(bases), ptr(sweeps), ptr(status), ptr(ws),
-                                ws.numel(), stream_ptr(w.device)), "pp_mbest")
+        cur = torch.cuda.current_stream(w.device)
+        for b0, b1, ready in w.launch_plan():
+            if ready is not None:
+                cur.wait_event(ready)
+            _lib.check(lib.pp_mbest(C.c_void_p(w.ptr + b0 * w.ldx * 8), w.ldx, b1 - b0, w.n, num, min_length, pmax,
+                                    int(gamma), int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq), ptr(fo),
+                                    ptr(fc), tb.pmax, ptr(periods[b0:b1]), ptr(powers[b0:b1]),
+                                    ptr(None if bases is None else bases[b0:b1]), ptr(sweeps[b0:b1]), ptr(status[b0:b1]),
+                                    ptr(ws), ws.numel(), stream_ptr(w.device)), "pp_mbest")
         res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases), _export(w, status),
                           sweeps=_export(w, sweeps))
         if w.was_1d:

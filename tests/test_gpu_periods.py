@@ -379,3 +379,26 @@ def test_differential_many_windows(P, trunc):
         per, pw, _ = op.best_correlation(xb[b], 4, 300, 0.01, trunc)
         assert np.array_equal(bc.periods[b], per), ("bcorr", b)
         np.testing.assert_allclose(bc.powers[b], pw, rtol=RTOL, atol=1e-15)
+
+
+def test_mbest_pipelined_host_upload_matches_device_resident():
+    """Large host batches are uploaded in pieces on a side stream with one launch per piece
+    (pyperiod_b200/_device.py); results must equal the single-launch device-resident call."""
+    import torch
+    from pyperiod_b200 import Periods, _device
+    B, N, hop = _device.PIPELINE_MIN_WINDOWS + 1000, 256, 64
+    rng = np.random.default_rng(5)
+    stream = rng.standard_normal((B - 1) * hop + N)
+    P = Periods()
+    dev = torch.from_numpy(stream).cuda()
+    ref = P.m_best(torch.as_strided(dev, (B, N), (hop, 1)), num=3, max_length=64)
+    pinned = torch.from_numpy(stream).pin_memory()
+    got = P.m_best(torch.as_strided(pinned, (B, N), (hop, 1)), num=3, max_length=64)
+    strided = np.lib.stride_tricks.as_strided(stream, shape=(B, N), strides=(hop * 8, 8), writeable=False)
+    got_np = P.m_best(strided, num=3, max_length=64)
+    dense = P.m_best(np.ascontiguousarray(strided), num=3, max_length=64)
+    for g in (got, got_np, dense):
+        assert isinstance(g.periods, np.ndarray)
+        assert np.array_equal(g.periods, ref.periods.cpu().numpy().view(np.uint32))
+        assert np.array_equal(g.powers, ref.powers.cpu().numpy())
+        assert np.array_equal(g.status, ref.status.cpu().numpy())
