@@ -90,7 +90,7 @@ def check(rc: int, what: str):
         raise PPError(f"{what} failed ({rc}): {msg}")
 
 
-FOLD_HIERARCHICAL, FOLD_DIRECT = 0, 1
+FOLD_HIERARCHICAL, FOLD_DIRECT, FOLD_HIERARCHICAL_NO_RIDERS = 0, 1, 2
 
 
 def set_fold_mode(mode: int):

@@ -759,11 +759,11 @@ static int g_fold_mode = 0;
 static unsigned long long* g_prof = nullptr;
 
 static bool hier_applies(int metric, int trunc, int orth) {
-  return g_fold_mode == 0 && !trunc && !orth && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
+  return g_fold_mode != PP_FOLD_DIRECT && !trunc && !orth && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
 }
 
 static int plan_for(int algo, int N, int pmax, int num, SmemPlan& pl) {
-  pl = make_plan(N, pmax, algo == PP_ALGO_MBEST ? num : 0, true, g_fold_mode == 0 && (algo == PP_ALGO_MBEST || algo == PP_ALGO_SWEEP));
+  pl = make_plan(N, pmax, algo == PP_ALGO_MBEST ? num : 0, true, g_fold_mode != PP_FOLD_DIRECT && (algo == PP_ALGO_MBEST || algo == PP_ALGO_SWEEP));
   return 0;
 }
 
@@ -776,7 +776,8 @@ extern "C" {
 int pp_abi_version(void) { return PP_ABI_VERSION; }
 
 int pp_set_fold_mode(int32_t mode) {
-  if (mode != PP_FOLD_HIERARCHICAL && mode != PP_FOLD_DIRECT) return fail(-1, "unknown fold mode%s");
+  if (mode != PP_FOLD_HIERARCHICAL && mode != PP_FOLD_DIRECT && mode != PP_FOLD_HIERARCHICAL_NO_RIDERS)
+    return fail(-1, "unknown fold mode%s");
   g_fold_mode = mode;
   return 0;
 }
@@ -890,11 +891,11 @@ int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, i
     if (!scr) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
   }
   uint2* tops = nullptr;
-  const int ntops = hier ? hier_top_count(pmin, pmax) : 0;
+  int ntops = hier ? hier_top_count(pmin, pmax) : 0;
   if (ntops > 0) {
     tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)ntops * sizeof(uint2)));
     if (!tops) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
-    tops_kernel<<<(ntops + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, pmin, pmax, tops);
+    ntops = build_hier_jobs(N, pmin, pmax, tops, (cudaStream_t)stream);
   }
   Tables tb{chain_off, chain_q, nullptr, nullptr};
   sweep_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, pmin, pmax, metric, trunc, orth, hier,
@@ -929,11 +930,11 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   if (!next_window) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
   if (int rc = check_cuda(cudaMemsetAsync(next_window, 0, sizeof(int), (cudaStream_t)stream), "cudaMemsetAsync")) return rc;
   uint2* tops = nullptr;
-  const int ntops = hier ? hier_top_count(pmin, pmax) : 0;
+  int ntops = hier ? hier_top_count(pmin, pmax) : 0;
   if (ntops > 0) {
     tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)ntops * sizeof(uint2)));
     if (!tops) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
-    tops_kernel<<<(ntops + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, pmin, pmax, tops);
+    ntops = build_hier_jobs(N, pmin, pmax, tops, (cudaStream_t)stream);
   }
   Tables tb{chain_off, chain_q, fac_off, fac};
   mbest_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,

@@ -697,7 +697,7 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   if (B == 0) return 0;
   DeviceFacts f;
   if (int rc = device_facts(f)) return rc;
-  const int hier = (pp_get_fold_mode() == PP_FOLD_HIERARCHICAL && !trunc) ? 1 : 0;
+  const int hier = (pp_get_fold_mode() != PP_FOLD_DIRECT && !trunc) ? 1 : 0;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0);
   if (int rc = prep_kernel(qo_find_kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B, 2);
@@ -707,11 +707,11 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   double* nr = carve(workspace, workspace_bytes, off, (size_t)grid * num * 8);
   if (!G || !Pt || !nr) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
   uint2* tops = nullptr;
-  const int ntops = hier ? hier_top_count(pmin, pmax) : 0;
+  int ntops = hier ? hier_top_count(pmin, pmax) : 0;
   if (ntops > 0) {
     tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)ntops * sizeof(uint2)));
     if (!tops) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
-    tops_kernel<<<(ntops + 127) / 128, 128, 0, (cudaStream_t)stream>>>(N, pmin, pmax, tops);
+    ntops = build_hier_jobs(N, pmin, pmax, tops, (cudaStream_t)stream);
   }
   QoOut o{periods, norms, n_periods, dict_q, dict_keep, n_dict, n_weights, weights, res, status};
   qo_find_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, thresh, pmin, pmax, trunc,

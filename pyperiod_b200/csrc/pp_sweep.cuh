@@ -96,9 +96,10 @@ struct RankCtx {
   int metric;
   int N;
   int pmin;
+  int pmax;
 };
 __device__ __forceinline__ RankCtx rank_ctx(const SweepParams* sp) {
-  return RankCtx{sp->nskip > 0 ? sp->skip : nullptr, sp->metric_out, sp->rcp, sp->sqrtN, sp->metric, sp->N, sp->pmin};
+  return RankCtx{sp->nskip > 0 ? sp->skip : nullptr, sp->metric_out, sp->rcp, sp->sqrtN, sp->metric, sp->N, sp->pmin, sp->pmax};
 }
 
 __device__ __forceinline__ void consider(const RankCtx& rc, double key, int p, Best& best) {
@@ -130,7 +131,7 @@ __device__ __forceinline__ void consider_lane(const RankCtx& rc, double key, int
 // pipe the fold is bound by, so they are worth saving.)
 template <int K>
 __device__ __forceinline__ double warp_sum_multi(const double (&v)[K]) {
-  static_assert(K == 1 || K == 2 || K == 4, "K must be 1, 2 or 4");
+  static_assert(K == 1 || K == 2 || K == 4 || K == 8, "K must be 1, 2, 4 or 8");
   const int lane = threadIdx.x & 31;
   if constexpr (K == 1) {
     return warp_sum(v[0]);
@@ -140,6 +141,24 @@ __device__ __forceinline__ double warp_sum_multi(const double (&v)[K]) {
     keep += __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[1], 16);
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
+    return keep;
+  } else if constexpr (K == 8) {
+    const bool hi = (lane & 16) != 0;
+    double k4[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      k4[i] = hi ? v[4 + i] : v[i];
+      k4[i] += __shfl_xor_sync(0xffffffffu, hi ? v[i] : v[4 + i], 16);
+    }
+    const bool hi8 = (lane & 8) != 0;
+    double k0 = hi8 ? k4[2] : k4[0], k1 = hi8 ? k4[3] : k4[1];
+    k0 += __shfl_xor_sync(0xffffffffu, hi8 ? k4[0] : k4[2], 8);
+    k1 += __shfl_xor_sync(0xffffffffu, hi8 ? k4[1] : k4[3], 8);
+    const bool hi4 = (lane & 4) != 0;
+    double keep = hi4 ? k1 : k0;
+    keep += __shfl_xor_sync(0xffffffffu, hi4 ? k0 : k1, 4);
+#pragma unroll
+    for (int o = 2; o > 0; o >>= 1) keep += __shfl_xor_sync(0xffffffffu, keep, o);
     return keep;
   } else {
     const bool hi = (lane & 16) != 0;
@@ -365,44 +384,72 @@ __host__ __device__ inline int hier_scratch_len(int pmax) { return ((((pmax >> 3
 // hold one more term on every residue.  A tile therefore covers the whole residue range [0, g) with
 // one code path: no split at rr, the tail row is a predicated load.
 //
-// compile-time recursion over the levels l = LV .. 0 (keeps every accumulator index static).
-// For level l the tile contributes q_s = sum_j acc[s][j]^2 of each of its 2^l sets to T[l], and to A[l]
-// (residues with one more term) for the warp-uniform top sets and, lane by lane, for set 0 under the tail.
-template <int L, int J, int LV>
-struct hier_levels {
-  static __device__ __forceinline__ void run(double (&acc)[1 << L][J], int M0, const bool (&tail)[J],
-                                             double (&T)[L + 1], double (&A)[L + 1]) {
+// Riders.  A job with base g and S accumulator sets yields the fold of every period g d, d | S.  With
+// S = 3 * 2^LH one pass over the window serves TWO tops: the host q = g 2^LH (g odd, LH in {1, 2}) with its
+// chain q/2 .. g, and the rider R = 3 q / 2 or 3 q / 4 (whichever lies in (pmax/2, pmax]) with its chain
+// down to 3 g.  About a fifth of the tops ride (the multiples of 3 whose host exists), i.e. a fifth fewer
+// passes over the window; the price is a longer level computation per tile.
+
+// energy terms of one level held in `sets` accumulator sets v[0 .. sets): T += sum of squares, A += the part
+// whose residues hold one more term (warp-uniform top sets, and set 0 under the tail row)
+template <int SETS, int DIM0, int J>
+__device__ __forceinline__ void level_energy(const double (&v)[DIM0][J], int extra, const bool (&tail)[J], double& T,
+                                             double& A) {
+#pragma unroll
+  for (int s = 0; s < SETS; ++s) {
+    const double q = sum_sq<J>(v[s]);
+    T += q;
+    if (s >= SETS - extra) A += q;  // warp-uniform
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+    if (tail[j]) A = fma(v[0][j], v[0][j], A);
+}
+
+// v[s] += v[s + SETS/2]: the sets of the level with half as many sets
+template <int SETS, int DIM0, int J>
+__device__ __forceinline__ void level_halve(double (&v)[DIM0][J]) {
+#pragma unroll
+  for (int s = 0; s < SETS / 2; ++s)
+#pragma unroll
+    for (int j = 0; j < J; ++j) v[s][j] += v[s + SETS / 2][j];
+}
+
+// levels 2^LV .. 1 of a power-of-two set array (compile-time recursion keeps every index static)
+template <int DIM0, int J, int LV, int NL>
+struct pow2_levels {
+  static __device__ __forceinline__ void run(double (&v)[DIM0][J], int M0, const bool (&tail)[J], double (&T)[NL],
+                                             double (&A)[NL]) {
     constexpr int sets = 1 << LV;
-    const int extra = M0 & (sets - 1);
-#pragma unroll
-    for (int s = 0; s < sets; ++s) {
-      const double q = sum_sq<J>(acc[s]);
-      T[LV] += q;
-      if (s >= sets - extra) A[LV] += q;  // warp-uniform
-    }
-#pragma unroll
-    for (int j = 0; j < J; ++j)
-      if (tail[j]) A[LV] = fma(acc[0][j], acc[0][j], A[LV]);
+    level_energy<sets, DIM0, J>(v, M0 & (sets - 1), tail, T[LV], A[LV]);
     if constexpr (LV > 0) {
-      constexpr int half = sets >> 1;
-#pragma unroll
-      for (int s = 0; s < half; ++s)
-#pragma unroll
-        for (int j = 0; j < J; ++j) acc[s][j] += acc[s + half][j];
-      hier_levels<L, J, LV - 1>::run(acc, M0, tail, T, A);
+      level_halve<sets, DIM0, J>(v);
+      pow2_levels<DIM0, J, LV - 1, NL>::run(v, M0, tail, T, A);
+    }
+  }
+};
+// levels 3 * 2^LV .. 3 of a rider chain
+template <int DIM0, int J, int LV, int NL>
+struct rider_levels {
+  static __device__ __forceinline__ void run(double (&v)[DIM0][J], int M0, const bool (&tail)[J], double (&T)[NL],
+                                             double (&A)[NL]) {
+    constexpr int sets = 3 << LV;
+    level_energy<sets, DIM0, J>(v, M0 % sets, tail, T[LV], A[LV]);
+    if constexpr (LV > 0) {
+      level_halve<sets, DIM0, J>(v);
+      rider_levels<DIM0, J, LV - 1, NL>::run(v, M0, tail, T, A);
     }
   }
 };
 
-// One register tile of a top q = g * 2^L: base residues ra + lane + 32 j (j < J), all M0 complete base
-// rows plus the tail row.  MASK: the tile may run past g (lanes beyond it are zeroed before the energies).
-template <int L, int J, bool MASK>
-__device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, int ra, int M0, int rr,
-                                          double (&T)[L + 1], double (&A)[L + 1], double* scr) {
-  constexpr int S = 1 << L;
+// Rows (stride g) of base residues ra + lane + 32 j accumulated into S sets by (row - M0) mod S, plus the
+// predicated tail row into set 0.  head = M0 mod S, groups = M0 / S (warp-uniform, computed once per job).
+// MASK: the tile may run past g (lanes beyond it are zeroed).
+template <int S, int J, bool MASK>
+__device__ __forceinline__ void hier_accumulate(const double* __restrict__ xs, int g, int ra, int M0, int rr, int head,
+                                                int groups, double (&acc)[S][J], bool (&tail)[J]) {
   const int lane = threadIdx.x & 31;
   const double* ptr = xs + ra + lane;
-  double acc[S][J];
   if constexpr (S == 1) {
 #pragma unroll
     for (int j = 0; j < J; ++j) acc[0][j] = ptr[32 * j];
@@ -417,16 +464,15 @@ __device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, 
     for (int s = 0; s < S; ++s)
 #pragma unroll
       for (int j = 0; j < J; ++j) acc[s][j] = 0.0;
-    const int head = M0 & (S - 1);  // rows before the first complete group of S
 #pragma unroll
-    for (int s = 1; s < S; ++s) {
+    for (int s = 1; s < S; ++s) {  // rows before the first complete group of S
       if (s >= S - head) {
         add_row<J>(acc[s], ptr);
         ptr += g;
       }
     }
 #pragma unroll 1
-    for (int i = M0 >> L; i > 0; --i) {
+    for (int i = groups; i > 0; --i) {
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         add_row<J>(acc[s], ptr);
@@ -434,7 +480,6 @@ __device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, 
       }
     }
   }
-  bool tail[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) tail[j] = ra + lane + 32 * j < rr;
   if (ra < rr) {  // warp-uniform: most tiles of a top lie entirely past the tail row
@@ -454,12 +499,45 @@ __device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, 
       }
     }
   }
-  hier_levels<L, J, L>::run(acc, M0, tail, T, A);
+}
+
+// One register tile of a plain top q = g * 2^L.
+template <int L, int J, bool MASK>
+__device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, int ra, int M0, int rr,
+                                          double (&T)[L + 1], double (&A)[L + 1], double* scr) {
+  constexpr int S = 1 << L;
+  const int lane = threadIdx.x & 31;
+  double acc[S][J];
+  bool tail[J];
+  hier_accumulate<S, J, MASK>(xs, g, ra, M0, rr, M0 & (S - 1), M0 >> L, acc, tail);
+  pow2_levels<S, J, L, L + 1>::run(acc, M0, tail, T, A);
   if (scr != nullptr) {
 #pragma unroll
     for (int j = 0; j < J; ++j)
       if (!MASK || ra + lane + 32 * j < g) scr[ra + lane + 32 * j] = acc[0][j];
   }
+}
+
+// One register tile of a host + rider job: S = 3 * 2^LH sets.  Th/Ah: host levels 2^LH .. 1, Tr/Ar: rider
+// levels 3 * 2^(LH-1) .. 3.
+template <int LH, int J, bool MASK>
+__device__ __forceinline__ void rider_tile(const double* __restrict__ xs, int g, int ra, int M0, int rr, int head,
+                                           int groups, double (&Th)[LH + 1], double (&Ah)[LH + 1], double (&Tr)[LH],
+                                           double (&Ar)[LH]) {
+  constexpr int S = 3 << LH, SH = 1 << LH;
+  double acc[S][J];
+  bool tail[J];
+  hier_accumulate<S, J, MASK>(xs, g, ra, M0, rr, head, groups, acc, tail);
+  {  // host chain: sets t, t + SH, t + 2 SH fold into level SH
+    double hv[SH][J];
+#pragma unroll
+    for (int t = 0; t < SH; ++t)
+#pragma unroll
+      for (int j = 0; j < J; ++j) hv[t][j] = (acc[t][j] + acc[t + SH][j]) + acc[t + 2 * SH][j];
+    pow2_levels<SH, J, LH, LH + 1>::run(hv, M0, tail, Th, Ah);
+  }
+  level_halve<S, S, J>(acc);  // level 3 * 2^(LH-1)
+  rider_levels<S, J, LH - 1, LH>::run(acc, M0, tail, Tr, Ar);
 }
 
 // register columns per accumulator set of a hierarchical tile: 16 accumulators per lane, at most 8 columns
@@ -546,37 +624,166 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
   }
 }
 
-// Descriptor of one top q = g 2^L: x = g | L << 16, y = floor(N / g) | (N mod g) << 16.
-// Built once per launch in the order the tops are handed out: grouped by L = min(ctz(q), 3) (capped so
-// that g >= pmin) so that all warps of the SM run the same specialisation at the same time, ascending
-// q inside a group.
-__host__ __device__ inline int hier_top_count(int pmin, int pmax) {
-  const int top_lo = pmin > (pmax >> 1) + 1 ? pmin : (pmax >> 1) + 1;
-  return pmax >= top_lo ? pmax - top_lo + 1 : 0;
+// A host top q = g 2^LH (g odd) together with its rider; candidates g 2^i (i <= LH) and 3 g 2^i (i < LH) that
+// lie in [pmin, pmax].
+template <int LH>
+__device__ __forceinline__ void warp_hier_rider_L(RankCtx rc, int g, int M0, int rr, WarpRank& wr) {
+  constexpr int S = 3 << LH;
+#ifndef PP_RIDER_J1
+#define PP_RIDER_J1 2
+#endif
+  constexpr int J = LH == 1 ? PP_RIDER_J1 : 2;
+  const int lane = threadIdx.x & 31;
+  const double* xs = staged_window();
+  const int head = M0 % S, groups = M0 / S;
+  double Th[LH + 1], Ah[LH + 1], Tr[LH], Ar[LH];
+#pragma unroll
+  for (int i = 0; i <= LH; ++i) Th[i] = Ah[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < LH; ++i) Tr[i] = Ar[i] = 0.0;
+  int ra = 0;
+  for (; ra + 32 * J <= g; ra += 32 * J) rider_tile<LH, J, false>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+  if constexpr (J > 2)
+    for (; ra + 64 <= g; ra += 64) rider_tile<LH, 2, false>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+  for (; ra < g; ra += 32) rider_tile<LH, 1, true>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+  // values 0 .. LH: host levels g 2^i; values LH+1 .. 2 LH: rider levels 3 g 2^i
+  constexpr int NV = 2 * LH + 1;          // 3 or 5
+  constexpr int KP = NV <= 4 ? 4 : 8;
+  double e[KP];
+#pragma unroll
+  for (int i = 0; i < KP; ++i) e[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i <= LH; ++i) {
+    const int M = M0 >> i;
+    const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+    e[i] = fma(w_diff, Ah[i], w_lo * Th[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < LH; ++i) {
+    const int M = M0 / (3 << i);
+    const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+    e[LH + 1 + i] = fma(w_diff, Ar[i], w_lo * Tr[i]);
+  }
+  const double key = warp_sum_multi<KP>(e);
+  constexpr int shift = KP == 4 ? 3 : 2;
+  const int k = lane >> shift;
+  int p = 0;
+  if (k <= LH) p = g << k;
+  else if (k < NV) p = (3 * g) << (k - LH - 1);
+  if (p < rc.pmin || p > rc.pmax) p = 0;
+  consider_lane(rc, key, p, (lane & ((1 << shift) - 1)) == 0, wr.best);
 }
 
-static __global__ void tops_kernel(int N, int pmin, int pmax, uint2* __restrict__ tops) {
-  const int top_lo = max(pmin, (pmax >> 1) + 1);
-  const int q = top_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (q > pmax) return;
-  auto level = [&](int t) {
-    int L = min(__ffs(t) - 1, 3);
-    while (L > 0 && (t >> L) < pmin) --L;
-    return L;
-  };
-  const int L = level(q);
-  // rank = tops with a smaller level + tops of the same level below q
-  int rank = 0;
-  for (int t = top_lo; t <= pmax; ++t) {
-    const int lt = level(t);
-    rank += (lt < L) || (lt == L && t < q);
+// ------------------------------------------------------------------------------------------
+// job table
+// ------------------------------------------------------------------------------------------
+// Descriptor of one job: x = g | L << 16 | rider << 20, y = floor(N / g) | (N mod g) << 16.
+// Built once per launch in hand-out order: grouped by class (plain L = 0..3, then hosts with a rider) so
+// that all warps of an SM run the same specialisation at the same time, ascending q inside a class.
+// (Handing out the long rider jobs FIRST measured 12 % slower.)
+__host__ __device__ inline int hier_ctz(int v) {
+  int c = 0;
+  while (!(v & 1) && c < 30) {
+    v >>= 1;
+    ++c;
   }
-  const int g = q >> L, M0 = N / g, rr = N - M0 * g;
-  tops[rank] = make_uint2((unsigned)g | ((unsigned)L << 16), (unsigned)M0 | ((unsigned)rr << 16));
+  return c;
+}
+__host__ __device__ inline int hier_top_lo(int pmin, int pmax) {
+  return pmin > (pmax >> 1) + 1 ? pmin : (pmax >> 1) + 1;
+}
+// upper bound on the number of jobs (= number of tops)
+__host__ __device__ inline int hier_top_count(int pmin, int pmax) {
+  const int top_lo = hier_top_lo(pmin, pmax);
+  return pmax >= top_lo ? pmax - top_lo + 1 : 0;
+}
+__host__ __device__ inline int hier_level(int t, int pmin) {
+  int L = hier_ctz(t);
+  if (L > 3) L = 3;
+  while (L > 0 && (t >> L) < pmin) --L;
+  return L;
+}
+// the top that rides on host q, or 0
+__host__ __device__ inline int hier_rider_of(int q, int pmin, int pmax, bool riders) {
+  if (!riders) return 0;
+  const int L = hier_level(q, pmin);
+  if (L < 1 || L > 2 || hier_ctz(q) != L) return 0;  // host classes: q = 2 g or 4 g, g odd
+  int R;
+  if (3 * q <= 2 * pmax) R = 3 * q / 2;
+  else if (L == 2) R = 3 * q / 4;
+  else return 0;
+  if (R < hier_top_lo(pmin, pmax) || R > pmax) return 0;
+  if (hier_level(R, pmin) != hier_ctz(R)) return 0;  // the rider's own chain is exactly 3 g 2^i
+  return R;
+}
+constexpr int kHierRiderMaxTops = 4096;  // rider matching runs in one CTA with two ints of shared memory per top
+
+// number of jobs the table will hold (host-side mirror of tops_kernel)
+inline int hier_job_count(int pmin, int pmax, bool riders) {
+  const int n = hier_top_count(pmin, pmax);
+  if (!riders || n > kHierRiderMaxTops) return n;
+  const int lo = hier_top_lo(pmin, pmax);
+  int jobs = n;
+  for (int q = lo; q <= pmax; ++q)
+    if (hier_rider_of(q, pmin, pmax, true)) --jobs;
+  return jobs;
+}
+
+// one CTA; dynamic shared memory: 2 ints per top
+static __global__ void tops_kernel(int N, int pmin, int pmax, int riders, uint2* __restrict__ tops) {
+  extern __shared__ int tk_smem[];
+  const int lo = hier_top_lo(pmin, pmax);
+  const int n = pmax >= lo ? pmax - lo + 1 : 0;
+  int* rider = tk_smem;      // rider[t - lo]: the top riding on t (0: none)
+  int* cls = tk_smem + n;    // cls[t - lo]: hand-out class of t, -1 if t rides on another top
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    rider[i] = hier_rider_of(lo + i, pmin, pmax, riders != 0);
+    cls[i] = 0;
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (rider[i]) cls[rider[i] - lo] = -1;  // each top rides on at most one host
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x)
+    if (cls[i] == 0) cls[i] = rider[i] ? 4 + hier_level(lo + i, pmin) : hier_level(lo + i, pmin);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = cls[i];
+    if (c < 0) continue;
+    int rank = 0;
+    for (int u = 0; u < n; ++u) {
+      const int cu = cls[u];
+      rank += (cu >= 0) && (cu < c || (cu == c && u < i));
+    }
+    const int q = lo + i, L = hier_level(q, pmin);
+    const int g = q >> L, M0 = N / g, rr = N - M0 * g;
+    tops[rank] = make_uint2((unsigned)g | ((unsigned)L << 16) | ((rider[i] ? 1u : 0u) << 20),
+                            (unsigned)M0 | ((unsigned)rr << 16));
+  }
+}
+
+// Build the job table in the caller-provided buffer (>= hier_top_count entries) on `stream`; returns the
+// number of jobs.
+inline int build_hier_jobs(int N, int pmin, int pmax, uint2* tops, cudaStream_t stream) {
+  const int n = hier_top_count(pmin, pmax);
+  if (n <= 0) return 0;
+  const bool riders = n <= kHierRiderMaxTops && pp_get_fold_mode() != PP_FOLD_HIERARCHICAL_NO_RIDERS;
+  const size_t smem = (size_t)2 * n * sizeof(int);
+  if (smem > 48 * 1024)
+    cudaFuncSetAttribute(tops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  tops_kernel<<<1, 512, smem, stream>>>(N, pmin, pmax, riders ? 1 : 0, tops);
+  return hier_job_count(pmin, pmax, riders);
 }
 
 __device__ __forceinline__ void warp_hier_top(const RankCtx& rc, uint2 e, double* scr, WarpRank& wr) {
-  const int g = e.x & 0xffff, L = e.x >> 16, M0 = e.y & 0xffff, rr = e.y >> 16;
+  const int g = e.x & 0xffff, L = (e.x >> 16) & 0xf, M0 = e.y & 0xffff, rr = e.y >> 16;
+#ifndef PP_NO_RIDERS
+  if (e.x >> 20) {
+    if (L == 1) warp_hier_rider_L<1>(rc, g, M0, rr, wr);
+    else warp_hier_rider_L<2>(rc, g, M0, rr, wr);
+    return;
+  }
+#endif
   switch (L) {
     case 0: warp_hier_top_L<0>(rc, g, M0, rr, scr, wr); break;
     case 1: warp_hier_top_L<1>(rc, g, M0, rr, scr, wr); break;

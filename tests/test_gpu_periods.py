@@ -109,14 +109,16 @@ def test_sweep_metrics_vs_oracle(P, trunc, orth):
 
 
 @pytest.mark.parametrize("n,pmin,pmax", [(4096, 2, 1024), (2000, 2, 666), (4095, 3, 1000), (1000, 17, 500),
-                                          (8192, 2, 2730), (512, 2, 100), (4096, 600, 1024)])
+                                          (8192, 2, 2730), (512, 2, 100), (4096, 600, 1024), (4096, 2, 1365),
+                                          (3001, 2, 1500), (777, 5, 259), (4096, 2, 682), (1024, 2, 341)])
 def test_sweep_hierarchical_matches_direct(P, n, pmin, pmax):
-    """The hierarchical ranking sweep (S_p from S_2p) agrees with the sequential fold to rounding."""
+    """The hierarchical ranking sweep (S_p from S_2p, tops that are 3/2 or 3/4 of an even top riding on its
+    pass) agrees with the sequential fold to rounding, for every candidate period."""
     from pyperiod_b200 import _lib
     xb = synth.synth_batch(3, n, 4242)
     try:
         out = {}
-        for mode in (_lib.FOLD_DIRECT, _lib.FOLD_HIERARCHICAL):
+        for mode in (_lib.FOLD_DIRECT, _lib.FOLD_HIERARCHICAL_NO_RIDERS, _lib.FOLD_HIERARCHICAL):
             _lib.set_fold_mode(mode)
             for metric in ("norm", "gamma"):
                 out[mode, metric] = P().sweep(xb, metric=metric, min_length=pmin, max_length=pmax)
@@ -129,6 +131,9 @@ def test_sweep_hierarchical_matches_direct(P, n, pmin, pmax):
         np.testing.assert_allclose(mh[:, pmin:], md[:, pmin:], rtol=1e-13, atol=0)
         assert np.array_equal(pd_, ph)
         np.testing.assert_allclose(vh, vd, rtol=1e-13)
+        mn, pn, vn = out[_lib.FOLD_HIERARCHICAL_NO_RIDERS, metric]
+        np.testing.assert_allclose(mn[:, pmin:], md[:, pmin:], rtol=1e-13, atol=0)
+        assert np.array_equal(pd_, pn)
 
 
 def test_mbest_fold_modes_agree(P):
