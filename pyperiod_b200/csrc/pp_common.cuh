@@ -135,6 +135,25 @@ struct WindowLoader {
 };
 
 // ------------------------------------------------------------------------------------------
+// dynamic hand-out of windows to the CTAs of a persistent grid
+// ------------------------------------------------------------------------------------------
+// Per-window cost varies (accepted periods, rounds, dictionary sizes), and a static stride leaves a tail of
+// idle CTAs at the end of a launch.  `counter` is a global int zeroed on the stream before the launch
+// (nullptr => static stride).  Usage:  for (WindowQueue q(counter); q.b < B; q.next()) { ... q.b ... }
+struct WindowQueue {
+  int* counter;
+  int b;
+  __device__ explicit WindowQueue(int* c) : counter(c), b(blockIdx.x) {}
+  __device__ void next() {  // all threads call; contains CTA barriers
+    __shared__ int s_next;
+    __syncthreads();  // everyone is done with window b
+    if (threadIdx.x == 0) s_next = counter ? (int)gridDim.x + atomicAdd(counter, 1) : b + (int)gridDim.x;
+    __syncthreads();
+    b = s_next;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
 // exact fold + mean: bit-for-bit the reference's numpy arithmetic (Periods.py:171-198)
 // ------------------------------------------------------------------------------------------
 // Source element n is src[n] (WRAP=false) or src[n mod P] (WRAP=true: the length-N tiling

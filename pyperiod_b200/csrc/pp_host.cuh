@@ -53,4 +53,12 @@ static inline double* carve(void* ws, size_t ws_bytes, size_t& off, size_t bytes
   return p;
 }
 
+// global window counter of a WindowQueue, zeroed on `stream`; nullptr (static stride) when the workspace has no room
+static inline int* carve_window_counter(void* ws, size_t ws_bytes, size_t& off, cudaStream_t stream) {
+  double* p = carve(ws, ws_bytes, off, 256);
+  if (p == nullptr) return nullptr;
+  if (cudaMemsetAsync(p, 0, sizeof(int), stream) != cudaSuccess) return nullptr;
+  return reinterpret_cast<int*>(p);
+}
+
 }  // namespace pp

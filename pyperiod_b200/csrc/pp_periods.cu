@@ -160,7 +160,7 @@ norm_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int p, doub
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, int pmax, int metric, int trunc,
              int orth, int hier, Tables tb, double* __restrict__ metric_out, int32_t* __restrict__ best_p,
-             double* __restrict__ best_val, double* __restrict__ warp_scr, const uint2* __restrict__ tops, int ntops) {
+             double* __restrict__ best_val, double* __restrict__ warp_scr, const uint2* __restrict__ tops, int ntops, int* __restrict__ next_window) {
   unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, pmax, 0, true, hier != 0);
   Smem sm(smem_raw, pl);
@@ -168,7 +168,8 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
   loader.init(sm.bar);
   zero_pad(sm.xs, N, pl.xs_len);
   sweep_shared_init(sm.sweep);
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  for (WindowQueue wq(next_window); wq.b < B; wq.next()) {
+    const int b = wq.b;
     loader.load(sm.xs, x + (size_t)b * ldx, N);
     double e_res = 0.0;
     if (metric == PP_METRIC_IMPOSED) e_res = cta_sum_sq(sm.xs, N, sm.red);
@@ -586,7 +587,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thresh, int n_periods, int trunc_i,
            int orth_i, Tables tb, int kmax, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
            double* __restrict__ bases_out, int32_t* __restrict__ count_out, int32_t* __restrict__ status_out,
-           double* __restrict__ ws_scr) {
+           double* __restrict__ ws_scr, int* __restrict__ next_window) {
   unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, n_periods, 0, true);
   Smem sm(smem_raw, pl);
@@ -597,7 +598,8 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
   loader.init(sm.bar);
   zero_pad(sm.xs, N, pl.xs_len);
   sweep_shared_init(sm.sweep);
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  for (WindowQueue wq(next_window); wq.b < B; wq.next()) {
+    const int b = wq.b;
     loader.load(sm.xs, x + (size_t)b * ldx, N);
     const double e_data = cta_sum_sq(sm.xs, N, sm.red);
     if (threadIdx.x == 0) {
@@ -667,7 +669,7 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, int max_length, double ratio,
              int trunc_i, int orth_i, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
-             double* __restrict__ bases_out, int32_t* __restrict__ status_out) {
+             double* __restrict__ bases_out, int32_t* __restrict__ status_out, int* __restrict__ next_window) {
   unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, max_length, 0, true);
   Smem sm(smem_raw, pl);
@@ -677,7 +679,8 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
   loader.init(sm.bar);
   zero_pad(sm.xs, N, pl.xs_len);
   sweep_shared_init(sm.sweep);
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  for (WindowQueue wq(next_window); wq.b < B; wq.next()) {
+    const int b = wq.b;
     loader.load(sm.xs, x + (size_t)b * ldx, N);
     const double og = sqrt(cta_sum_sq(sm.xs, N, sm.red)) / sqrtN;
     double prev = og;
@@ -782,6 +785,11 @@ int pp_set_fold_mode(int32_t mode) {
   return 0;
 }
 int pp_get_fold_mode(void) { return g_fold_mode; }
+int pp_sweep_passes(int32_t pmin, int32_t pmax) {
+  if (pmax < pmin) return 0;
+  if (g_fold_mode == PP_FOLD_DIRECT) return pmax - pmin + 1;
+  return hier_job_count(pmin, pmax, g_fold_mode == PP_FOLD_HIERARCHICAL);
+}
 int pp_set_profile_buffer(void* dev_u64x8) {
   g_prof = reinterpret_cast<unsigned long long*>(dev_u64x8);
   return 0;
@@ -898,8 +906,10 @@ int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, i
     ntops = build_hier_jobs(N, pmin, pmax, tops, (cudaStream_t)stream);
   }
   Tables tb{chain_off, chain_q, nullptr, nullptr};
+  int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
   sweep_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, pmin, pmax, metric, trunc, orth, hier,
-                                                                     tb, metric_out, best_p, best_val, scr, tops, ntops);
+                                                                     tb, metric_out, best_p, best_val, scr, tops, ntops,
+                                                                     next_window);
   return check_cuda(cudaGetLastError(), "sweep_kernel launch");
 }
 
@@ -967,8 +977,10 @@ int pp_small_to_large(const double* x, int64_t ldx, int32_t B, int32_t N, double
     if (!scr) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
   }
   Tables tb{chain_off, chain_q, nullptr, nullptr};
+  int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
   s2l_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, thresh, n_periods, trunc, orth, tb,
-                                                                   kmax, periods, powers, bases, count, status, scr);
+                                                                   kmax, periods, powers, bases, count, status, scr,
+                                                                   next_window);
   return check_cuda(cudaGetLastError(), "s2l_kernel launch");
 }
 
@@ -977,8 +989,6 @@ int pp_best_correlation(const double* x, int64_t ldx, int32_t B, int32_t N, int3
                         int32_t table_pmax, uint32_t* periods, double* powers, double* bases, int32_t* status,
                         void* workspace, size_t workspace_bytes, void* stream) {
   if (B == 0) return 0;  // empty batch: nothing to validate or launch
-  (void)workspace;
-  (void)workspace_bytes;
   if (int rc = check_common(x, ldx, B, N)) return rc;
   if (num < 1) return fail(-1, "num must be >= 1%s");
   if (max_length < 3 || max_length > N + 1) return fail(-1, "need 3 <= max_length <= N+1%s");
@@ -991,8 +1001,10 @@ int pp_best_correlation(const double* x, int64_t ldx, int32_t B, int32_t N, int3
   if (int rc = prep_kernel(bcorr_kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B);
   Tables tb{chain_off, chain_q, nullptr, nullptr};
+  size_t off = 0;
+  int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
   bcorr_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, max_length, ratio, trunc, orth,
-                                                                     tb, periods, powers, bases, status);
+                                                                     tb, periods, powers, bases, status, next_window);
   return check_cuda(cudaGetLastError(), "bcorr_kernel launch");
 }
 

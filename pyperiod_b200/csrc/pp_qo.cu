@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, double thresh, int pmin, int pmax,
                int trunc, int hier, const int32_t* __restrict__ phi, int rmax, QoOut out, double* __restrict__ ws_G,
                double* __restrict__ ws_Pt, double* __restrict__ ws_norms, const uint2* __restrict__ tops, int ntops,
-               unsigned long long* __restrict__ prof) {
+               unsigned long long* __restrict__ prof, int* __restrict__ next_window) {
   unsigned char* smem = pp_smem;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0);
   const size_t ldg = (size_t)pl.rmax;
@@ -503,7 +503,8 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
   for (int i = N + tid; i < pl.xs_len; i += kThreads) c.xs[i] = 0.0;
   sweep_shared_init(sweep);
 
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  for (WindowQueue wq(next_window); wq.b < B; wq.next()) {
+    const int b = wq.b;
     loader.load(x0, x + (size_t)b * ldx, N);
     // zero-signal early out (QOPeriods.py:394-406): sum |x| <= 1e-16
     double sa = 0.0;
@@ -616,7 +617,7 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
 __global__ void __launch_bounds__(kThreads, 2)
 qo_solve_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int kmax, const int32_t* __restrict__ periods,
                 const int32_t* __restrict__ nper, int pmax, const int32_t* __restrict__ phi, int rmax, QoOut out,
-                double* __restrict__ ws_G, double* __restrict__ ws_Pt) {
+                double* __restrict__ ws_G, double* __restrict__ ws_Pt, int* __restrict__ next_window) {
   unsigned char* smem = pp_smem;
   const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
   const size_t ldg = (size_t)pl.rmax;
@@ -629,7 +630,8 @@ qo_solve_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int kma
   c.t = timers;
   WindowLoader loader;
   loader.init(bar);
-  for (int b = blockIdx.x; b < B; b += gridDim.x) {
+  for (WindowQueue wq(next_window); wq.b < B; wq.next()) {
+    const int b = wq.b;
     loader.load(x0, x + (size_t)b * ldx, N);
     const int nfound = min(nper[b], kmax);
     for (int i = tid; i < nfound; i += kThreads) c.found[i] = periods[(size_t)b * kmax + i];
@@ -714,9 +716,11 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
     ntops = build_hier_jobs(N, pmin, pmax, tops, (cudaStream_t)stream);
   }
   QoOut o{periods, norms, n_periods, dict_q, dict_keep, n_dict, n_weights, weights, res, status};
+  int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
   qo_find_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, thresh, pmin, pmax, trunc,
                                                                        hier, phi, pl.rmax, o, G, Pt, nr, tops, ntops,
-                                                                       reinterpret_cast<unsigned long long*>(pp_get_profile_buffer()));
+                                                                       reinterpret_cast<unsigned long long*>(pp_get_profile_buffer()),
+                                                                       next_window);
   return check_cuda(cudaGetLastError(), "qo_find_kernel launch");
 }
 
@@ -739,8 +743,9 @@ int pp_qo_solve(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t kmax
   double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.rmax * 8);
   if (!G || !Pt) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
   QoOut o{nullptr, nullptr, nullptr, dict_q, dict_keep, n_dict, n_weights, weights, res, status};
+  int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
   qo_solve_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, kmax, periods, nper, pmax, phi,
-                                                                        pl.rmax, o, G, Pt);
+                                                                        pl.rmax, o, G, Pt, next_window);
   return check_cuda(cudaGetLastError(), "qo_solve_kernel launch");
 }
 

@@ -288,10 +288,12 @@ class Periods:
         powers = torch.empty((w.b, num), dtype=torch.float64, device=w.device)
         bases = torch.empty((w.b, num, w.n), dtype=torch.float64, device=w.device) if return_bases else None
         status = torch.empty((w.b,), dtype=torch.int32, device=w.device)
+        ws = Workspace.get(w.device, lib.pp_workspace_bytes(_lib.ALGO_BCORR, w.n, max_length, num,
+                                                            int(self._orthogonalize)))
         _lib.check(lib.pp_best_correlation(ptr(w.tensor), w.ldx, w.b, w.n, num, max_length, ratio,
                                            int(self._trunc_to_integer_multiple), int(self._orthogonalize), ptr(co),
                                            ptr(cq), tb.pmax, ptr(periods), ptr(powers), ptr(bases), ptr(status),
-                                           C.c_void_p(0), 0, stream_ptr(w.device)), "pp_best_correlation")
+                                           ptr(ws), ws.numel(), stream_ptr(w.device)), "pp_best_correlation")
         res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases), _export(w, status))
         if w.was_1d:
             if int(res.status[0]) == _lib.STATUS_NO_PERIOD:
