@@ -540,9 +540,12 @@ __device__ __forceinline__ void rider_tile(const double* __restrict__ xs, int g,
   rider_levels<S, J, LH - 1, LH>::run(acc, M0, tail, Tr, Ar);
 }
 
-// register columns per accumulator set of a hierarchical tile: 16 accumulators per lane, at most 8 columns
+// register columns per accumulator set of a hierarchical tile: 8 accumulators per lane (8 / 4 / 2 / 1 columns
+// for L = 0..3).  16 accumulators halve the number of tiles of L >= 1 but measured 1.4 % slower: the larger
+// tile bodies cost more in instruction fetch than the saved per-tile overhead (ncu: 9 % of the stall samples
+// are no_instruction once the rider tiles are in the kernel).
 #ifndef PP_HIER_ACCS
-#define PP_HIER_ACCS 16
+#define PP_HIER_ACCS 8
 #endif
 template <int L>
 struct hier_cols {
@@ -564,8 +567,10 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
   for (int i = 0; i <= L; ++i) T[i] = A[i] = 0.0;
   int ra = 0;
   for (; ra + 32 * J <= g; ra += 32 * J) hier_tile<L, J, false>(xs, g, ra, M0, rr, T, A, out);
+#ifndef PP_NO_J2_TILES
   if constexpr (J > 2)
     for (; ra + 64 <= g; ra += 64) hier_tile<L, 2, false>(xs, g, ra, M0, rr, T, A, out);
+#endif
   for (; ra < g; ra += 32) hier_tile<L, 1, true>(xs, g, ra, M0, rr, T, A, out);
   // per-lane partial energies of the L + 1 levels, reduced together
   constexpr int KP = L == 0 ? 1 : (L == 1 ? 2 : 4);
