@@ -201,6 +201,7 @@ int pp_ramanujan_select(const double *norms, int32_t B, int32_t ld_norms, int32_
 /* ---- roofline denominators measured live -----------------------
  * kind 0: shared-memory load bandwidth, out_host[0] = bytes/s over the whole chip;
  * kind 1: FP64 add throughput,           out_host[0] = adds/s  over the whole chip;
+ * kind 2: FP64 tensor cores (DMMA m8n8k4), out_host[0] = flop/s over the whole chip;
  * out_host[1] = SM clock (MHz) observed during the run, out_host[2] = kernel ms.
  * Synchronous; allocates and frees its own 64-byte scratch. */
 int pp_microbench(int32_t kind, int32_t iters, double *out_host);

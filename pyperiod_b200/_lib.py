@@ -105,7 +105,7 @@ def sweep_passes(pmin: int, pmax: int) -> int:
 
 
 def microbench(kind: int, iters: int = 4000) -> dict:
-    """Measured chip-wide peak: kind 0 = shared-memory bytes/s, kind 1 = FP64 adds/s."""
+    """Measured chip-wide peak: kind 0 = shared-memory bytes/s, kind 1 = FP64 adds/s, kind 2 = DMMA flop/s."""
     out = (C.c_double * 3)()
     check(load().pp_microbench(kind, iters, out), "pp_microbench")
     return {"per_s": out[0], "sm_mhz": out[1], "ms": out[2]}

@@ -55,16 +55,39 @@ __global__ void __launch_bounds__(1024) dadd_kernel(int iters, double seed, doub
   const double t = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
   if (t == 0.123456789) *sink = t;
 }
+// 8 independent m8n8k4 FP64 tensor-core accumulation chains per warp (SASS DMMA): the denominator of the
+// Ramanujan contraction's roofline.
+__global__ void __launch_bounds__(1024) dmma_kernel(int iters, double seed, double* sink, long long* cycles) {
+  double c[8][2];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) c[u][0] = c[u][1] = seed * (u + 1);
+  const double a = seed + 1e-9 * (double)threadIdx.x, b = 1.0 - 1e-9 * (double)(threadIdx.x & 7);
+  const long long t0 = clock64();
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[u][0]), "+d"(c[u][1])
+                   : "d"(a), "d"(b));
+  }
+  const long long t1 = clock64();
+  if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+  double t = 0.0;
+#pragma unroll
+  for (int u = 0; u < 8; ++u) t += c[u][0] + c[u][1];
+  if (t == 0.123456789) *sink = t;
+}
 }  // namespace pp
 
 using namespace pp;
 
 // kind 0: shared-memory bandwidth  -> out_host[0] = bytes/s (whole chip)
 // kind 1: FP64 add throughput      -> out_host[0] = adds/s  (whole chip)
+// kind 2: FP64 tensor-core (DMMA m8n8k4) throughput -> out_host[0] = flop/s (whole chip)
 // out_host[1] = SM clock in MHz during the run (device cycles / event time); out_host[2] = ms.
 // Synchronous (host timing with CUDA events); call outside any timed region.
 extern "C" int pp_microbench(int32_t kind, int32_t iters, double* out_host) {
-  if (out_host == nullptr || iters < 1 || kind < 0 || kind > 1) return fail(-1, "bad microbench arguments%s", "");
+  if (out_host == nullptr || iters < 1 || kind < 0 || kind > 2) return fail(-1, "bad microbench arguments%s", "");
   int dev = 0, sms = 0;
   if (int rc = check_cuda(cudaGetDevice(&dev), "cudaGetDevice")) return rc;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -84,8 +107,10 @@ extern "C" int pp_microbench(int32_t kind, int32_t iters, double* out_host) {
     cudaEventRecord(e0);
     if (kind == 0)
       smem_bw_kernel<<<blocks, threads, smem>>>(iters, reinterpret_cast<unsigned long long*>(scratch) + 2, cyc);
-    else
+    else if (kind == 1)
       dadd_kernel<<<blocks, threads>>>(iters, 1.0, reinterpret_cast<double*>(scratch) + 2, cyc);
+    else
+      dmma_kernel<<<blocks, threads>>>(iters, 1.0, reinterpret_cast<double*>(scratch) + 2, cyc);
     cudaEventRecord(e1);
     if (int rc = check_cuda(cudaEventSynchronize(e1), "microbench kernel")) {
       cudaFree(scratch);
@@ -101,7 +126,8 @@ extern "C" int pp_microbench(int32_t kind, int32_t iters, double* out_host) {
     }
   }
   const double secs = best_ms * 1e-3;
-  const double per_thread = kind == 0 ? (double)iters * 8 * 16 : (double)iters * 32;
+  // kind 2: 8 MMAs of 8*8*4*2 = 512 flop per warp and iteration = 128 flop per thread
+  const double per_thread = kind == 0 ? (double)iters * 8 * 16 : (kind == 1 ? (double)iters * 32 : (double)iters * 128);
   out_host[0] = per_thread * threads * blocks / secs;
   // two CTAs share an SM, so one CTA's cycle count spans (about) the whole kernel
   out_host[1] = (double)best_cyc / secs * 1e-6;
