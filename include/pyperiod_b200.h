@@ -181,6 +181,16 @@ int pp_qo_solve(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t kmax
                 int32_t *dict_q, int32_t *dict_keep, int32_t *n_dict, int32_t *n_weights, double *weights,
                 double *res, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 
+/* Solve stage for a caller-supplied dictionary layout: entry k of window b is the period dict_q[b,k] with its
+ * first dict_rows[b,k] natural-basis rows (0 = all rows).  Replaces get_subspaces + solve_quadratic of the
+ * QOPeriodsWithGCDsExtracted subclass (QOPeriodsWithGCDsExtracted.py:98-143, QOPeriods.py:743-805), whose
+ * layout depends on CPython set order and is therefore built by the host layer.  weights[B, rmax],
+ * res[B, N] (nullable), status: PP_STATUS_OK / SINGULAR / TOO_LARGE. */
+int pp_qo_solve_rows(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t kmax, const int32_t *dict_q,
+                     const int32_t *dict_rows, const int32_t *n_dict, int32_t pmax, int32_t rmax,
+                     int32_t *n_weights, double *weights, double *res, int32_t *status, void *workspace,
+                     size_t workspace_bytes, void *stream);
+
 /* ---- RamanujanPeriods.find_periods (RamanujanPeriods.py:67-86, 124-169) ------------------
  * norms[b, q] = sum_n (sum_i <x, r_i> r_i)[n]^2 over the q-row Ramanujan dictionary of period q,
  * evaluated in fp64 as the dense contraction (q / phi(q)^2) * circ(c_q) * S_q on the FP64 tensor

@@ -59,6 +59,29 @@ def get_subspaces(periods, n: int):
     return np.vstack(blocks), layout
 
 
+def get_subspaces_gcds_extracted(periods, n: int):
+    """Dictionary of QOPeriodsWithGCDsExtracted (QOPeriodsWithGCDsExtracted.py:98-143): the found periods
+    plus every common factor of every pair, iterated in the order of `set(sorted(P))`; a period keeps
+    p - sum(phi(f)) rows over its proper factors f that are themselves in P (0 -> all rows, :972)."""
+    q = [int(v) for v in periods]
+    pset = set()
+    for a, b in itertools.combinations(q, 2):
+        pset = pset.union(set.intersection(divisor_set(a), divisor_set(b)))
+    pset = pset.union(q)
+    pset = set(sorted(pset))
+    layout = {}
+    blocks = [np.zeros((0, n))]
+    for pp in pset:
+        f = divisor_set(pp)
+        if pp != 1:                      # get_factors(p, remove_n=True) keeps n when n == 1 (QOPeriods.py:73)
+            f = f - {pp}
+        f = f.intersection(pset)
+        keep = int(pp - np.sum(np.array([phi(v) for v in f])))
+        blocks.append(indicator_rows(pp, n, keep))
+        layout[str(pp)] = keep
+    return np.vstack(blocks), layout
+
+
 def solve_quadratic(x: np.ndarray, a: np.ndarray, kind: str = "solve"):
     """Normal equations (A A^T) w = A x and reconstruction A^T w.  QOPeriods.py:743-805."""
     gram = np.matmul(a, a.T)
@@ -71,8 +94,10 @@ def solve_quadratic(x: np.ndarray, a: np.ndarray, kind: str = "solve"):
 
 
 def find_periods(x: np.ndarray, num=None, thresh=None, min_length: int = 2, max_length=None,
-                 trunc: bool = False, test_function=None):
-    """QOPeriods.find_periods, default branch.  QOPeriods.py:313-596."""
+                 trunc: bool = False, test_function=None, gcds_extracted: bool = False):
+    """QOPeriods.find_periods, default branch.  QOPeriods.py:313-596.  `gcds_extracted` swaps in the
+    dictionary layout of the QOPeriodsWithGCDsExtracted subclass (same loop, inherited)."""
+    get_subspaces = get_subspaces_gcds_extracted if gcds_extracted else globals()["get_subspaces"]
     n = len(x)
     if max_length is None:
         max_length = int(np.floor(n / 3))

@@ -8,7 +8,8 @@ generators used by the tests and the benchmark.
 """
 from . import synth  # noqa: F401  (numpy only)
 
-__all__ = ["Periods", "BatchResult", "QOPeriods", "QOBatchResult", "RamanujanPeriods", "synth"]
+__all__ = ["Periods", "BatchResult", "QOPeriods", "QOBatchResult", "QOPeriodsWithGCDsExtracted", "RamanujanPeriods",
+           "synth"]
 
 
 def __getattr__(name):
@@ -16,7 +17,7 @@ def __getattr__(name):
     if name in ("Periods", "BatchResult"):
         from . import periods as _p
         return getattr(_p, name)
-    if name in ("QOPeriods", "QOBatchResult"):
+    if name in ("QOPeriods", "QOBatchResult", "QOPeriodsWithGCDsExtracted", "QOGcdBatchResult"):
         from . import qoperiods as _q
         return getattr(_q, name)
     if name == "RamanujanPeriods":

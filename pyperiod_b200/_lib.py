@@ -55,6 +55,7 @@ SIGNATURES = {
                                      _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
     "pp_qo_solve": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _i32,
                               _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "pp_qo_solve_rows": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
 }
 
 _lib = None

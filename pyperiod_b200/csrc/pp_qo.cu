@@ -344,11 +344,12 @@ __device__ void qo_layout(const QoCtx& c, int nfound) {
 
 // Returns 0 ok, PP_STATUS_SINGULAR, PP_STATUS_TOO_LARGE.  On success wv holds the weights, xs the residual,
 // and *e_recon the sum of squares of the reconstruction.  All threads call; contains barriers.
-__device__ int cta_qo_solve(const QoCtx& c, int nfound, double* e_recon) {
+__device__ int cta_qo_solve(const QoCtx& c, int nfound, double* e_recon, bool explicit_layout = false) {
   const int tid = threadIdx.x;
   const int N = c.N;
   long long tm = clock64();
-  qo_layout(c, nfound);
+  // explicit_layout: the caller has filled dict_q / dict_rows / dict_off and misc[0] (entries), misc[1] (rows)
+  if (!explicit_layout) qo_layout(c, nfound);
   __syncthreads();
   { const long long now = clock64(); c.t[0] += now - tm; tm = now; }
   const int ndict = c.misc[0], R = c.misc[1];
@@ -661,6 +662,64 @@ qo_solve_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int kma
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// solve stage for a caller-supplied dictionary layout (QOPeriodsWithGCDsExtracted.get_subspaces,
+// QOPeriodsWithGCDsExtracted.py:98-143: the layout depends on CPython set order and is built on the host)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads, 2)
+qo_solve_rows_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int kmax, const int32_t* __restrict__ dict_q,
+                     const int32_t* __restrict__ dict_rows, const int32_t* __restrict__ n_dict, int pmax, int rmax,
+                     int32_t* __restrict__ n_weights, double* __restrict__ weights, double* __restrict__ res,
+                     int32_t* __restrict__ status, double* __restrict__ ws_G, double* __restrict__ ws_Pt,
+                     int* __restrict__ next_window) {
+  unsigned char* smem = pp_smem;
+  const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
+  const size_t ldg = (size_t)pl.rmax;
+  QoCtx c = make_ctx(smem, pl, N, kmax, nullptr, ws_G + (size_t)blockIdx.x * ldg * ldg,
+                     ws_Pt + (size_t)blockIdx.x * kCholNb * ldg);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + pl.off_bar());
+  double* x0 = const_cast<double*>(c.x0);
+  const int tid = threadIdx.x;
+  long long timers[4] = {0, 0, 0, 0};
+  c.t = timers;
+  WindowLoader loader;
+  loader.init(bar);
+  for (WindowQueue wq(next_window); wq.b < B; wq.next()) {
+    const int b = wq.b;
+    loader.load(x0, x + (size_t)b * ldx, N);
+    const int nd = min(max(n_dict[b], 0), kmax);
+    if (tid == 0) {
+      int off = 0;
+      for (int k = 0; k < nd; ++k) {
+        const int q = dict_q[(size_t)b * kmax + k];
+        int rows = dict_rows[(size_t)b * kmax + k];
+        rows = rows > 0 && rows <= q ? rows : q;   // 0 keeps every row (QOPeriods.py:972)
+        c.dict_q[k] = q;
+        c.dict_keep[k] = rows;
+        c.dict_rows[k] = rows;
+        c.dict_off[k] = off;
+        off += rows;
+      }
+      c.dict_off[nd] = off;
+      c.misc[0] = nd;
+      c.misc[1] = off;
+    }
+    __syncthreads();
+    double e_recon = 0.0;
+    const int rc = cta_qo_solve(c, nd, &e_recon, true);
+    if (rc == PP_STATUS_OK) {
+      const int R = c.misc[1];
+      for (int i = tid; i < R; i += kThreads) weights[(size_t)b * c.rmax + i] = c.wv[i];
+      if (res)
+        for (int n = tid; n < N; n += kThreads) res[(size_t)b * N + n] = c.xs[n];
+      if (tid == 0) n_weights[b] = R;
+    } else if (tid == 0) {
+      n_weights[b] = 0;
+    }
+    if (tid == 0) status[b] = rc;
+  }
+}
+
 }  // namespace pp
 
 using namespace pp;
@@ -747,6 +806,32 @@ int pp_qo_solve(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t kmax
   qo_solve_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, kmax, periods, nper, pmax, phi,
                                                                         pl.rmax, o, G, Pt, next_window);
   return check_cuda(cudaGetLastError(), "qo_solve_kernel launch");
+}
+
+int pp_qo_solve_rows(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t kmax, const int32_t* dict_q,
+                     const int32_t* dict_rows, const int32_t* n_dict, int32_t pmax, int32_t rmax, int32_t* n_weights,
+                     double* weights, double* res, int32_t* status, void* workspace, size_t workspace_bytes,
+                     void* stream) {
+  if (B == 0) return 0;  // empty batch: nothing to validate or launch
+  if (x == nullptr || B < 0 || N < 2 || ldx < 1) return fail(-1, "bad window arguments%s");
+  if (kmax < 1 || kmax > 256) return fail(-1, "need 1 <= kmax <= 256%s");
+  if (pmax < 1 || pmax > N) return fail(-1, "need 1 <= pmax <= N%s");
+  if (rmax < 2) return fail(-1, "rmax must be >= 2%s");
+  if (!dict_q || !dict_rows || !n_dict || !n_weights || !weights || !status) return fail(-1, "pointers are null%s");
+  DeviceFacts f;
+  if (int rc = device_facts(f)) return rc;
+  const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
+  if (int rc = prep_kernel(qo_solve_rows_kernel, pl.bytes(), f)) return rc;
+  const int grid = grid_for(f, pl.bytes(), B, 2);
+  size_t off = 0;
+  double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.rmax * 8);
+  double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.rmax * 8);
+  if (!G || !Pt) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
+  int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
+  qo_solve_rows_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, kmax, dict_q, dict_rows, n_dict,
+                                                                             pmax, pl.rmax, n_weights, weights, res,
+                                                                             status, G, Pt, next_window);
+  return check_cuda(cudaGetLastError(), "qo_solve_rows_kernel launch");
 }
 
 }  // extern "C"

@@ -251,3 +251,120 @@ def _reduce_rows(a: torch.Tensor) -> torch.Tensor:
         if r > rank:
             kept, rank = trial, r
     return kept
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# QOPeriodsWithGCDsExtracted (pyPeriod/QOPeriodsWithGCDsExtracted.py:93-143)
+# ---------------------------------------------------------------------------------------------------------------
+def gcds_extracted_layout(periods) -> dict:
+    """{str(p): rows kept} of QOPeriodsWithGCDsExtracted.get_subspaces (QOPeriodsWithGCDsExtracted.py:98-143).
+
+    The dictionary holds the found periods plus every common factor of every pair, in the iteration order of
+    `set(sorted(P))` -- a CPython set of ints, evaluated here exactly as the reference evaluates it -- and a period
+    keeps p - sum(phi(f)) rows over its proper factors f that are themselves in P (0 = all rows, QOPeriods.py:972).
+    """
+    q = [int(v) for v in periods]
+    phi = get_tables(max(q + [2])).phi
+    divisors = lambda n: {d for d in range(1, n + 1) if n % d == 0}
+    pset = set()
+    for a, b in itertools.combinations(q, 2):
+        pset = pset.union(set.intersection(divisors(a), divisors(b)))
+    pset = pset.union(q)
+    pset = set(sorted(pset))
+    layout = {}
+    for p in pset:
+        f = divisors(p)
+        if p != 1:  # get_factors(p, remove_n=True) keeps n when n == 1 (QOPeriods.py:73)
+            f = f - {p}
+        layout[str(p)] = int(p - sum(int(phi[v]) for v in f.intersection(pset)))
+    return layout
+
+
+@dataclass
+class QOGcdBatchResult:
+    """Batch outputs of QOPeriodsWithGCDsExtracted.find_periods (numpy)."""
+    base: QOBatchResult   # the inherited loop's periods / norms / status
+    layouts: list         # per window: {str(p): keep} in dictionary order (None where nothing was solved)
+    weights: np.ndarray   # (B, rmax)
+    n_weights: np.ndarray
+    res: np.ndarray       # (B, N)
+    status: np.ndarray    # (B,) status of the re-solve with the GCD-extracted dictionary
+    n: int = 0
+
+    def window(self, b: int):
+        out, res = self.base.window(b)
+        st = int(np.asarray(self.base.status if not isinstance(self.base.status, torch.Tensor)
+                            else self.base.status.cpu())[b])
+        if st == _lib.STATUS_ZERO_INPUT or self.layouts[b] is None:
+            return out, res
+        if st != _lib.STATUS_OK or int(self.status[b]) != _lib.STATUS_OK:
+            raise NotImplementedError("window %d: the inherited loop stopped on a singular / oversized system; the "
+                                      "GCD-extracted dictionary has no duplicate rows there and the reference "
+                                      "would carry on differently" % b)
+        lay = self.layouts[b]
+        out = dict(out)
+        out["basis_dictionary"] = dict(lay)
+        out["weights"] = np.array(self.weights[b, : int(self.n_weights[b])])
+        out["subspaces"] = build_subspaces([int(k) for k in lay], list(lay.values()), self.n)
+        return out, np.array(self.res[b])
+
+
+class QOPeriodsWithGCDsExtracted(QOPeriods):
+    """Drop-in for pyPeriod.QOPeriodsWithGCDsExtracted: the inherited residualisation loop with a dictionary that
+    also holds the common factors of every pair of found periods.  Both dictionaries span the same space, so the
+    loop (sweeps, residuals, stop test) is the device loop of QOPeriods; the layout is evaluated on the host
+    (CPython set order is part of the reference's output) and the weights are re-solved on the device."""
+
+    def __init__(self, basis_type="natural", trunc_to_integer_multiple=False, device=None):
+        super().__init__(basis_type, trunc_to_integer_multiple, device=device)
+
+    def get_subspaces(self, Q, N):
+        lay = gcds_extracted_layout(Q)
+        return build_subspaces([int(k) for k in lay], list(lay.values()), N), lay
+
+    def find_periods(self, data, num=None, thresh=None, min_length=2, max_length=None, update_weights=True,
+                     rmax=None, kmax=64, **kwargs):
+        arr = data if isinstance(data, torch.Tensor) else np.asarray(data, dtype=np.float64)
+        was_1d = arr.ndim == 1
+        batch = arr.reshape(1, -1) if was_1d else arr
+        base = QOPeriods.find_periods(self, batch, num, thresh, min_length, max_length, update_weights,
+                                      return_res=True, rmax=rmax, **kwargs)
+        g = (lambda t: t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t))
+        dq, nd, st = g(base.dict_q), g(base.n_dict), g(base.status)
+        bsz, n = dq.shape[0], base.n
+        lq = np.zeros((bsz, kmax), np.int32)
+        lr = np.zeros((bsz, kmax), np.int32)
+        ln = np.zeros((bsz,), np.int32)
+        layouts = []
+        for b in range(bsz):
+            if st[b] == _lib.STATUS_ZERO_INPUT or nd[b] == 0:
+                layouts.append(None)
+                continue
+            lay = gcds_extracted_layout(dq[b, : nd[b]])
+            if len(lay) > kmax:
+                raise ValueError(f"window {b}: {len(lay)} dictionary entries > kmax={kmax}")
+            layouts.append(lay)
+            ln[b] = len(lay)
+            lq[b, : len(lay)] = [int(k) for k in lay]
+            lr[b, : len(lay)] = list(lay.values())
+        lib = _lib.load()
+        w = stage_windows(batch, self._device)
+        dev = w.device
+        if rmax is None:
+            rmax = min(n, 1024)
+        pmax = int(max(int(lq.max()), 2))
+        ws = Workspace.get(dev, lib.pp_qo_workspace_bytes(n, pmax, kmax, rmax))
+        t_lq, t_lr, t_ln = (torch.from_numpy(a).to(dev) for a in (lq, lr, ln))
+        weights = torch.zeros((bsz, (rmax + 1) & ~1), dtype=torch.float64, device=dev)
+        res = torch.empty((bsz, n), dtype=torch.float64, device=dev)
+        n_weights = torch.zeros((bsz,), dtype=torch.int32, device=dev)
+        status = torch.zeros((bsz,), dtype=torch.int32, device=dev)
+        _lib.check(lib.pp_qo_solve_rows(ptr(w.tensor), w.ldx, bsz, n, kmax, ptr(t_lq), ptr(t_lr), ptr(t_ln), pmax,
+                                        int(rmax), ptr(n_weights), ptr(weights), ptr(res), ptr(status), ptr(ws),
+                                        ws.numel(), stream_ptr(dev)), "pp_qo_solve_rows")
+        out = QOGcdBatchResult(base, layouts, to_host(weights), to_host(n_weights), to_host(res), to_host(status), n=n)
+        if was_1d:
+            pair = out.window(0)
+            self._output = self._output_bases = pair[0]
+            return pair
+        return out

@@ -190,7 +190,27 @@ def gen_qo_ram():
     save("qo_ram_synth", **out)
 
 
+# ------------------------------------------------------------------ 7. QOPeriodsWithGCDsExtracted
+def gen_qo_gcd():
+    import importlib
+    gcd_cls = importlib.import_module(ref.__name__ + ".QOPeriodsWithGCDsExtracted").QOPeriodsWithGCDsExtracted
+    out = {}
+    cases = [(8800, 1500, dict(num=3, thresh=0.05, max_length=300)), (8801, 1500, dict(num=4, thresh=0.05, max_length=300)),
+             (8802, 1200, dict(num=4, thresh=0.02, max_length=200)), (50_000, 2048, dict(num=4, thresh=0.05))]
+    for i, (seed, n, kw) in enumerate(cases):
+        x = synth.synth(n, seed)
+        d, res = quiet(gcd_cls().find_periods, x, **kw)
+        out[f"c{i}_args"] = np.array([seed, n, kw["num"], kw.get("max_length", 0)])
+        out[f"c{i}_thresh"] = np.array(kw["thresh"])
+        out[f"c{i}_periods"], out[f"c{i}_norms"] = np.array(d["periods"]), np.array(d["norms"])
+        out[f"c{i}_weights"], out[f"c{i}_res"] = d["weights"], res
+        out[f"c{i}_dict_keys"] = np.array([int(k) for k in d["basis_dictionary"]])
+        out[f"c{i}_dict_vals"] = np.array([int(v) for v in d["basis_dictionary"].values()])
+        out[f"c{i}_subspaces_sha"] = np.array(sha(np.asarray(d["subspaces"], dtype=np.float64)))
+    save("qo_gcd", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["project", "readme", "mbest_stream", "s2l", "bcorr", "qo_ram"]
+    which = sys.argv[1:] or ["project", "readme", "mbest_stream", "s2l", "bcorr", "qo_ram", "qo_gcd"]
     for w in which:
         globals()["gen_" + w]()

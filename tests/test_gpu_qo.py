@@ -95,3 +95,29 @@ def test_unsupported_branches_raise(QO):
         QO().find_periods(x, num=1, thresh=0.1, update_weights=False)
     with pytest.raises(TypeError):
         QO().find_periods(x, num=2)
+
+
+def test_qo_gcds_extracted_vs_golden():
+    """QOPeriodsWithGCDsExtracted: device loop + host layout + device re-solve against the
+    reference's own outputs (tests/golden/qo_gcd.npz), 1-D and batched."""
+    from pyperiod_b200 import QOPeriodsWithGCDsExtracted as QG
+    g = load_golden("qo_gcd")
+    for i in range(4):
+        seed, n, num, max_length = (int(v) for v in g[f"c{i}_args"])
+        x = synth.synth(n, seed)
+        d, res = QG().find_periods(x, num=num, thresh=float(g[f"c{i}_thresh"]), max_length=max_length or None)
+        assert np.array_equal(np.asarray(d["periods"]), g[f"c{i}_periods"])
+        assert [int(k) for k in d["basis_dictionary"]] == g[f"c{i}_dict_keys"].tolist()
+        assert [int(v) for v in d["basis_dictionary"].values()] == g[f"c{i}_dict_vals"].tolist()
+        np.testing.assert_allclose(d["norms"], g[f"c{i}_norms"], rtol=1e-10)
+        np.testing.assert_allclose(d["weights"], g[f"c{i}_weights"], rtol=1e-8, atol=1e-11)
+        np.testing.assert_allclose(res, g[f"c{i}_res"], rtol=0, atol=1e-11)
+        assert d["subspaces"].shape == (len(d["weights"]), n)
+    # batch of two equal-length windows == the 1-D calls
+    xb = np.stack([synth.synth(1500, 8800), synth.synth(1500, 8801)])
+    out = QG().find_periods(xb, num=3, thresh=0.05, max_length=300)
+    for b in range(2):
+        d1, r1 = QG().find_periods(xb[b], num=3, thresh=0.05, max_length=300)
+        db, rb = out.window(b)
+        assert db["basis_dictionary"] == d1["basis_dictionary"]
+        assert np.array_equal(db["weights"], d1["weights"]) and np.array_equal(rb, r1)

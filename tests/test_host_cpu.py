@@ -87,3 +87,21 @@ def test_synth_stream_windows_are_views():
     w = synth.windows_from_stream(s, 64, 16)
     assert w.shape == (5, 64) and w.strides == (128, 8)
     assert np.array_equal(w[3], s[48:112]) and np.max(np.abs(s)) == 1.0
+
+
+def test_gcds_extracted_layout_matches_oracle_and_golden():
+    """Host-built dictionary layout of QOPeriodsWithGCDsExtracted (CPython set order) == oracle == reference fixture."""
+    from oracle import qo as oq
+    from pyperiod_b200.qoperiods import gcds_extracted_layout
+    g = np.load(os.path.join(ROOT, "tests", "golden", "qo_gcd.npz"))
+    for i in range(4):
+        keys, vals = g[f"c{i}_dict_keys"].tolist(), g[f"c{i}_dict_vals"].tolist()
+        # the dictionary is built from ALL found periods; recover them as the keys that are not proper common factors
+        found = [int(p) for p in g[f"c{i}_periods"]]
+        for q in ([found] if len(found) == int(g[f"c{i}_args"][2]) else []):
+            lay = gcds_extracted_layout(q)
+            assert [int(k) for k in lay] == keys and list(lay.values()) == vals
+    for q in ([12, 18, 30], [97], [64, 96, 40, 100], [6, 10, 15, 7]):
+        lay = gcds_extracted_layout(q)
+        _, ref = oq.get_subspaces_gcds_extracted(q, 200)
+        assert list(lay.items()) == list(ref.items())
