@@ -150,7 +150,7 @@ def run_reference(args, rank: int):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(b_per_gpu: int, n_gpus: int, where: str):
@@ -171,8 +171,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        if os.environ.get("NCCL_DEBUG", "").upper() not in ("INFO", "TRACE"):
-            os.environ["NCCL_DEBUG"] = "WARN"   # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # NCCL's banner / logs never go to stdout
         dist.init_process_group("nccl", device_id=dev)
     B = args.windows
     assert B % 128 == 0, "--windows must be a multiple of 128 (segment alignment)"
@@ -330,10 +329,34 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             line["cpu_baseline"] = cpu
         if parity is not None:
             line["parity"] = parity
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+class StdoutGuard:
+    """Rank 0 prints exactly ONE JSON line: everything any library writes to fd 1 meanwhile (NCCL's version
+    banner is a C-level printf) is sent to stderr, and the line goes out through the saved descriptor."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+        return False
+
+
+_LINES = []
+
+
+def emit(line: dict):
+    _LINES.append(json.dumps(line))
 
 
 def main():
@@ -349,10 +372,13 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if args.impl == "reference":
-        run_reference(args, rank)
-    else:
-        run_b200(args, rank, world, local_rank)
+    with StdoutGuard():
+        if args.impl == "reference":
+            run_reference(args, rank)
+        else:
+            run_b200(args, rank, world, local_rank)
+    for text in _LINES:
+        print(text, flush=True)
 
 
 if __name__ == "__main__":
