@@ -196,6 +196,7 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
       sp.rcp = sm.sweep->rcp;
       sp.tops = tops;
       sp.ntops = ntops;
+      sp.verify_keys = nullptr;
       sp.metric_out = metric_out ? metric_out + (size_t)b * (pmax + 1) : nullptr;
     }
     const SweepResult r = cta_sweep(sm.sweep);
@@ -332,6 +333,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.rcp = sm.sweep->rcp;
       sp.tops = tops;
       sp.ntops = ntops;
+      sp.verify_keys = nullptr;
     }
     __syncthreads();
 
@@ -625,6 +627,7 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
       sp.rcp = sm.sweep->rcp;
       sp.tops = nullptr;
       sp.ntops = 0;
+      sp.verify_keys = nullptr;
     }
     int count = 0;
     int pstart = 2;
@@ -669,9 +672,10 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, int max_length, double ratio,
              int trunc_i, int orth_i, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
-             double* __restrict__ bases_out, int32_t* __restrict__ status_out, int* __restrict__ next_window) {
+             double* __restrict__ bases_out, int32_t* __restrict__ status_out, int* __restrict__ next_window,
+             int hier, double* __restrict__ ws_keys, const uint2* __restrict__ tops, int ntops) {
   unsigned char* smem_raw = pp_smem;
-  const SmemPlan pl = make_plan(N, max_length, 0, true);
+  const SmemPlan pl = make_plan(N, max_length, 0, true, hier != 0);
   Smem sm(smem_raw, pl);
   const bool trunc = trunc_i != 0, orth = orth_i != 0;
   const double sqrtN = sqrt((double)N);
@@ -682,7 +686,8 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
   for (WindowQueue wq(next_window); wq.b < B; wq.next()) {
     const int b = wq.b;
     loader.load(sm.xs, x + (size_t)b * ldx, N);
-    const double og = sqrt(cta_sum_sq(sm.xs, N, sm.red)) / sqrtN;
+    double e_now = cta_sum_sq(sm.xs, N, sm.red);   // sum x^2 of the current residual
+    const double og = sqrt(e_now) / sqrtN;
     double prev = og;
     int status = PP_STATUS_OK;
     if (threadIdx.x == 0) {
@@ -704,11 +709,13 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.skip = nullptr;
       sp.nskip = 0;
       sp.metric_out = nullptr;
-      sp.hier_scr = nullptr;
-      sp.hier_len = 0;
+      // hierarchical MAXABS ranking + exact verification of the near-maximal candidates (pp_sweep.cuh)
+      sp.hier_scr = hier ? sm.hier : nullptr;
+      sp.hier_len = pl.hier_len;
       sp.rcp = sm.sweep->rcp;
-      sp.tops = nullptr;
-      sp.ntops = 0;
+      sp.tops = tops;
+      sp.ntops = ntops;
+      sp.verify_keys = hier ? ws_keys + (size_t)blockIdx.x * (max_length + 1) : nullptr;
     }
     for (int i = 0; i < num; ++i) {
       uint32_t out_p = 0u;
@@ -716,6 +723,7 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       bool keep = false;
       int p_sel = 0;
       if (status == PP_STATUS_OK) {
+        if (threadIdx.x == 0) sm.sweep->params.e_res = e_now;  // error bound of the hierarchical sums
         const SweepResult top = cta_sweep(sm.sweep);
         if (top.p == 0) {
           status = PP_STATUS_NO_PERIOD;
@@ -726,7 +734,8 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
                                    sm.vwin, sm.utmp);
           cta_subtract_tiled(sm.xs, N, sm.vwin, top.p);  // always (:340)
           __syncthreads();
-          const double now = sqrt(cta_sum_sq(sm.xs, N, sm.red)) / sqrtN;
+          e_now = cta_sum_sq(sm.xs, N, sm.red);
+          const double now = sqrt(e_now) / sqrtN;
           const double drop = (prev - now) / og;
           if (drop > ratio) {
             keep = true;
@@ -766,7 +775,7 @@ static bool hier_applies(int metric, int trunc, int orth) {
 }
 
 static int plan_for(int algo, int N, int pmax, int num, SmemPlan& pl) {
-  pl = make_plan(N, pmax, algo == PP_ALGO_MBEST ? num : 0, true, g_fold_mode != PP_FOLD_DIRECT && (algo == PP_ALGO_MBEST || algo == PP_ALGO_SWEEP));
+  pl = make_plan(N, pmax, algo == PP_ALGO_MBEST ? num : 0, true, g_fold_mode != PP_FOLD_DIRECT && (algo == PP_ALGO_MBEST || algo == PP_ALGO_SWEEP || algo == PP_ALGO_BCORR));
   return 0;
 }
 
@@ -827,6 +836,7 @@ size_t pp_workspace_bytes(int32_t algo, int32_t N, int32_t pmax, int32_t num, in
   size_t bytes = 1024 + 1024 + (size_t)(pmax + 2) * sizeof(uint2);
   if (algo == PP_ALGO_MBEST) bytes += grid * (size_t)num * pl.pv * 8;
   if (orth && algo != PP_ALGO_BCORR) bytes += grid * kWarps * 2 * (size_t)pl.pv * 8;
+  if (algo == PP_ALGO_BCORR) bytes += grid * (size_t)(pmax + 2) * 8;  // hierarchical keys awaiting verification
   return bytes;
 }
 
@@ -997,14 +1007,28 @@ int pp_best_correlation(const double* x, int64_t ldx, int32_t B, int32_t N, int3
   if (B == 0) return 0;
   DeviceFacts f;
   if (int rc = device_facts(f)) return rc;
-  const SmemPlan pl = make_plan(N, max_length, 0, true);
-  if (int rc = prep_kernel(bcorr_kernel, pl.bytes(), f)) return rc;
-  const int grid = grid_for(f, pl.bytes(), B);
-  Tables tb{chain_off, chain_q, nullptr, nullptr};
+  // hierarchical ranking needs room for the per-CTA key arrays and the job table; without it: sequential folds
   size_t off = 0;
   int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
+  int hier = g_fold_mode != PP_FOLD_DIRECT && max_length - 1 >= 4 ? 1 : 0;
+  const size_t grid_max = (size_t)f.sm_count * kCtasPerSm;
+  double* keys = nullptr;
+  uint2* tops = nullptr;
+  int ntops = 0;
+  if (hier) {
+    keys = carve(workspace, workspace_bytes, off, grid_max * (size_t)(max_length + 1) * 8);
+    ntops = hier_top_count(2, max_length - 1);
+    tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)(ntops > 0 ? ntops : 1) * sizeof(uint2)));
+    if (!keys || !tops || ntops <= 0) hier = 0;
+  }
+  const SmemPlan pl = make_plan(N, max_length, 0, true, hier != 0);
+  if (int rc = prep_kernel(bcorr_kernel, pl.bytes(), f)) return rc;
+  const int grid = grid_for(f, pl.bytes(), B);
+  if (hier) ntops = build_hier_jobs(N, 2, max_length - 1, tops, (cudaStream_t)stream);
+  Tables tb{chain_off, chain_q, nullptr, nullptr};
   bcorr_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, max_length, ratio, trunc, orth,
-                                                                     tb, periods, powers, bases, status, next_window);
+                                                                     tb, periods, powers, bases, status, next_window,
+                                                                     hier, keys, tops, ntops);
   return check_cuda(cudaGetLastError(), "bcorr_kernel launch");
 }
 

@@ -559,6 +559,7 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
       sp.rcp = sweep->rcp;
       sp.tops = tops;
       sp.ntops = ntops;
+      sp.verify_keys = nullptr;
     }
     __syncthreads();
     int nfound = 0;

@@ -57,6 +57,7 @@ struct SweepParams {
   const double* rcp;     // shared table rcp[m] = 1.0 / m for m < kRcpTab (energy weights without a division)
   const uint2* tops;     // global: descriptors of the hierarchical tops in hand-out order (tops_kernel)
   int ntops;
+  double* verify_keys;   // global [pmax+1], nullable: lets MAXABS sweeps rank hierarchically (needs e_res = sum x^2)
 };
 
 struct SweepResult {
@@ -129,10 +130,45 @@ __device__ __forceinline__ void consider_lane(const RankCtx& rc, double key, int
 // Warp totals of K per-lane values with a transposed butterfly: K/2 + ... exchanges instead of 5 K.
 // On return lane l holds the total of value l >> (5 - log2 K).  (Shuffles share the shared-memory data
 // pipe the fold is bound by, so they are worth saving.)
-template <int K>
+template <int K, bool MAXOP = false>
 __device__ __forceinline__ double warp_sum_multi(const double (&v)[K]) {
   static_assert(K == 1 || K == 2 || K == 4 || K == 8, "K must be 1, 2, 4 or 8");
   const int lane = threadIdx.x & 31;
+  if constexpr (MAXOP) {  // same butterflies with max instead of + (MAXABS sweeps)
+    auto comb = [](double a, double b) { return fmax(a, b); };
+    if constexpr (K == 1) {
+      return warp_max(v[0]);
+    } else if constexpr (K == 2) {
+      const bool hi = (lane & 16) != 0;
+      double keep = comb(hi ? v[1] : v[0], __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[1], 16));
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) keep = comb(keep, __shfl_xor_sync(0xffffffffu, keep, o));
+      return keep;
+    } else if constexpr (K == 4) {
+      const bool hi = (lane & 16) != 0;
+      double k0 = comb(hi ? v[2] : v[0], __shfl_xor_sync(0xffffffffu, hi ? v[0] : v[2], 16));
+      double k1 = comb(hi ? v[3] : v[1], __shfl_xor_sync(0xffffffffu, hi ? v[1] : v[3], 16));
+      const bool hi8 = (lane & 8) != 0;
+      double keep = comb(hi8 ? k1 : k0, __shfl_xor_sync(0xffffffffu, hi8 ? k0 : k1, 8));
+#pragma unroll
+      for (int o = 4; o > 0; o >>= 1) keep = comb(keep, __shfl_xor_sync(0xffffffffu, keep, o));
+      return keep;
+    } else {
+      const bool hi = (lane & 16) != 0;
+      double k4[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        k4[i] = comb(hi ? v[4 + i] : v[i], __shfl_xor_sync(0xffffffffu, hi ? v[i] : v[4 + i], 16));
+      const bool hi8 = (lane & 8) != 0;
+      double k0 = comb(hi8 ? k4[2] : k4[0], __shfl_xor_sync(0xffffffffu, hi8 ? k4[0] : k4[2], 8));
+      double k1 = comb(hi8 ? k4[3] : k4[1], __shfl_xor_sync(0xffffffffu, hi8 ? k4[1] : k4[3], 8));
+      const bool hi4 = (lane & 4) != 0;
+      double keep = comb(hi4 ? k1 : k0, __shfl_xor_sync(0xffffffffu, hi4 ? k0 : k1, 4));
+#pragma unroll
+      for (int o = 2; o > 0; o >>= 1) keep = comb(keep, __shfl_xor_sync(0xffffffffu, keep, o));
+      return keep;
+    }
+  }
   if constexpr (K == 1) {
     return warp_sum(v[0]);
   } else if constexpr (K == 2) {
@@ -392,18 +428,26 @@ __host__ __device__ inline int hier_scratch_len(int pmax) { return ((((pmax >> 3
 
 // energy terms of one level held in `sets` accumulator sets v[0 .. sets): T += sum of squares, A += the part
 // whose residues hold one more term (warp-uniform top sets, and set 0 under the tail row)
-template <int SETS, int DIM0, int J>
+// MAXABS: T = max |sum| instead (best-correlation metric; counts play no role and A is unused).
+template <int SETS, int DIM0, int J, bool MAXABS>
 __device__ __forceinline__ void level_energy(const double (&v)[DIM0][J], int extra, const bool (&tail)[J], double& T,
                                              double& A) {
+  if constexpr (MAXABS) {
 #pragma unroll
-  for (int s = 0; s < SETS; ++s) {
-    const double q = sum_sq<J>(v[s]);
-    T += q;
-    if (s >= SETS - extra) A += q;  // warp-uniform
+    for (int s = 0; s < SETS; ++s)
+#pragma unroll
+      for (int j = 0; j < J; ++j) T = fmax(T, fabs(v[s][j]));
+  } else {
+#pragma unroll
+    for (int s = 0; s < SETS; ++s) {
+      const double q = sum_sq<J>(v[s]);
+      T += q;
+      if (s >= SETS - extra) A += q;  // warp-uniform
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+      if (tail[j]) A = fma(v[0][j], v[0][j], A);
   }
-#pragma unroll
-  for (int j = 0; j < J; ++j)
-    if (tail[j]) A = fma(v[0][j], v[0][j], A);
 }
 
 // v[s] += v[s + SETS/2]: the sets of the level with half as many sets
@@ -416,28 +460,28 @@ __device__ __forceinline__ void level_halve(double (&v)[DIM0][J]) {
 }
 
 // levels 2^LV .. 1 of a power-of-two set array (compile-time recursion keeps every index static)
-template <int DIM0, int J, int LV, int NL>
+template <int DIM0, int J, int LV, int NL, bool MAXABS>
 struct pow2_levels {
   static __device__ __forceinline__ void run(double (&v)[DIM0][J], int M0, const bool (&tail)[J], double (&T)[NL],
                                              double (&A)[NL]) {
     constexpr int sets = 1 << LV;
-    level_energy<sets, DIM0, J>(v, M0 & (sets - 1), tail, T[LV], A[LV]);
+    level_energy<sets, DIM0, J, MAXABS>(v, M0 & (sets - 1), tail, T[LV], A[LV]);
     if constexpr (LV > 0) {
       level_halve<sets, DIM0, J>(v);
-      pow2_levels<DIM0, J, LV - 1, NL>::run(v, M0, tail, T, A);
+      pow2_levels<DIM0, J, LV - 1, NL, MAXABS>::run(v, M0, tail, T, A);
     }
   }
 };
 // levels 3 * 2^LV .. 3 of a rider chain
-template <int DIM0, int J, int LV, int NL>
+template <int DIM0, int J, int LV, int NL, bool MAXABS>
 struct rider_levels {
   static __device__ __forceinline__ void run(double (&v)[DIM0][J], int M0, const bool (&tail)[J], double (&T)[NL],
                                              double (&A)[NL]) {
     constexpr int sets = 3 << LV;
-    level_energy<sets, DIM0, J>(v, M0 % sets, tail, T[LV], A[LV]);
+    level_energy<sets, DIM0, J, MAXABS>(v, M0 % sets, tail, T[LV], A[LV]);
     if constexpr (LV > 0) {
       level_halve<sets, DIM0, J>(v);
-      rider_levels<DIM0, J, LV - 1, NL>::run(v, M0, tail, T, A);
+      rider_levels<DIM0, J, LV - 1, NL, MAXABS>::run(v, M0, tail, T, A);
     }
   }
 };
@@ -502,7 +546,7 @@ __device__ __forceinline__ void hier_accumulate(const double* __restrict__ xs, i
 }
 
 // One register tile of a plain top q = g * 2^L.
-template <int L, int J, bool MASK>
+template <int L, int J, bool MASK, bool MAXABS>
 __device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, int ra, int M0, int rr,
                                           double (&T)[L + 1], double (&A)[L + 1], double* scr) {
   constexpr int S = 1 << L;
@@ -510,7 +554,7 @@ __device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, 
   double acc[S][J];
   bool tail[J];
   hier_accumulate<S, J, MASK>(xs, g, ra, M0, rr, M0 & (S - 1), M0 >> L, acc, tail);
-  pow2_levels<S, J, L, L + 1>::run(acc, M0, tail, T, A);
+  pow2_levels<S, J, L, L + 1, MAXABS>::run(acc, M0, tail, T, A);
   if (scr != nullptr) {
 #pragma unroll
     for (int j = 0; j < J; ++j)
@@ -520,7 +564,7 @@ __device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, 
 
 // One register tile of a host + rider job: S = 3 * 2^LH sets.  Th/Ah: host levels 2^LH .. 1, Tr/Ar: rider
 // levels 3 * 2^(LH-1) .. 3.
-template <int LH, int J, bool MASK>
+template <int LH, int J, bool MASK, bool MAXABS>
 __device__ __forceinline__ void rider_tile(const double* __restrict__ xs, int g, int ra, int M0, int rr, int head,
                                            int groups, double (&Th)[LH + 1], double (&Ah)[LH + 1], double (&Tr)[LH],
                                            double (&Ar)[LH]) {
@@ -534,10 +578,10 @@ __device__ __forceinline__ void rider_tile(const double* __restrict__ xs, int g,
     for (int t = 0; t < SH; ++t)
 #pragma unroll
       for (int j = 0; j < J; ++j) hv[t][j] = (acc[t][j] + acc[t + SH][j]) + acc[t + 2 * SH][j];
-    pow2_levels<SH, J, LH, LH + 1>::run(hv, M0, tail, Th, Ah);
+    pow2_levels<SH, J, LH, LH + 1, MAXABS>::run(hv, M0, tail, Th, Ah);
   }
   level_halve<S, S, J>(acc);  // level 3 * 2^(LH-1)
-  rider_levels<S, J, LH - 1, LH>::run(acc, M0, tail, Tr, Ar);
+  rider_levels<S, J, LH - 1, LH, MAXABS>::run(acc, M0, tail, Tr, Ar);
 }
 
 // register columns per accumulator set of a hierarchical tile: 8 accumulators per lane (8 / 4 / 2 / 1 columns
@@ -553,7 +597,7 @@ struct hier_cols {
 };
 
 // One top period q = g * 2^L and every candidate q / 2^k below it.  Non-trunc, non-orth, NORM / GAMMA.
-template <int L>
+template <int L, bool MAXABS>
 __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int rr, double* scr, WarpRank& wr) {
   // M0 = floor(N / g) complete base rows; base residues below rr = N - M0 g have one more (tail) row
   constexpr int J = hier_cols<L>::value;
@@ -566,21 +610,23 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
 #pragma unroll
   for (int i = 0; i <= L; ++i) T[i] = A[i] = 0.0;
   int ra = 0;
-  for (; ra + 32 * J <= g; ra += 32 * J) hier_tile<L, J, false>(xs, g, ra, M0, rr, T, A, out);
-#ifndef PP_NO_J2_TILES
+  for (; ra + 32 * J <= g; ra += 32 * J) hier_tile<L, J, false, MAXABS>(xs, g, ra, M0, rr, T, A, out);
   if constexpr (J > 2)
-    for (; ra + 64 <= g; ra += 64) hier_tile<L, 2, false>(xs, g, ra, M0, rr, T, A, out);
-#endif
-  for (; ra < g; ra += 32) hier_tile<L, 1, true>(xs, g, ra, M0, rr, T, A, out);
+    for (; ra + 64 <= g; ra += 64) hier_tile<L, 2, false, MAXABS>(xs, g, ra, M0, rr, T, A, out);
+  for (; ra < g; ra += 32) hier_tile<L, 1, true, MAXABS>(xs, g, ra, M0, rr, T, A, out);
   // per-lane partial energies of the L + 1 levels, reduced together
   constexpr int KP = L == 0 ? 1 : (L == 1 ? 2 : 4);
   double e[KP];
 #pragma unroll
   for (int i = 0; i < KP; ++i) {
     if (i <= L) {
-      const int M = M0 >> i;
-      const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
-      e[i] = fma(w_diff, A[i], w_lo * T[i]);
+      if constexpr (MAXABS) {
+        e[i] = T[i];
+      } else {
+        const int M = M0 >> i;
+        const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+        e[i] = fma(w_diff, A[i], w_lo * T[i]);
+      }
     } else {
       e[i] = 0.0;
     }
@@ -591,12 +637,12 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
       wr.pend_p = g;
     } else {
       const double pair[2] = {wr.pend, e[0]};
-      const double key = warp_sum_multi<2>(pair);
+      const double key = warp_sum_multi<2, MAXABS>(pair);
       consider_lane(rc, key, (lane & 16) ? g : wr.pend_p, (lane & 15) == 0, wr.best);
       wr.pend_p = 0;
     }
   } else {
-    const double key = warp_sum_multi<KP>(e);
+    const double key = warp_sum_multi<KP, MAXABS>(e);
     constexpr int shift = KP == 2 ? 4 : 3;
     const int k = lane >> shift;
     consider_lane(rc, key, k <= L ? (g << k) : 0, (lane & ((1 << shift) - 1)) == 0, wr.best);
@@ -615,11 +661,16 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
       for (int r = lane; r < h2; r += 32) {
         const double v = src[r] + src[r + h2];
         dst[r] = v;
-        t = fma(v, v, t);
-        if (r < r0h) a = fma(v, v, a);
+        if constexpr (MAXABS) {
+          t = fmax(t, fabs(v));
+        } else {
+          t = fma(v, v, t);
+          if (r < r0h) a = fma(v, v, a);
+        }
       }
       __syncwarp();
-      consider(rc, warp_sum(fma(w_diff, a, w_lo * t)), h2, best);
+      if constexpr (MAXABS) consider(rc, warp_max(t), h2, best);
+      else consider(rc, warp_sum(fma(w_diff, a, w_lo * t)), h2, best);
       double* swp = src;
       src = dst;
       dst = swp;
@@ -631,7 +682,7 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
 
 // A host top q = g 2^LH (g odd) together with its rider; candidates g 2^i (i <= LH) and 3 g 2^i (i < LH) that
 // lie in [pmin, pmax].
-template <int LH>
+template <int LH, bool MAXABS>
 __device__ __forceinline__ void warp_hier_rider_L(RankCtx rc, int g, int M0, int rr, WarpRank& wr) {
   constexpr int S = 3 << LH;
 #ifndef PP_RIDER_J1
@@ -647,10 +698,11 @@ __device__ __forceinline__ void warp_hier_rider_L(RankCtx rc, int g, int M0, int
 #pragma unroll
   for (int i = 0; i < LH; ++i) Tr[i] = Ar[i] = 0.0;
   int ra = 0;
-  for (; ra + 32 * J <= g; ra += 32 * J) rider_tile<LH, J, false>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+  for (; ra + 32 * J <= g; ra += 32 * J)
+    rider_tile<LH, J, false, MAXABS>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
   if constexpr (J > 2)
-    for (; ra + 64 <= g; ra += 64) rider_tile<LH, 2, false>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
-  for (; ra < g; ra += 32) rider_tile<LH, 1, true>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+    for (; ra + 64 <= g; ra += 64) rider_tile<LH, 2, false, MAXABS>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+  for (; ra < g; ra += 32) rider_tile<LH, 1, true, MAXABS>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
   // values 0 .. LH: host levels g 2^i; values LH+1 .. 2 LH: rider levels 3 g 2^i
   constexpr int NV = 2 * LH + 1;          // 3 or 5
   constexpr int KP = NV <= 4 ? 4 : 8;
@@ -659,17 +711,25 @@ __device__ __forceinline__ void warp_hier_rider_L(RankCtx rc, int g, int M0, int
   for (int i = 0; i < KP; ++i) e[i] = 0.0;
 #pragma unroll
   for (int i = 0; i <= LH; ++i) {
-    const int M = M0 >> i;
-    const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
-    e[i] = fma(w_diff, Ah[i], w_lo * Th[i]);
+    if constexpr (MAXABS) {
+      e[i] = Th[i];
+    } else {
+      const int M = M0 >> i;
+      const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+      e[i] = fma(w_diff, Ah[i], w_lo * Th[i]);
+    }
   }
 #pragma unroll
   for (int i = 0; i < LH; ++i) {
-    const int M = M0 / (3 << i);
-    const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
-    e[LH + 1 + i] = fma(w_diff, Ar[i], w_lo * Tr[i]);
+    if constexpr (MAXABS) {
+      e[LH + 1 + i] = Tr[i];
+    } else {
+      const int M = M0 / (3 << i);
+      const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+      e[LH + 1 + i] = fma(w_diff, Ar[i], w_lo * Tr[i]);
+    }
   }
-  const double key = warp_sum_multi<KP>(e);
+  const double key = warp_sum_multi<KP, MAXABS>(e);
   constexpr int shift = KP == 4 ? 3 : 2;
   const int k = lane >> shift;
   int p = 0;
@@ -780,30 +840,35 @@ inline int build_hier_jobs(int N, int pmin, int pmax, uint2* tops, cudaStream_t 
   return hier_job_count(pmin, pmax, riders);
 }
 
+template <bool MAXABS>
 __device__ __forceinline__ void warp_hier_top(const RankCtx& rc, uint2 e, double* scr, WarpRank& wr) {
   const int g = e.x & 0xffff, L = (e.x >> 16) & 0xf, M0 = e.y & 0xffff, rr = e.y >> 16;
 #ifndef PP_NO_RIDERS
   if (e.x >> 20) {
-    if (L == 1) warp_hier_rider_L<1>(rc, g, M0, rr, wr);
-    else warp_hier_rider_L<2>(rc, g, M0, rr, wr);
+    if (L == 1) warp_hier_rider_L<1, MAXABS>(rc, g, M0, rr, wr);
+    else warp_hier_rider_L<2, MAXABS>(rc, g, M0, rr, wr);
     return;
   }
 #endif
   switch (L) {
-    case 0: warp_hier_top_L<0>(rc, g, M0, rr, scr, wr); break;
-    case 1: warp_hier_top_L<1>(rc, g, M0, rr, scr, wr); break;
-    case 2: warp_hier_top_L<2>(rc, g, M0, rr, scr, wr); break;
-    default: warp_hier_top_L<3>(rc, g, M0, rr, scr, wr); break;
+    case 0: warp_hier_top_L<0, MAXABS>(rc, g, M0, rr, scr, wr); break;
+    case 1: warp_hier_top_L<1, MAXABS>(rc, g, M0, rr, scr, wr); break;
+    case 2: warp_hier_top_L<2, MAXABS>(rc, g, M0, rr, scr, wr); break;
+    default: warp_hier_top_L<3, MAXABS>(rc, g, M0, rr, scr, wr); break;
   }
 }
 
 // ------------------------------------------------------------------------------------------
 // CTA-level sweep
 // ------------------------------------------------------------------------------------------
+constexpr int kMaxVerify = 32;  // candidates re-evaluated exactly after a hierarchical MAXABS sweep
+
 struct SweepShared {
   double rcp[kRcpTab];  // rcp[m] = 1 / m (rcp[0] unused); filled once per CTA by sweep_shared_init
   SweepParams params;
   int counter;  // next candidate index
+  int ncand;    // hierarchical MAXABS: candidates to verify
+  int cand[kMaxVerify];
   int hit_p;    // first-hit mode: lowest period over threshold so far
   double wkey[kWarps];
   int wp[kWarps];
@@ -835,22 +900,30 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   const double thresh = sp->thresh;
   const bool first_hit = thresh >= 0.0;
   Best best{0.0, 0};
+  // MAXABS (best-correlation) may rank hierarchically only when the caller provides `verify_keys`: the metric
+  // must be the reference's bit-exact sequential sum, so the hierarchical pass only NOMINATES candidates and
+  // the near-maximal ones are re-evaluated exactly below.
+  const bool hier_maxabs = metric == PP_METRIC_MAXABS && sp->verify_keys != nullptr;
   const bool hier = sp->hier_scr != nullptr && sp->tops != nullptr && !first_hit && !sp->orth && !sp->trunc &&
-                    (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
+                    (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA || hier_maxabs);
   if (hier) {
     // tops: candidates p with 2p > pmax; everything else is derived from exactly one of them
     const uint2* __restrict__ tops = sp->tops;
     const int total = sp->ntops;
     double* scr = sp->hier_scr + (size_t)wid * sp->hier_len;
+    RankCtx hrc = rc;
+    if (hier_maxabs) hrc.metric_out = sp->verify_keys;  // every candidate's hierarchical key, for the verification
     WarpRank wr{best, 0.0, 0};
     while (true) {
       int idx = 0;
       if (lane == 0) idx = atomicAdd(&sh->counter, 1);
       idx = __shfl_sync(0xffffffffu, idx, 0);
       if (idx >= total) break;
-      warp_hier_top(rc, __ldg(tops + idx), scr, wr);
+      if (hier_maxabs) warp_hier_top<true>(hrc, __ldg(tops + idx), scr, wr);
+      else warp_hier_top<false>(hrc, __ldg(tops + idx), scr, wr);
     }
-    if (wr.pend_p != 0) consider(rc, warp_sum(wr.pend), wr.pend_p, wr.best);  // odd top left without a partner
+    if (wr.pend_p != 0)  // odd top left without a partner
+      consider(hrc, hier_maxabs ? warp_max(wr.pend) : warp_sum(wr.pend), wr.pend_p, wr.best);
     best = warp_best(metric, wr.best);
   } else {
     const int ncand = pmax - pmin + 1;
@@ -894,6 +967,47 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
       if (res.p == 0 || q < res.p) res = Best{k, q};
     } else if (better(metric, k, q, res)) {
       res = Best{k, q};
+    }
+  }
+  if (hier && hier_maxabs && res.p != 0) {
+    // Exact verification.  A hierarchical sum differs from the sequential one by at most
+    // err = 2 N eps sum|x| <= 2 N eps sqrt(N e_res); a candidate whose hierarchical key lies more than 2 err below
+    // the hierarchical maximum cannot reach the exact maximum.  The others (normally just one) are folded
+    // sequentially and ranked with the reference's rule (strict '>', lowest p on ties).
+    const double err = 2.0 * (double)rc.N * 1.2e-16 * sqrt((double)rc.N * sp->e_res);
+    const double floor_key = res.key - 2.0 * err - 1e-13 * res.key;
+    const double* keys = sp->verify_keys;
+    if (threadIdx.x == 0) sh->ncand = 0;
+    __syncthreads();  // also: every key written during the sweep is visible
+    for (int p = pmin + threadIdx.x; p <= pmax; p += kThreads) {
+      if (keys[p] >= floor_key) {
+        const int slot = atomicAdd(&sh->ncand, 1);
+        if (slot < kMaxVerify) sh->cand[slot] = p;
+      }
+    }
+    __syncthreads();
+    const int nc = sh->ncand;
+    Best exact{0.0, 0};
+    if (nc <= kMaxVerify) {
+      for (int c = wid; c < nc; c += kWarps) {
+        const int p = sh->cand[c];
+        consider(rc, warp_period_key<kPassMaxAbs>(sp, p), p, exact);
+      }
+    } else {  // degenerate input (masses of near-ties): fold every candidate sequentially
+      for (int p = pmin + wid; p <= pmax; p += kWarps) consider(rc, warp_period_key<kPassMaxAbs>(sp, p), p, exact);
+    }
+    __syncthreads();  // wkey / wp were read by everyone above
+    if (lane == 0) {
+      sh->wkey[wid] = exact.key;
+      sh->wp[wid] = exact.p;
+    }
+    __syncthreads();
+    res = Best{0.0, 0};
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) {
+      const double k = sh->wkey[w];
+      const int q = sh->wp[w];
+      if (q != 0 && better(metric, k, q, res)) res = Best{k, q};
     }
   }
   SweepResult out{0.0, res.p};

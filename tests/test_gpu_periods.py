@@ -407,3 +407,35 @@ def test_mbest_pipelined_host_upload_matches_device_resident():
         assert np.array_equal(g.periods, ref.periods.cpu().numpy().view(np.uint32))
         assert np.array_equal(g.powers, ref.powers.cpu().numpy())
         assert np.array_equal(g.status, ref.status.cpu().numpy())
+
+
+def test_best_correlation_hierarchical_nomination_is_exact(P):
+    """best_correlation ranks hierarchically and re-evaluates the near-maximal candidates with sequential folds
+    (pp_sweep.cuh); the result must be bit-identical to the all-sequential sweep, also on inputs full of exact ties."""
+    from pyperiod_b200 import _lib
+    n = 2048
+    rows = [synth.synth(n, 70_000 + i) for i in range(40)]
+    t = np.arange(n)
+    rows.append(np.sin(2 * np.pi * t / 10.0))                       # clean period 10: ties at 10, 20, 30, ...
+    rows.append((t % 64 == 0).astype(np.float64))                   # impulse train: |S| equal for many periods
+    rows.append(np.ones(n))                                          # constant
+    rows.append(np.where(t < 300, synth.synth(n, 5)[:n], 0.0))       # mostly zero padding
+    rows.append(synth.synth(n, 6) * 1e-200)                          # tiny scale
+    rows.append(np.sign(np.sin(2 * np.pi * t / 37.0)))               # square wave, integer-valued sums
+    xb = np.stack(rows)
+    out = {}
+    try:
+        for mode in (_lib.FOLD_DIRECT, _lib.FOLD_HIERARCHICAL):
+            _lib.set_fold_mode(mode)
+            for trunc, orth in ((False, False), (True, True)):
+                with warnings.catch_warnings():
+                    warnings.simplefilter("ignore")
+                    out[mode, trunc] = P(trunc, orth).best_correlation(xb, num=6, return_bases=True)
+    finally:
+        _lib.set_fold_mode(_lib.FOLD_HIERARCHICAL)
+    for trunc in (False, True):
+        a, b = out[_lib.FOLD_DIRECT, trunc], out[_lib.FOLD_HIERARCHICAL, trunc]
+        assert np.array_equal(a.periods, b.periods)
+        assert np.array_equal(a.powers, b.powers)
+        assert np.array_equal(a.status, b.status)
+        assert np.array_equal(a.bases, b.bases, equal_nan=True)

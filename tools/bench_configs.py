@@ -104,7 +104,9 @@ def main():
           "seconds": t, "windows_per_s": B / t,
           "roofline": {"bound": "smem", "achieved": B * canon / t / 1e9, "peak": smem_peak / 1e9, "unit": "GB/s",
                        "frac": B * canon / t / smem_peak,
-                       "algorithmic": "10 rounds x 2728 periods x 8192 sequential adds x 8 B (exact MAXABS folds)"},
+                       "algorithmic": "10 rounds x 2728 periods x 8192 sequential adds x 8 B (canonical); executed: hierarchical "
+                                      "nomination (%d passes per round) + exact sequential folds of the near-maximal "
+                                      "candidates" % _lib.sweep_passes(2, 2729)},
           "cpu_baseline": cpu(_cpu_bcorr, base, 40, "oracle best_correlation(num=10, trunc, orth)")})
 
     # config 5a: QOPeriods.find_periods(num=4, thresh=0.05), N=4096 (65,536 windows in the config; a slice here)
