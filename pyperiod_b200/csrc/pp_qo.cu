@@ -38,8 +38,11 @@ struct QoPlan {
   __host__ __device__ size_t off_bar() const { return off_red() + 2 * kWarps * 8; }
   __host__ __device__ size_t off_sweep() const { return off_bar() + 16; }
   __host__ __device__ size_t off_ints() const { return off_sweep() + ((sizeof(SweepShared) + 15) & ~15); }
-  // ints: found[num] dict_q[num] dict_keep[num] dict_rows[num] dict_off[num+1] seen[seen_words] misc[16]
-  __host__ __device__ size_t bytes() const { return off_ints() + (size_t)(5 * num + 1 + seen_words + 16) * 4 + 16; }
+  // ints: found[num] dict_q[num] dict_keep[num] dict_rows[num] dict_off[num+1] prev_rows[num] seen[seen_words] misc[16]
+  __host__ __device__ size_t bytes() const { return off_ints() + (size_t)(6 * num + 1 + seen_words + 16) * 4 + 16; }
+  // leading dimension of the per-CTA Gram matrix: fixed for the whole window so that the factor of one round can
+  // be extended in the next; not a power of two (column walks would hit one L2 set)
+  __host__ __device__ int ldg() const { return rmax + 8; }
 };
 
 __host__ __device__ inline QoPlan make_qo_plan(int N, int pmax, int num, int rmax, bool hier) {
@@ -64,8 +67,10 @@ struct CholSmem {
   double* Li;   // [32][33] inverse of the factored block
 };
 
+// row0 (a multiple of 32): rows below it already hold the factor of the leading row0 x row0 block (previous round);
+// only the rows from row0 on are factored, with exactly the operations the full factorisation would apply to them.
 __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __restrict__ Pt, const CholSmem& cs,
-                             int* flag) {
+                             int* flag, int row0 = 0) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) *flag = 0;
   for (int kb = 0; kb < R; kb += kCholNb) {
@@ -78,12 +83,14 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
       cs.D[r * (kCholNb + 1) + c] = v;
     }
     __syncthreads();
+    const bool old_block = kb + nb <= row0;  // already factored: only its inverse is needed
     if (wid == 0) {
       // lane owns row `lane` of the block in registers; column k is broadcast through cs.rD each step
       double r[kCholNb];
 #pragma unroll
       for (int c = 0; c < kCholNb; ++c) r[c] = cs.D[lane * (kCholNb + 1) + c];
       bool ok = true;
+      if (!old_block) {  // warp-uniform
 #pragma unroll
       for (int k = 0; k < kCholNb; ++k) {
         const double dkk = __shfl_sync(0xffffffffu, r[k], k);
@@ -96,6 +103,7 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
 #pragma unroll
         for (int j = k + 1; j < kCholNb; ++j) r[j] = fma(-l, cs.rD[j], r[j]);   // only j <= lane is ever used
         __syncwarp();
+      }
       }
       if (!ok && lane == 0) *flag = 1;
 #pragma unroll
@@ -118,9 +126,11 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
     __syncthreads();
     if (*flag) return false;
     // write the factored diagonal block back
-    for (int idx = tid; idx < nb * nb; idx += kThreads) {
-      const int r = idx / nb, c = idx - r * nb;
-      if (c <= r) A[(size_t)(kb + r) * ld + kb + c] = cs.D[r * (kCholNb + 1) + c];
+    if (!old_block) {
+      for (int idx = tid; idx < nb * nb; idx += kThreads) {
+        const int r = idx / nb, c = idx - r * nb;
+        if (c <= r) A[(size_t)(kb + r) * ld + kb + c] = cs.D[r * (kCholNb + 1) + c];
+      }
     }
     const int below = R - kb - nb;
     if (below <= 0) {
@@ -133,6 +143,11 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
       double* a = A + (size_t)i * ld + kb;
 #pragma unroll
       for (int c = 0; c < kCholNb; ++c) row[c] = (c < nb) ? a[c] : 0.0;
+      if (i < row0) {  // finished row of the previous factor: only its transposed copy is needed
+#pragma unroll
+        for (int c = 0; c < kCholNb; ++c) Pt[(size_t)c * ld + i] = row[c];
+        continue;
+      }
       double outv[kCholNb];
 #pragma unroll
       for (int c = 0; c < kCholNb; ++c) {
@@ -165,6 +180,7 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
         while ((it + 1) * (it + 2) / 2 <= pr) ++it;
         const int jt = pr - it * (it + 1) / 2;
         const int ti = base + it * kCholTile, tj = base + jt * kCholTile;
+        if (ti + kCholTile <= row0) continue;  // rows of the previous factor (tiles are 32-aligned, as row0 is)
         const int i0 = ti + ty * 4, j0 = tj + tx * 8;
         double acc[4][8];
 #pragma unroll
@@ -289,9 +305,11 @@ struct QoCtx {
   int* dict_keep;       // value stored in the reference's basis_dictionary (0 for a repeated period)
   int* dict_rows;       // rows actually present in A (keep, or q when keep == 0: `if keep:` QOPeriods.py:972)
   int* dict_off;        // row offsets, [ndict+1]
+  int* prev_rows;       // dict_rows of the round whose Cholesky factor is still in G (incremental factorisation)
+  int ldg;              // leading dimension of G and Pt
   uint32_t* seen;       // bitmap of divisors already counted
   int seen_words;
-  int* misc;            // [0]=ndict [1]=R [2]=flag
+  int* misc;            // [0]=ndict [1]=R [2]=flag [3]=layout scratch [8]=entries and [9]=rows of the factor held in G
   double* G;            // global, rmax*rmax
   double* Pt;           // global, 32*rmax
   CholSmem cs;
@@ -360,7 +378,19 @@ __device__ int cta_qo_solve(const QoCtx& c, int nfound, double* e_recon, bool ex
     *e_recon = 0.0;
     return PP_STATUS_OK;
   }
-  const int ld = (R + 1) & ~1;
+  const int ld = c.ldg;
+  // The dictionary only grows from round to round (unless a repeated period rewrites an entry), so the factor of
+  // the previous round is the leading block of this round's: rebuild and factor only the rows from the last
+  // 32-aligned boundary on (the partial block below it is rebuilt from its integer counts).
+  if (tid == 0) {
+    const int nd_prev = c.misc[8], r_prev = c.misc[9];
+    bool grow = r_prev > 0 && ndict >= nd_prev;
+    for (int k = 0; grow && k < nd_prev; ++k) grow = c.dict_rows[k] == c.prev_rows[k];
+    c.misc[10] = grow ? (r_prev / kCholNb) * kCholNb : 0;
+    c.misc[9] = 0;  // no valid factor until this round's succeeds
+  }
+  __syncthreads();
+  const int row_lo = c.misc[10];
   // W = A x: fold sums of the original data, one thread per kept row, terms in increasing n
   for (int k = 0; k < ndict; ++k) {
     const int q = c.dict_q[k], rows = c.dict_rows[k], off = c.dict_off[k];
@@ -371,17 +401,21 @@ __device__ int cta_qo_solve(const QoCtx& c, int nfound, double* e_recon, bool ex
     }
   }
   // G = A A^T, lower triangle: zero, diagonal counts, then co-occurrence counts of residue pairs
-  for (size_t idx = tid; idx < (size_t)R * ld; idx += kThreads) c.G[idx] = 0.0;
+  for (int r = row_lo; r < R; ++r)
+    for (int j = tid; j <= r; j += kThreads) c.G[(size_t)r * ld + j] = 0.0;
   __syncthreads();
   for (int a = 0; a < ndict; ++a) {
     const int qa = c.dict_q[a], ra = c.dict_rows[a], oa = c.dict_off[a];
-    for (int i = tid; i < ra; i += kThreads) c.G[(size_t)(oa + i) * ld + oa + i] = (double)((N - 1 - i) / qa + 1);
+    if (oa + ra <= row_lo) continue;  // rows of the factor that is kept
+    for (int i = tid; i < ra; i += kThreads)
+      if (oa + i >= row_lo) c.G[(size_t)(oa + i) * ld + oa + i] = (double)((N - 1 - i) / qa + 1);
     for (int b = 0; b < a; ++b) {
       const int qb = c.dict_q[b], rb = c.dict_rows[b], ob = c.dict_off[b];
       int i = tid % qa, j = tid % qb;
       const int si = kThreads % qa, sj = kThreads % qb;
       for (int n = tid; n < N; n += kThreads) {
-        if (i < ra && j < rb) atomicAdd(&c.G[(size_t)(oa + i) * ld + ob + j], 1.0);  // integer-valued: order-free
+        if (i < ra && j < rb && oa + i >= row_lo)
+          atomicAdd(&c.G[(size_t)(oa + i) * ld + ob + j], 1.0);  // integer-valued: order-free
         i += si; if (i >= qa) i -= qa;
         j += sj; if (j >= qb) j -= qb;
       }
@@ -389,7 +423,12 @@ __device__ int cta_qo_solve(const QoCtx& c, int nfound, double* e_recon, bool ex
   }
   __syncthreads();
   { const long long now = clock64(); c.t[1] += now - tm; tm = now; }
-  if (!cta_cholesky(c.G, R, ld, c.Pt, c.cs, &c.misc[2])) return PP_STATUS_SINGULAR;
+  if (!cta_cholesky(c.G, R, ld, c.Pt, c.cs, &c.misc[2], row_lo)) return PP_STATUS_SINGULAR;
+  if (tid == 0) {  // G now holds the factor of this dictionary
+    c.misc[8] = ndict;
+    c.misc[9] = R;
+    for (int k = 0; k < ndict; ++k) c.prev_rows[k] = c.dict_rows[k];
+  }
   { const long long now = clock64(); c.t[2] += now - tm; tm = now; }
   cta_chol_solve(c.G, R, ld, c.wv, c.cs);
   // reconstruction A^T w and residual
@@ -468,9 +507,11 @@ __device__ __forceinline__ QoCtx make_ctx(unsigned char* smem, const QoPlan& pl,
   c.dict_keep = ints + 2 * num;
   c.dict_rows = ints + 3 * num;
   c.dict_off = ints + 4 * num;
-  c.seen = reinterpret_cast<uint32_t*>(ints + 5 * num + 1);
+  c.prev_rows = ints + 5 * num + 1;
+  c.ldg = pl.ldg();
+  c.seen = reinterpret_cast<uint32_t*>(ints + 6 * num + 1);
   c.seen_words = pl.seen_words;
-  c.misc = ints + 5 * num + 1 + pl.seen_words;
+  c.misc = ints + 6 * num + 1 + pl.seen_words;
   c.G = G;
   c.Pt = Pt;
   c.t = nullptr;
@@ -487,8 +528,8 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
                unsigned long long* __restrict__ prof, int* __restrict__ next_window) {
   unsigned char* smem = pp_smem;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0);
-  const size_t ldg = (size_t)pl.rmax;
-  QoCtx c = make_ctx(smem, pl, N, num, phi, ws_G + (size_t)blockIdx.x * ldg * ldg,
+  const size_t ldg = (size_t)pl.ldg();
+  QoCtx c = make_ctx(smem, pl, N, num, phi, ws_G + (size_t)blockIdx.x * pl.rmax * ldg,
                      ws_Pt + (size_t)blockIdx.x * kCholNb * ldg);
   SweepShared* sweep = reinterpret_cast<SweepShared*>(smem + pl.off_sweep());
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + pl.off_bar());
@@ -524,6 +565,8 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
     if (tid == 0) {
       c.misc[0] = 0;
       c.misc[1] = 0;
+      c.misc[8] = 0;  // no Cholesky factor of this window in G yet
+      c.misc[9] = 0;
     }
     __syncthreads();
     qo_commit(c, out, b, 0, round_norms);
@@ -622,8 +665,8 @@ qo_solve_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int kma
                 double* __restrict__ ws_G, double* __restrict__ ws_Pt, int* __restrict__ next_window) {
   unsigned char* smem = pp_smem;
   const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
-  const size_t ldg = (size_t)pl.rmax;
-  QoCtx c = make_ctx(smem, pl, N, kmax, phi, ws_G + (size_t)blockIdx.x * ldg * ldg,
+  const size_t ldg = (size_t)pl.ldg();
+  QoCtx c = make_ctx(smem, pl, N, kmax, phi, ws_G + (size_t)blockIdx.x * pl.rmax * ldg,
                      ws_Pt + (size_t)blockIdx.x * kCholNb * ldg);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + pl.off_bar());
   double* x0 = const_cast<double*>(c.x0);
@@ -637,6 +680,7 @@ qo_solve_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int kma
     loader.load(x0, x + (size_t)b * ldx, N);
     const int nfound = min(nper[b], kmax);
     for (int i = tid; i < nfound; i += kThreads) c.found[i] = periods[(size_t)b * kmax + i];
+    if (tid == 0) c.misc[8] = c.misc[9] = 0;  // one solve per window: nothing to extend
     __syncthreads();
     double e_recon = 0.0;
     const int rc = cta_qo_solve(c, nfound, &e_recon);
@@ -675,8 +719,8 @@ qo_solve_rows_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, in
                      int* __restrict__ next_window) {
   unsigned char* smem = pp_smem;
   const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
-  const size_t ldg = (size_t)pl.rmax;
-  QoCtx c = make_ctx(smem, pl, N, kmax, nullptr, ws_G + (size_t)blockIdx.x * ldg * ldg,
+  const size_t ldg = (size_t)pl.ldg();
+  QoCtx c = make_ctx(smem, pl, N, kmax, nullptr, ws_G + (size_t)blockIdx.x * pl.rmax * ldg,
                      ws_Pt + (size_t)blockIdx.x * kCholNb * ldg);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + pl.off_bar());
   double* x0 = const_cast<double*>(c.x0);
@@ -704,6 +748,7 @@ qo_solve_rows_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, in
       c.dict_off[nd] = off;
       c.misc[0] = nd;
       c.misc[1] = off;
+      c.misc[8] = c.misc[9] = 0;  // one solve per window: nothing to extend
     }
     __syncthreads();
     double e_recon = 0.0;
@@ -733,7 +778,7 @@ size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax)
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, true);
   const size_t grid = (size_t)f.sm_count * 2;
   return 8192 + (size_t)(pmax + 2) * sizeof(uint2) +
-         grid * ((size_t)pl.rmax * pl.rmax + (size_t)kCholNb * pl.rmax + (size_t)num + 64) * 8;
+         grid * ((size_t)pl.rmax * pl.ldg() + (size_t)kCholNb * pl.ldg() + (size_t)num + 64) * 8;
 }
 
 static int qo_check(const void* x, int64_t ldx, int B, int N, int num, int pmax, int rmax, const void* phi,
@@ -764,8 +809,8 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   if (int rc = prep_kernel(qo_find_kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B, 2);
   size_t off = 0;
-  double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.rmax * 8);
-  double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.rmax * 8);
+  double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.ldg() * 8);
+  double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.ldg() * 8);
   double* nr = carve(workspace, workspace_bytes, off, (size_t)grid * num * 8);
   if (!G || !Pt || !nr) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
   uint2* tops = nullptr;
@@ -799,8 +844,8 @@ int pp_qo_solve(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t kmax
   if (int rc = prep_kernel(qo_solve_kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B, 2);
   size_t off = 0;
-  double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.rmax * 8);
-  double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.rmax * 8);
+  double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.ldg() * 8);
+  double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.ldg() * 8);
   if (!G || !Pt) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
   QoOut o{nullptr, nullptr, nullptr, dict_q, dict_keep, n_dict, n_weights, weights, res, status};
   int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
@@ -825,8 +870,8 @@ int pp_qo_solve_rows(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t
   if (int rc = prep_kernel(qo_solve_rows_kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B, 2);
   size_t off = 0;
-  double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.rmax * 8);
-  double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.rmax * 8);
+  double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.ldg() * 8);
+  double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.ldg() * 8);
   if (!G || !Pt) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
   int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
   qo_solve_rows_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, kmax, dict_q, dict_rows, n_dict,
