@@ -70,9 +70,10 @@ struct CholSmem {
 // row0 (a multiple of 32): rows below it already hold the factor of the leading row0 x row0 block (previous round);
 // only the rows from row0 on are factored, with exactly the operations the full factorisation would apply to them.
 __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __restrict__ Pt, const CholSmem& cs,
-                             int* flag, int row0 = 0) {
+                             int* flag, int row0 = 0, long long* tphase = nullptr) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   if (tid == 0) *flag = 0;
+  long long tq = clock64();
   for (int kb = 0; kb < R; kb += kCholNb) {
     const int nb = min(kCholNb, R - kb);
     // (1) diagonal block -> shared memory, padded with the identity to 32 x 32
@@ -148,23 +149,22 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
         for (int c = 0; c < kCholNb; ++c) Pt[(size_t)c * ld + i] = row[c];
         continue;
       }
-      double outv[kCholNb];
+      // out[c] = sum_{m <= c} row[m] Li[c][m] depends on the loaded row only: store as we go (no second array)
 #pragma unroll
       for (int c = 0; c < kCholNb; ++c) {
-        double v = 0.0;
+        double v0 = 0.0, v1 = 0.0;
 #pragma unroll
-        for (int m = 0; m <= c; ++m) v = fma(row[m], cs.Li[c * (kCholNb + 1) + m], v);
-        outv[c] = v;
-      }
-#pragma unroll
-      for (int c = 0; c < kCholNb; ++c) row[c] = outv[c];
-#pragma unroll
-      for (int c = 0; c < kCholNb; ++c) {
-        if (c < nb) a[c] = row[c];
-        Pt[(size_t)c * ld + i] = row[c];  // transposed copy: coalesced tile loads below
+        for (int m = 0; m <= c; m += 2) {
+          v0 = fma(row[m], cs.Li[c * (kCholNb + 1) + m], v0);
+          if (m + 1 <= c) v1 = fma(row[m + 1], cs.Li[c * (kCholNb + 1) + m + 1], v1);
+        }
+        const double v = v0 + v1;
+        if (c < nb) a[c] = v;
+        Pt[(size_t)c * ld + i] = v;  // transposed copy: coalesced tile loads below
       }
     }
     __syncthreads();
+    if (tphase) { const long long now = clock64(); tphase[0] += now - tq; tq = now; }
     // (3) trailing update  A[i][j] -= sum_k P[i][k] P[j][k]  (j <= i).  Each warp owns 32 x 32 output
     // tiles (round-robin over the lower-triangular tile pairs) and streams the transposed panel Pt
     // straight from L1/L2 into registers: no shared-memory staging, no CTA barrier inside the update.
@@ -188,7 +188,7 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
 #pragma unroll
           for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
         const bool full = (ti + kCholTile <= R) && (tj + kCholTile <= R);
-#pragma unroll 4
+#pragma unroll 2
         for (int k = 0; k < kCholNb; ++k) {
           const double* pk = Pt + (size_t)k * ld;
           double av[4], bv[8];
@@ -227,6 +227,7 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
       }
     }
     __syncthreads();
+    if (tphase) { const long long now = clock64(); tphase[1] += now - tq; tq = now; }
   }
   return true;
 }
@@ -423,7 +424,7 @@ __device__ int cta_qo_solve(const QoCtx& c, int nfound, double* e_recon, bool ex
   }
   __syncthreads();
   { const long long now = clock64(); c.t[1] += now - tm; tm = now; }
-  if (!cta_cholesky(c.G, R, ld, c.Pt, c.cs, &c.misc[2], row_lo)) return PP_STATUS_SINGULAR;
+  if (!cta_cholesky(c.G, R, ld, c.Pt, c.cs, &c.misc[2], row_lo, c.t + 4)) return PP_STATUS_SINGULAR;
   if (tid == 0) {  // G now holds the factor of this dictionary
     c.misc[8] = ndict;
     c.misc[9] = R;
@@ -537,7 +538,7 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
   double* x0 = const_cast<double*>(c.x0);
   const double sqrtN = sqrt((double)N);
   const int tid = threadIdx.x;
-  long long timers[4] = {0, 0, 0, 0}, t_sweep = 0;
+  long long timers[6] = {0, 0, 0, 0, 0, 0}, t_sweep = 0;
   c.t = timers;
 
   WindowLoader loader;
@@ -652,6 +653,8 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
     atomicAdd(prof + 2, (unsigned long long)timers[1]);
     atomicAdd(prof + 3, (unsigned long long)timers[2]);
     atomicAdd(prof + 5, (unsigned long long)timers[3]);
+    atomicAdd(prof + 6, (unsigned long long)timers[4]);
+    atomicAdd(prof + 7, (unsigned long long)timers[5]);
     atomicAdd(prof + 4, (unsigned long long)((B - blockIdx.x + gridDim.x - 1) / gridDim.x));
   }
 }
@@ -671,7 +674,7 @@ qo_solve_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int kma
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + pl.off_bar());
   double* x0 = const_cast<double*>(c.x0);
   const int tid = threadIdx.x;
-  long long timers[4] = {0, 0, 0, 0};
+  long long timers[6] = {0, 0, 0, 0, 0, 0};
   c.t = timers;
   WindowLoader loader;
   loader.init(bar);
@@ -725,7 +728,7 @@ qo_solve_rows_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, in
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + pl.off_bar());
   double* x0 = const_cast<double*>(c.x0);
   const int tid = threadIdx.x;
-  long long timers[4] = {0, 0, 0, 0};
+  long long timers[6] = {0, 0, 0, 0, 0, 0};
   c.t = timers;
   WindowLoader loader;
   loader.init(bar);

@@ -15,4 +15,4 @@ e0.record(); r = q.find_periods(x, num=4, thresh=0.05, return_res=False); e1.rec
 ms = e0.elapsed_time(e1)
 p = prof.cpu().numpy().astype(float)
 print(f"B={B} {ms:.1f} ms {B/ms*1e3:.0f} win/s rows={float(r.n_weights.float().mean()):.0f} status!=0: {int((r.status!=0).sum())}")
-print("cycles/window: sweep %.0f layout %.0f build %.0f cholesky %.0f solve+recon %.0f" % (p[0]/p[4], p[1]/p[4], p[2]/p[4], p[3]/p[4], p[5]/p[4]))
+print("cycles/window: sweep %.0f layout %.0f build %.0f cholesky %.0f (diag+panel %.0f, trailing %.0f) solve+recon %.0f" % (p[0]/p[4], p[1]/p[4], p[2]/p[4], p[3]/p[4], p[6]/p[4], p[7]/p[4], p[5]/p[4]))
