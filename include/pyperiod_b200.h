@@ -68,11 +68,15 @@ const char *pp_last_error(void);
  *       (3 * 2^L accumulator sets at base g), which saves about a fifth of the passes.
  *   PP_FOLD_DIRECT: every candidate period is folded sequentially from the window.
  *   PP_FOLD_HIERARCHICAL_NO_RIDERS: hierarchical, one pass per top (for comparisons).
+ *   PP_FOLD_NOMINATE_F32: M-best ranks with the hierarchical sweep in float (half the shared-memory
+ *       traffic), then folds every candidate whose error bound reaches the best one sequentially in fp64:
+ *       the selected periods and norms are those of the exact fold.
  * Outputs that must be bit-exact (project(), the bases, MAXABS metrics) never use the
  * hierarchical sums.  Process-wide setting. */
 #define PP_FOLD_HIERARCHICAL 0
 #define PP_FOLD_DIRECT 1
 #define PP_FOLD_HIERARCHICAL_NO_RIDERS 2
+#define PP_FOLD_NOMINATE_F32 3
 int pp_set_fold_mode(int32_t mode);
 int pp_get_fold_mode(void);
 /* Passes over the window one ranking sweep of [pmin, pmax] executes under the current fold mode

@@ -92,7 +92,7 @@ def check(rc: int, what: str):
         raise PPError(f"{what} failed ({rc}): {msg}")
 
 
-FOLD_HIERARCHICAL, FOLD_DIRECT, FOLD_HIERARCHICAL_NO_RIDERS = 0, 1, 2
+FOLD_HIERARCHICAL, FOLD_DIRECT, FOLD_HIERARCHICAL_NO_RIDERS, FOLD_NOMINATE_F32 = 0, 1, 2, 3
 
 
 def set_fold_mode(mode: int):

@@ -39,6 +39,7 @@ struct SmemPlan {
   int num;      // slots (M-best) / rounds
   int skip_words;
   int hier_len; // doubles per warp of hierarchical-sweep scratch (0 = none)
+  int xf_len;   // floats per fp32 copy of the window (0 = none; two copies, see SweepParams::xf0)
   __host__ __device__ size_t off_vwin() const { return (size_t)xs_len * 8; }
   __host__ __device__ size_t off_utmp() const { return off_vwin() + (size_t)pv * 8; }
   // the hierarchical-sweep scratch is only live inside a sweep, vwin/utmp only between sweeps: they share bytes
@@ -57,12 +58,17 @@ struct SmemPlan {
   __host__ __device__ size_t off_slot() const { return off_periods() + (size_t)num * 4; }
   __host__ __device__ size_t off_skip() const { return off_slot() + (size_t)num * 4; }
   __host__ __device__ size_t off_misc() const { return off_skip() + (size_t)skip_words * 4; }
-  __host__ __device__ size_t bytes() const { return off_misc() + 64; }
+  __host__ __device__ size_t off_xf() const { return (off_misc() + 64 + 15) & ~(size_t)15; }
+  __host__ __device__ size_t bytes() const { return off_xf() + 2 * (size_t)xf_len * 4; }
 };
 
-__host__ __device__ inline SmemPlan make_plan(int N, int pmax, int num, bool sweep_pad, bool hier = false) {
+constexpr int kF32Pad = 320;  // floats after the window in the fp32 copies: masked 64-wide tiles read past N
+
+__host__ __device__ inline SmemPlan make_plan(int N, int pmax, int num, bool sweep_pad, bool hier = false,
+                                              bool f32 = false) {
   SmemPlan pl;
   pl.hier_len = hier ? hier_scratch_len(pmax) : 0;
+  pl.xf_len = (hier && f32) ? ((N + kF32Pad + 3) & ~3) : 0;
   pl.xs_len = sweep_pad ? ((N + kSweepPad + 1) & ~1) : ((N + 1) & ~1);
   pl.pv = (pmax + 2) & ~1;
   pl.num = num;
@@ -85,6 +91,8 @@ struct Smem {
   int* slot;
   uint32_t* skip;
   int* misc;
+  float* xf0;
+  float* xf1;
   __device__ Smem(unsigned char* base, const SmemPlan& pl) {
     xs = reinterpret_cast<double*>(base);
     vwin = reinterpret_cast<double*>(base + pl.off_vwin());
@@ -100,8 +108,19 @@ struct Smem {
     slot = reinterpret_cast<int*>(base + pl.off_slot());
     skip = reinterpret_cast<uint32_t*>(base + pl.off_skip());
     misc = reinterpret_cast<int*>(base + pl.off_misc());
+    xf0 = pl.xf_len ? reinterpret_cast<float*>(base + pl.off_xf()) : nullptr;
+    xf1 = pl.xf_len ? xf0 + pl.xf_len : nullptr;
   }
 };
+
+// fp32 copies of the (residual) window: xf0[n] = x[n], xf1[n] = x[n + 1]; zero past N.  No barrier inside.
+__device__ __forceinline__ void refresh_f32_copies(const double* xs, int N, float* xf0, float* xf1) {
+  for (int n = threadIdx.x; n < N; n += kThreads) {
+    const float v = (float)xs[n];
+    xf0[n] = v;
+    if (n > 0) xf1[n - 1] = v;
+  }
+}
 
 __device__ __forceinline__ void zero_pad(double* xs, int from, int to) {
   for (int i = from + threadIdx.x; i < to; i += kThreads) xs[i] = 0.0;
@@ -197,6 +216,8 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
       sp.tops = tops;
       sp.ntops = ntops;
       sp.verify_keys = nullptr;
+      sp.xf0_off = 0;
+      sp.xf1_off = 0;
       sp.metric_out = metric_out ? metric_out + (size_t)b * (pmax + 1) : nullptr;
     }
     const SweepResult r = cta_sweep(sm.sweep);
@@ -270,9 +291,9 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
              int trunc_i, int orth_i, int hier, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
              double* __restrict__ bases_out, int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
              double* __restrict__ ws_slots, double* __restrict__ ws_scr, const uint2* __restrict__ tops, int ntops,
-             int* __restrict__ next_window, unsigned long long* __restrict__ prof) {
+             int* __restrict__ next_window, unsigned long long* __restrict__ prof, int f32, double* __restrict__ ws_keys) {
   unsigned char* smem_raw = pp_smem;
-  const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0);
+  const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0, f32 != 0);
   Smem sm(smem_raw, pl);
   const bool trunc = trunc_i != 0, orth = orth_i != 0;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -286,6 +307,12 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
   loader.init(sm.bar);
   zero_pad(sm.xs, N, pl.xs_len);
   sweep_shared_init(sm.sweep);
+  if (sm.xf0 != nullptr) {  // zero tails of the fp32 copies (xf1[N-1] = x[N] = 0 included)
+    for (int n = N - 1 + threadIdx.x; n < pl.xf_len; n += kThreads) {
+      if (n >= N) sm.xf0[n] = 0.f;
+      sm.xf1[n] = 0.f;
+    }
+  }
 
   // windows are handed out dynamically (global counter, zeroed per launch): per-window cost varies with the
   // number of sweeps and step-2 work, and a static stride leaves a tail of idle CTAs at the end of a launch
@@ -296,6 +323,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     loader.load(sm.xs, x + (size_t)b * ldx, N);
     const double e_data = cta_sum_sq(sm.xs, N, sm.red);
     const double data_norm = sqrt(e_data) / sqrtN;  // periodic_norm(data), Periods.py:600
+    if (sm.xf0 != nullptr) refresh_f32_copies(sm.xs, N, sm.xf0, sm.xf1);  // published by the barrier below
     if (threadIdx.x == 0) {
       misc[0] = 0;
       misc[1] = 0;
@@ -322,7 +350,9 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.warp_scr = my_scr;
       sp.pv = pl.pv;
       sp.sqrtN = sqrtN;
-      sp.e_res = 0.0;
+      // fp32 nomination: the residual of an orthogonal projection never has more energy than the data, so the
+      // data's energy bounds the float error of every sweep of this window
+      sp.e_res = e_data;
       sp.data_norm = 1.0;
       sp.thresh = -1.0;
       sp.skip = sm.skip;
@@ -333,7 +363,9 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.rcp = sm.sweep->rcp;
       sp.tops = tops;
       sp.ntops = ntops;
-      sp.verify_keys = nullptr;
+      sp.verify_keys = sm.xf0 != nullptr ? ws_keys + (size_t)blockIdx.x * (pmax + 2) : nullptr;
+      sp.xf0_off = sm.xf0 != nullptr ? (int)pl.off_xf() : 0;
+      sp.xf1_off = sm.xf0 != nullptr ? (int)(pl.off_xf() + (size_t)pl.xf_len * 4) : 0;
     }
     __syncthreads();
 
@@ -398,6 +430,10 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
         }
       }
       cta_subtract_tiled(sm.xs, N, sm.vwin, top.p);  // always (:537)
+      if (sm.xf0 != nullptr) {
+        __syncthreads();
+        refresh_f32_copies(sm.xs, N, sm.xf0, sm.xf1);
+      }
       __syncthreads();
       { const long long t = clock64(); t_upd += t - t_mark; t_mark = t; }
     }
@@ -552,8 +588,14 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       atomicAdd(prof + 3, (unsigned long long)t_step2);
       atomicAdd(prof + 4, 1ull);
       atomicAdd(prof + 5, (unsigned long long)t_fac);
-      atomicAdd(prof + 6, (unsigned long long)t_dec);
-      atomicAdd(prof + 7, (unsigned long long)t_blk);
+      if (sm.xf0 != nullptr) {  // fp32 nomination statistics instead of the step-2 detail
+        atomicAdd(prof + 6, sm.sweep->stat_nominated);
+        atomicAdd(prof + 7, sm.sweep->stat_fallback);
+        sm.sweep->stat_nominated = sm.sweep->stat_fallback = 0ull;
+      } else {
+        atomicAdd(prof + 6, (unsigned long long)t_dec);
+        atomicAdd(prof + 7, (unsigned long long)t_blk);
+      }
     }
     const int status = misc[4];
     for (int i = threadIdx.x; i < num; i += kThreads) {
@@ -628,6 +670,8 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
       sp.tops = nullptr;
       sp.ntops = 0;
       sp.verify_keys = nullptr;
+      sp.xf0_off = 0;
+      sp.xf1_off = 0;
     }
     int count = 0;
     int pstart = 2;
@@ -716,6 +760,8 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.tops = tops;
       sp.ntops = ntops;
       sp.verify_keys = hier ? ws_keys + (size_t)blockIdx.x * (max_length + 1) : nullptr;
+      sp.xf0_off = 0;
+      sp.xf1_off = 0;
     }
     for (int i = 0; i < num; ++i) {
       uint32_t out_p = 0u;
@@ -788,7 +834,8 @@ extern "C" {
 int pp_abi_version(void) { return PP_ABI_VERSION; }
 
 int pp_set_fold_mode(int32_t mode) {
-  if (mode != PP_FOLD_HIERARCHICAL && mode != PP_FOLD_DIRECT && mode != PP_FOLD_HIERARCHICAL_NO_RIDERS)
+  if (mode != PP_FOLD_HIERARCHICAL && mode != PP_FOLD_DIRECT && mode != PP_FOLD_HIERARCHICAL_NO_RIDERS &&
+      mode != PP_FOLD_NOMINATE_F32)
     return fail(-1, "unknown fold mode%s");
   g_fold_mode = mode;
   return 0;
@@ -797,7 +844,7 @@ int pp_get_fold_mode(void) { return g_fold_mode; }
 int pp_sweep_passes(int32_t pmin, int32_t pmax) {
   if (pmax < pmin) return 0;
   if (g_fold_mode == PP_FOLD_DIRECT) return pmax - pmin + 1;
-  return hier_job_count(pmin, pmax, g_fold_mode == PP_FOLD_HIERARCHICAL);
+  return hier_job_count(pmin, pmax, g_fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS);
 }
 int pp_set_profile_buffer(void* dev_u64x8) {
   g_prof = reinterpret_cast<unsigned long long*>(dev_u64x8);
@@ -834,7 +881,7 @@ size_t pp_workspace_bytes(int32_t algo, int32_t N, int32_t pmax, int32_t num, in
   plan_for(algo, N, pmax, num, pl);
   const size_t grid = (size_t)f.sm_count * kCtasPerSm;  // upper bound on the persistent grid
   size_t bytes = 1024 + 1024 + (size_t)(pmax + 2) * sizeof(uint2);
-  if (algo == PP_ALGO_MBEST) bytes += grid * (size_t)num * pl.pv * 8;
+  if (algo == PP_ALGO_MBEST) bytes += grid * ((size_t)num * pl.pv + (size_t)(pmax + 2)) * 8;
   if (orth && algo != PP_ALGO_BCORR) bytes += grid * kWarps * 2 * (size_t)pl.pv * 8;
   if (algo == PP_ALGO_BCORR) bytes += grid * (size_t)(pmax + 2) * 8;  // hierarchical keys awaiting verification
   return bytes;
@@ -939,10 +986,13 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   DeviceFacts f;
   if (int rc = device_facts(f)) return rc;
   const int hier = hier_applies(gamma ? PP_METRIC_GAMMA : PP_METRIC_NORM, trunc, orth) ? 1 : 0;
-  const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0);
+  const int f32 = (hier && g_fold_mode == PP_FOLD_NOMINATE_F32) ? 1 : 0;
+  const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0, f32 != 0);
   if (int rc = prep_kernel(mbest_kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B);
   size_t off = 0;
+  double* keys = f32 ? carve(workspace, workspace_bytes, off, (size_t)grid * (pmax + 2) * 8) : nullptr;
+  if (f32 && !keys) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
   double* slots = carve(workspace, workspace_bytes, off, (size_t)grid * num * pl.pv * 8);
   double* scr = orth ? carve(workspace, workspace_bytes, off, (size_t)grid * kWarps * 2 * pl.pv * 8) : nullptr;
   if (!slots || (orth && !scr)) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
@@ -959,7 +1009,7 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   Tables tb{chain_off, chain_q, fac_off, fac};
   mbest_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,
                                                                      hier, tb, periods, powers, bases, sweeps, status,
-                                                                     slots, scr, tops, ntops, next_window, g_prof);
+                                                                     slots, scr, tops, ntops, next_window, g_prof, f32, keys);
   return check_cuda(cudaGetLastError(), "mbest_kernel launch");
 }
 

@@ -604,6 +604,8 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
       sp.tops = tops;
       sp.ntops = ntops;
       sp.verify_keys = nullptr;
+      sp.xf0_off = 0;
+      sp.xf1_off = 0;
     }
     __syncthreads();
     int nfound = 0;

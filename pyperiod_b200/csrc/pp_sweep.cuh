@@ -58,6 +58,12 @@ struct SweepParams {
   const uint2* tops;     // global: descriptors of the hierarchical tops in hand-out order (tops_kernel)
   int ntops;
   double* verify_keys;   // global [pmax+1], nullable: lets MAXABS sweeps rank hierarchically (needs e_res = sum x^2)
+  // fp32 nomination (NORM / GAMMA ranking sweeps): two float copies of the window in shared memory, xf1[n] = x[n+1],
+  // so that a pair of consecutive samples can always be read with one aligned 8-byte load.  Needs verify_keys
+  // and e_res >= sum x^2.  offset 0 => fp64 hierarchical sweep.
+  // (byte offsets into the kernel's dynamic shared memory, so that the loads stay LDS; 0 = none)
+  int xf0_off;
+  int xf1_off;
 };
 
 struct SweepResult {
@@ -740,6 +746,373 @@ __device__ __forceinline__ void warp_hier_rider_L(RankCtx rc, int g, int M0, int
 }
 
 // ------------------------------------------------------------------------------------------
+// fp32 nomination sweep
+// ------------------------------------------------------------------------------------------
+// The same jobs (tops, chains, riders) evaluated in float: a lane owns the residue PAIR ra + 2 lane + 64 j + {0, 1},
+// one aligned LDS.64 feeds two FADDs, so a pass costs half the shared-memory wavefronts and half the
+// instructions of the fp64 pass.  The float energies only NOMINATE: cta_sweep re-evaluates every candidate whose
+// upper bound reaches the best lower bound with the sequential fp64 fold, so the selected period and its norm are
+// those of the exact fold (pp_sweep.cuh: cta_sweep).
+struct F32Window {
+  int off0;  // byte offset in pp_smem of x0[n] = (float) x[n]
+  int off1;  // byte offset in pp_smem of x1[n] = (float) x[n + 1]
+  // aligned pointer to the pairs (e + 2 lane, e + 2 lane + 1), e = element index of the pair owned by lane 0
+  __device__ __forceinline__ const float2* row(int e) const {
+    const int byte = (e & 1) ? off1 + 4 * (e - 1) : off0 + 4 * e;
+    return reinterpret_cast<const float2*>(pp_smem + byte) + (threadIdx.x & 31);
+  }
+};
+
+template <int J>
+__device__ __forceinline__ void add_row_f32(float2 (&acc)[J], const float2* __restrict__ row) {
+  float2 t[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) t[j] = row[32 * j];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    acc[j].x += t[j].x;
+    acc[j].y += t[j].y;
+  }
+}
+
+template <int J>
+__device__ __forceinline__ float sum_sq_f32(const float2 (&v)[J]) {
+  float lo = v[0].x * v[0].x, hi = v[0].y * v[0].y;
+#pragma unroll
+  for (int j = 1; j < J; ++j) {
+    lo = fmaf(v[j].x, v[j].x, lo);
+    hi = fmaf(v[j].y, v[j].y, hi);
+  }
+  return lo + hi;
+}
+
+template <int SETS, int DIM0, int J>
+__device__ __forceinline__ void level_energy_f32(const float2 (&v)[DIM0][J], int extra, const bool (&tail)[J][2], float& T,
+                                                 float& A) {
+#pragma unroll
+  for (int s = 0; s < SETS; ++s) {
+    const float q = sum_sq_f32<J>(v[s]);
+    T += q;
+    if (s >= SETS - extra) A += q;  // warp-uniform
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    if (tail[j][0]) A = fmaf(v[0][j].x, v[0][j].x, A);
+    if (tail[j][1]) A = fmaf(v[0][j].y, v[0][j].y, A);
+  }
+}
+template <int SETS, int DIM0, int J>
+__device__ __forceinline__ void level_halve_f32(float2 (&v)[DIM0][J]) {
+#pragma unroll
+  for (int s = 0; s < SETS / 2; ++s)
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      v[s][j].x += v[s + SETS / 2][j].x;
+      v[s][j].y += v[s + SETS / 2][j].y;
+    }
+}
+template <int DIM0, int J, int LV, int NL>
+struct pow2_levels_f32 {
+  static __device__ __forceinline__ void run(float2 (&v)[DIM0][J], int M0, const bool (&tail)[J][2], float (&T)[NL],
+                                             float (&A)[NL]) {
+    constexpr int sets = 1 << LV;
+    level_energy_f32<sets, DIM0, J>(v, M0 & (sets - 1), tail, T[LV], A[LV]);
+    if constexpr (LV > 0) {
+      level_halve_f32<sets, DIM0, J>(v);
+      pow2_levels_f32<DIM0, J, LV - 1, NL>::run(v, M0, tail, T, A);
+    }
+  }
+};
+template <int DIM0, int J, int LV, int NL>
+struct rider_levels_f32 {
+  static __device__ __forceinline__ void run(float2 (&v)[DIM0][J], int M0, const bool (&tail)[J][2], float (&T)[NL],
+                                             float (&A)[NL]) {
+    constexpr int sets = 3 << LV;
+    level_energy_f32<sets, DIM0, J>(v, M0 % sets, tail, T[LV], A[LV]);
+    if constexpr (LV > 0) {
+      level_halve_f32<sets, DIM0, J>(v);
+      rider_levels_f32<DIM0, J, LV - 1, NL>::run(v, M0, tail, T, A);
+    }
+  }
+};
+
+// rows (stride g) of the base-residue pairs ra + 2 lane + 64 j + {0, 1} into S sets by (row - M0) mod S, plus the
+// predicated tail row into set 0; lanes / components past g are zeroed when MASK.
+template <int S, int J, bool MASK>
+__device__ __forceinline__ void hier_accumulate_f32(const F32Window& w, int g, int ra, int M0, int rr, int head,
+                                                    int groups, float2 (&acc)[S][J], bool (&tail)[J][2]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int s = 0; s < S; ++s)
+#pragma unroll
+    for (int j = 0; j < J; ++j) acc[s][j] = make_float2(0.f, 0.f);
+  int e = ra;
+  if constexpr (S == 1) {
+#pragma unroll 2
+    for (int k = 0; k < M0; ++k) {
+      add_row_f32<J>(acc[0], w.row(e));
+      e += g;
+    }
+  } else {
+#pragma unroll
+    for (int s = 1; s < S; ++s) {  // rows before the first complete group of S
+      if (s >= S - head) {
+        add_row_f32<J>(acc[s], w.row(e));
+        e += g;
+      }
+    }
+#pragma unroll 1
+    for (int i = groups; i > 0; --i) {
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        add_row_f32<J>(acc[s], w.row(e));
+        e += g;
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int r = ra + 2 * lane + 64 * j;
+    tail[j][0] = r < rr;
+    tail[j][1] = r + 1 < rr;
+  }
+  if (ra < rr) {  // warp-uniform
+    const float2* row = w.row(e);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      float2 t = make_float2(0.f, 0.f);
+      if (tail[j][0]) t = row[32 * j];  // predicated: the tail row of a residue >= rr lies past the window
+      acc[0][j].x += t.x;
+      acc[0][j].y += tail[j][1] ? t.y : 0.f;
+    }
+  }
+  if (MASK) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int r = ra + 2 * lane + 64 * j;
+#pragma unroll
+      for (int s = 0; s < S; ++s) {
+        if (r >= g) acc[s][j].x = 0.f;
+        if (r + 1 >= g) acc[s][j].y = 0.f;
+      }
+    }
+  }
+}
+
+// per-tile float partial energies go into double accumulators (the sum over tiles is then exact enough to ignore)
+template <int NL>
+__device__ __forceinline__ void fold_partial(double (&T)[NL], double (&A)[NL], const float (&t)[NL], const float (&a)[NL]) {
+#pragma unroll
+  for (int i = 0; i < NL; ++i) {
+    T[i] += (double)t[i];
+    A[i] += (double)a[i];
+  }
+}
+
+template <int L, int J, bool MASK>
+__device__ __forceinline__ void hier_tile_f32(const F32Window& w, int g, int ra, int M0, int rr, double (&T)[L + 1],
+                                              double (&A)[L + 1], double* scr) {
+  constexpr int S = 1 << L;
+  const int lane = threadIdx.x & 31;
+  float2 acc[S][J];
+  bool tail[J][2];
+  hier_accumulate_f32<S, J, MASK>(w, g, ra, M0, rr, M0 & (S - 1), M0 >> L, acc, tail);
+  float t[L + 1], a[L + 1];
+#pragma unroll
+  for (int i = 0; i <= L; ++i) t[i] = a[i] = 0.f;
+  pow2_levels_f32<S, J, L, L + 1>::run(acc, M0, tail, t, a);
+  fold_partial<L + 1>(T, A, t, a);
+  if (scr != nullptr) {
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int r = ra + 2 * lane + 64 * j;
+      if (r < g) scr[r] = (double)acc[0][j].x;
+      if (r + 1 < g) scr[r + 1] = (double)acc[0][j].y;
+    }
+  }
+}
+
+template <int LH, int J, bool MASK>
+__device__ __forceinline__ void rider_tile_f32(const F32Window& w, int g, int ra, int M0, int rr, int head, int groups,
+                                               double (&Th)[LH + 1], double (&Ah)[LH + 1], double (&Tr)[LH],
+                                               double (&Ar)[LH]) {
+  constexpr int S = 3 << LH, SH = 1 << LH;
+  float2 acc[S][J];
+  bool tail[J][2];
+  hier_accumulate_f32<S, J, MASK>(w, g, ra, M0, rr, head, groups, acc, tail);
+  {
+    float2 hv[SH][J];
+#pragma unroll
+    for (int t = 0; t < SH; ++t)
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        hv[t][j].x = (acc[t][j].x + acc[t + SH][j].x) + acc[t + 2 * SH][j].x;
+        hv[t][j].y = (acc[t][j].y + acc[t + SH][j].y) + acc[t + 2 * SH][j].y;
+      }
+    float t[LH + 1], a[LH + 1];
+#pragma unroll
+    for (int i = 0; i <= LH; ++i) t[i] = a[i] = 0.f;
+    pow2_levels_f32<SH, J, LH, LH + 1>::run(hv, M0, tail, t, a);
+    fold_partial<LH + 1>(Th, Ah, t, a);
+  }
+  level_halve_f32<S, S, J>(acc);
+  float t[LH], a[LH];
+#pragma unroll
+  for (int i = 0; i < LH; ++i) t[i] = a[i] = 0.f;
+  rider_levels_f32<S, J, LH - 1, LH>::run(acc, M0, tail, t, a);
+  fold_partial<LH>(Tr, Ar, t, a);
+}
+
+// columns (of 64 residues) per accumulator set: 8 float accumulators per lane for L <= 2, 16 for L = 3
+#ifndef PP_F32_COLS0
+#define PP_F32_COLS0 4
+#endif
+template <int L>
+struct hier_cols_f32 {
+  static constexpr int value = (PP_F32_COLS0 >> L) > 1 ? (PP_F32_COLS0 >> L) : 1;
+};
+
+// float energies of one top and its chain, written to keys[] (no ranking here)
+template <int L>
+__device__ __forceinline__ void warp_hier_top_f32(const RankCtx& rc, const F32Window& w, double* keys, int g, int M0,
+                                                  int rr, double* scr, double& pend, int& pend_p) {
+  constexpr int J = hier_cols_f32<L>::value;
+  const int lane = threadIdx.x & 31;
+  const int N = rc.N;
+  const bool chain = (L == 3) && !(g & 1) && (g >> 1) >= rc.pmin;
+  double* out = chain ? scr : nullptr;
+  double T[L + 1], A[L + 1];
+#pragma unroll
+  for (int i = 0; i <= L; ++i) T[i] = A[i] = 0.0;
+  int ra = 0;
+  for (; ra + 64 * J <= g; ra += 64 * J) hier_tile_f32<L, J, false>(w, g, ra, M0, rr, T, A, out);
+#ifdef PP_F32_REM2
+  if constexpr (J > 2)
+    for (; ra + 128 <= g; ra += 128) hier_tile_f32<L, 2, false>(w, g, ra, M0, rr, T, A, out);
+#endif
+  for (; ra < g; ra += 64) hier_tile_f32<L, 1, true>(w, g, ra, M0, rr, T, A, out);
+  constexpr int KP = L == 0 ? 1 : (L == 1 ? 2 : 4);
+  double e[KP];
+#pragma unroll
+  for (int i = 0; i < KP; ++i) {
+    if (i <= L) {
+      const int M = M0 >> i;
+      const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+      e[i] = fma(w_diff, A[i], w_lo * T[i]);
+    } else {
+      e[i] = 0.0;
+    }
+  }
+  if constexpr (L == 0) {
+    if (pend_p == 0) {
+      pend = e[0];
+      pend_p = g;
+    } else {
+      const double pair[2] = {pend, e[0]};
+      const double key = warp_sum_multi<2>(pair);
+      if ((lane & 15) == 0) keys[(lane & 16) ? g : pend_p] = key;
+      pend_p = 0;
+    }
+  } else {
+    const double key = warp_sum_multi<KP>(e);
+    constexpr int shift = KP == 2 ? 4 : 3;
+    const int k = lane >> shift;
+    if ((lane & ((1 << shift) - 1)) == 0 && k <= L) keys[g << k] = key;
+  }
+  if (chain) {
+    __syncwarp();
+    double* src = scr;
+    double* dst = scr + ((g + 1) & ~1);
+    int h = g;
+    while (!(h & 1) && (h >> 1) >= rc.pmin) {
+      const int h2 = h >> 1;
+      const int M = N / h2, r0h = N - M * h2;
+      const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+      double t = 0.0, a = 0.0;
+      for (int r = lane; r < h2; r += 32) {
+        const double v = src[r] + src[r + h2];
+        dst[r] = v;
+        t = fma(v, v, t);
+        if (r < r0h) a = fma(v, v, a);
+      }
+      __syncwarp();
+      const double key = warp_sum(fma(w_diff, a, w_lo * t));
+      if (lane == 0) keys[h2] = key;
+      double* swp = src;
+      src = dst;
+      dst = swp;
+      h = h2;
+    }
+    __syncwarp();
+  }
+}
+
+template <int LH>
+__device__ __forceinline__ void warp_hier_rider_f32(const RankCtx& rc, const F32Window& w, double* keys, int g, int M0,
+                                                    int rr) {
+  constexpr int S = 3 << LH;
+  const int lane = threadIdx.x & 31;
+  const int head = M0 % S, groups = M0 / S;
+  double Th[LH + 1], Ah[LH + 1], Tr[LH], Ar[LH];
+#pragma unroll
+  for (int i = 0; i <= LH; ++i) Th[i] = Ah[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < LH; ++i) Tr[i] = Ar[i] = 0.0;
+  int ra = 0;
+  for (; ra + 64 <= g; ra += 64) rider_tile_f32<LH, 1, false>(w, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+  for (; ra < g; ra += 64) rider_tile_f32<LH, 1, true>(w, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+  constexpr int NV = 2 * LH + 1;
+  constexpr int KP = NV <= 4 ? 4 : 8;
+  double e[KP];
+#pragma unroll
+  for (int i = 0; i < KP; ++i) e[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i <= LH; ++i) {
+    const int M = M0 >> i;
+    const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+    e[i] = fma(w_diff, Ah[i], w_lo * Th[i]);
+  }
+#pragma unroll
+  for (int i = 0; i < LH; ++i) {
+    const int M = M0 / (3 << i);
+    const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+    e[LH + 1 + i] = fma(w_diff, Ar[i], w_lo * Tr[i]);
+  }
+  const double key = warp_sum_multi<KP>(e);
+  constexpr int shift = KP == 4 ? 3 : 2;
+  const int k = lane >> shift;
+  int p = 0;
+  if (k <= LH) p = g << k;
+  else if (k < NV) p = (3 * g) << (k - LH - 1);
+  if (p < rc.pmin || p > rc.pmax) p = 0;
+  if (p != 0 && (lane & ((1 << shift) - 1)) == 0) keys[p] = key;
+}
+
+__device__ __forceinline__ void warp_hier_job_f32(const RankCtx& rc, const F32Window& w, double* keys, uint2 e, double* scr,
+                                                  double& pend, int& pend_p) {
+  const int g = e.x & 0xffff, L = (e.x >> 16) & 0xf, M0 = e.y & 0xffff, rr = e.y >> 16;
+  if (e.x >> 20) {
+    if (L == 1) warp_hier_rider_f32<1>(rc, w, keys, g, M0, rr);
+    else warp_hier_rider_f32<2>(rc, w, keys, g, M0, rr);
+    return;
+  }
+  switch (L) {
+    case 0: warp_hier_top_f32<0>(rc, w, keys, g, M0, rr, scr, pend, pend_p); break;
+    case 1: warp_hier_top_f32<1>(rc, w, keys, g, M0, rr, scr, pend, pend_p); break;
+    case 2: warp_hier_top_f32<2>(rc, w, keys, g, M0, rr, scr, pend, pend_p); break;
+    default: warp_hier_top_f32<3>(rc, w, keys, g, M0, rr, scr, pend, pend_p); break;
+  }
+}
+
+// Upper bound of |float energy - exact energy| of candidate p (first-order, doubled): input rounding, the float
+// summation of ceil(N/p) terms per residue (any order), the float squares and per-tile energy sums (<= 40 u);
+// everything relative to sum x^2 because sum_r (sum_{i in r} |x_i|)^2 / cnt_r <= sum x^2 (Cauchy-Schwarz).
+__device__ __forceinline__ double f32_energy_tol(int N, int p, double e_res) {
+  const double u = 5.9604644775390625e-08;  // 2^-24
+  return 2.0 * (2.0 * (double)((N + p - 1) / p) + 40.0) * u * e_res;
+}
+
+// ------------------------------------------------------------------------------------------
 // job table
 // ------------------------------------------------------------------------------------------
 // Descriptor of one job: x = g | L << 16 | rider << 20, y = floor(N / g) | (N mod g) << 16.
@@ -867,7 +1240,8 @@ struct SweepShared {
   double rcp[kRcpTab];  // rcp[m] = 1 / m (rcp[0] unused); filled once per CTA by sweep_shared_init
   SweepParams params;
   int counter;  // next candidate index
-  int ncand;    // hierarchical MAXABS: candidates to verify
+  int ncand;    // hierarchical MAXABS / fp32 nomination: candidates to verify
+  unsigned long long stat_nominated, stat_fallback;  // fp32 nomination statistics (development aid)
   int cand[kMaxVerify];
   int hit_p;    // first-hit mode: lowest period over threshold so far
   double wkey[kWarps];
@@ -875,6 +1249,7 @@ struct SweepShared {
 };
 
 __device__ __forceinline__ void sweep_shared_init(SweepShared* sh) {
+  if (threadIdx.x == 0) sh->stat_nominated = sh->stat_fallback = 0ull;
   for (int m = threadIdx.x; m < kRcpTab; m += kThreads) sh->rcp[m] = m ? 1.0 / (double)m : 0.0;
 }
 
@@ -906,7 +1281,76 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   const bool hier_maxabs = metric == PP_METRIC_MAXABS && sp->verify_keys != nullptr;
   const bool hier = sp->hier_scr != nullptr && sp->tops != nullptr && !first_hit && !sp->orth && !sp->trunc &&
                     (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA || hier_maxabs);
-  if (hier) {
+  // fp32 nomination: the float pass fills verify_keys[], then every candidate whose upper bound reaches the best
+  // lower bound is folded sequentially in fp64 and ranked with the reference's rule.
+  bool ranked = false;
+  if (hier && !hier_maxabs && sp->xf0_off != 0 && sp->verify_keys != nullptr && sp->metric_out == nullptr) {
+    const uint2* __restrict__ tops = sp->tops;
+    const int total = sp->ntops;
+    double* scr = sp->hier_scr + (size_t)wid * sp->hier_len;
+    double* keys = sp->verify_keys;
+    const F32Window fw{sp->xf0_off, sp->xf1_off};
+    double pend = 0.0;
+    int pend_p = 0;
+    while (true) {
+      int idx = 0;
+      if (lane == 0) idx = atomicAdd(&sh->counter, 1);
+      idx = __shfl_sync(0xffffffffu, idx, 0);
+      if (idx >= total) break;
+      warp_hier_job_f32(rc, fw, keys, __ldg(tops + idx), scr, pend, pend_p);
+    }
+    if (pend_p != 0) {  // odd top left without a partner
+      const double key = warp_sum(pend);
+      if (lane == 0) keys[pend_p] = key;
+    }
+    if (threadIdx.x == 0) sh->ncand = 0;
+    __syncthreads();  // every float energy is in keys[]
+    const double e_res = sp->e_res;
+    const bool gam = metric == PP_METRIC_GAMMA;
+    const uint32_t* skip = rc.skip;
+    double lb = -1.0;  // best guaranteed lower bound of a ranking value
+    for (int p = pmin + threadIdx.x; p <= pmax; p += kThreads) {
+      if (skip != nullptr && ((skip[p >> 5] >> (p & 31)) & 1u)) continue;
+      double v = keys[p] - f32_energy_tol(rc.N, p, e_res);
+      if (gam) v = v / (double)p;
+      lb = fmax(lb, v);
+    }
+    lb = warp_max(lb);
+    if (lane == 0) sh->wkey[wid] = lb;
+    __syncthreads();
+    lb = sh->wkey[0];
+#pragma unroll
+    for (int w2 = 1; w2 < kWarps; ++w2) lb = fmax(lb, sh->wkey[w2]);
+    for (int p = pmin + threadIdx.x; p <= pmax; p += kThreads) {
+      if (skip != nullptr && ((skip[p >> 5] >> (p & 31)) & 1u)) continue;
+      double v = keys[p] + f32_energy_tol(rc.N, p, e_res);
+      if (gam) v = v / (double)p;
+      if (v >= lb) {
+        const int slot = atomicAdd(&sh->ncand, 1);
+        if (slot < kMaxVerify) sh->cand[slot] = p;
+      }
+    }
+    __syncthreads();
+    const int nc = sh->ncand;
+    if (threadIdx.x == 0) {
+      sh->stat_nominated += (unsigned long long)nc;
+      sh->stat_fallback += nc > kMaxVerify ? 1ull : 0ull;
+    }
+    if (nc <= kMaxVerify) {
+      RankCtx vrc = rc;
+      vrc.skip = nullptr;  // skipped periods were not nominated
+      for (int c = wid; c < nc; c += kWarps) {
+        const int p = sh->cand[c];
+        consider(vrc, warp_period_key<kPassEnergy>(sp, p), p, best);
+      }
+      ranked = true;
+    } else {  // too many near-ties for the float pass to separate: rank this sweep in fp64
+      if (threadIdx.x == 0) sh->counter = 0;
+    }
+    __syncthreads();  // wkey is rewritten below
+  }
+  if (ranked) {
+  } else if (hier) {
     // tops: candidates p with 2p > pmax; everything else is derived from exactly one of them
     const uint2* __restrict__ tops = sp->tops;
     const int total = sp->ntops;

@@ -439,3 +439,30 @@ def test_best_correlation_hierarchical_nomination_is_exact(P):
         assert np.array_equal(a.powers, b.powers)
         assert np.array_equal(a.status, b.status)
         assert np.array_equal(a.bases, b.bases, equal_nan=True)
+
+
+def test_mbest_f32_nomination_mode_is_exact(P):
+    """PP_FOLD_NOMINATE_F32: the ranking sweep runs in float and only nominates; every candidate whose error bound
+    reaches the best one is folded sequentially in fp64.  Period lists and sweep counts must equal the all-fp64
+    direct sweep, powers to rounding (the north star's "fp32 option keeps periods exact")."""
+    import torch
+    from pyperiod_b200 import _lib
+    B = 192
+    stream = synth.synth_stream(B)
+    win = torch.as_strided(torch.from_numpy(stream).cuda(), (B, 4096), (512, 1))
+    small = synth.synth_batch(16, 1000, 4711)
+    out = {}
+    try:
+        for mode in (_lib.FOLD_DIRECT, _lib.FOLD_NOMINATE_F32):
+            _lib.set_fold_mode(mode)
+            out[mode, "m"] = P().m_best(win, num=10, max_length=1024)
+            out[mode, "g"] = P().m_best_gamma(win, num=10, max_length=1024)
+            out[mode, "s"] = P().m_best(small, num=5)
+    finally:
+        _lib.set_fold_mode(_lib.FOLD_HIERARCHICAL)
+    for k in ("m", "g", "s"):
+        a, b = out[_lib.FOLD_DIRECT, k], out[_lib.FOLD_NOMINATE_F32, k]
+        g = (lambda t: t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t))
+        assert np.array_equal(g(a.periods), g(b.periods)), k
+        assert np.array_equal(g(a.sweeps), g(b.sweeps)), k
+        np.testing.assert_allclose(g(b.powers), g(a.powers), rtol=1e-12)

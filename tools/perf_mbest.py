@@ -13,7 +13,7 @@ P = Periods()
 prof = torch.zeros(8, dtype=torch.int64, device="cuda")
 _lib.load().pp_set_profile_buffer(prof.data_ptr())
 for mode in modes:
-    _lib.set_fold_mode({"direct": _lib.FOLD_DIRECT, "norider": _lib.FOLD_HIERARCHICAL_NO_RIDERS}.get(mode, _lib.FOLD_HIERARCHICAL))
+    _lib.set_fold_mode({"direct": _lib.FOLD_DIRECT, "norider": _lib.FOLD_HIERARCHICAL_NO_RIDERS, "f32": _lib.FOLD_NOMINATE_F32}.get(mode, _lib.FOLD_HIERARCHICAL))
     for name, fn in (("m_best", P.m_best), ("m_best_gamma", P.m_best_gamma)):
         fn(win, num=10, max_length=1024)
         fn(win, num=10, max_length=1024)
