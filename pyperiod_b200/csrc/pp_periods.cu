@@ -220,7 +220,7 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
       sp.xf1_off = 0;
       sp.metric_out = metric_out ? metric_out + (size_t)b * (pmax + 1) : nullptr;
     }
-    const SweepResult r = cta_sweep(sm.sweep);
+    const SweepResult r = cta_sweep<kSweepHier>(sm.sweep);
     if (threadIdx.x == 0) {
       best_p[b] = r.p;
       best_val[b] = r.val;
@@ -375,7 +375,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     const int guard = 12 * (pmax - pmin + 2) + 12 * num;
     while (true) {
       if (misc[0] >= num || misc[4] != PP_STATUS_OK) break;  // uniform: read after a barrier
-      const SweepResult top = cta_sweep(sm.sweep);
+      const SweepResult top = cta_sweep<kSweepHier | kSweepF32>(sm.sweep);
       ++sweeps;
       { const long long t = clock64(); t_sweep += t - t_mark; t_mark = t; }
       if (top.p == 0 || sweeps > guard) {
@@ -679,7 +679,7 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
     // the host rejects negative thresholds.
     while (pstart <= n_periods) {
       if (threadIdx.x == 0) sm.sweep->params.pmin = pstart;
-      const SweepResult hit = cta_sweep(sm.sweep);
+      const SweepResult hit = cta_sweep<0>(sm.sweep);
       if (hit.p == 0) break;
       const int clen = orth ? tb.chain_off[hit.p + 1] - tb.chain_off[hit.p] : 0;
       cta_project_exact<false>(sm.xs, 0, N, hit.p, trunc, orth ? tb.chain_q + tb.chain_off[hit.p] : nullptr, clen,
@@ -770,7 +770,7 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       int p_sel = 0;
       if (status == PP_STATUS_OK) {
         if (threadIdx.x == 0) sm.sweep->params.e_res = e_now;  // error bound of the hierarchical sums
-        const SweepResult top = cta_sweep(sm.sweep);
+        const SweepResult top = cta_sweep<kSweepHierMaxAbs>(sm.sweep);
         if (top.p == 0) {
           status = PP_STATUS_NO_PERIOD;
         } else {

@@ -1261,6 +1261,11 @@ __device__ __forceinline__ void sweep_shared_init(SweepShared* sh) {
 // sh->params must have been written by thread 0.  All threads call; the result is valid in all
 // threads.  Contains CTA barriers.  Kept out of line so the caller's live state does not compete
 // with the fold's registers.
+// FEAT selects the ranking paths compiled into this instance (a kernel only carries the code it can reach):
+constexpr int kSweepHier = 1;        // fp64 hierarchical NORM / GAMMA ranking
+constexpr int kSweepHierMaxAbs = 2;  // hierarchical MAXABS nomination + exact verification
+constexpr int kSweepF32 = 4;         // float nomination + exact verification
+template <int FEAT>
 static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   const SweepParams* sp = &sh->params;
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -1278,12 +1283,15 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   // MAXABS (best-correlation) may rank hierarchically only when the caller provides `verify_keys`: the metric
   // must be the reference's bit-exact sequential sum, so the hierarchical pass only NOMINATES candidates and
   // the near-maximal ones are re-evaluated exactly below.
-  const bool hier_maxabs = metric == PP_METRIC_MAXABS && sp->verify_keys != nullptr;
-  const bool hier = sp->hier_scr != nullptr && sp->tops != nullptr && !first_hit && !sp->orth && !sp->trunc &&
-                    (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA || hier_maxabs);
+  const bool hier_maxabs = (FEAT & kSweepHierMaxAbs) != 0 && metric == PP_METRIC_MAXABS && sp->verify_keys != nullptr;
+  const bool hier = (FEAT & (kSweepHier | kSweepHierMaxAbs | kSweepF32)) != 0 && sp->hier_scr != nullptr &&
+                    sp->tops != nullptr && !first_hit && !sp->orth && !sp->trunc &&
+                    (((FEAT & (kSweepHier | kSweepF32)) != 0 && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA)) ||
+                     hier_maxabs);
   // fp32 nomination: the float pass fills verify_keys[], then every candidate whose upper bound reaches the best
   // lower bound is folded sequentially in fp64 and ranked with the reference's rule.
   bool ranked = false;
+  if constexpr ((FEAT & kSweepF32) != 0)
   if (hier && !hier_maxabs && sp->xf0_off != 0 && sp->verify_keys != nullptr && sp->metric_out == nullptr) {
     const uint2* __restrict__ tops = sp->tops;
     const int total = sp->ntops;
@@ -1363,8 +1371,13 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
       if (lane == 0) idx = atomicAdd(&sh->counter, 1);
       idx = __shfl_sync(0xffffffffu, idx, 0);
       if (idx >= total) break;
-      if (hier_maxabs) warp_hier_top<true>(hrc, __ldg(tops + idx), scr, wr);
-      else warp_hier_top<false>(hrc, __ldg(tops + idx), scr, wr);
+      const uint2 job = __ldg(tops + idx);
+      if constexpr ((FEAT & kSweepHierMaxAbs) != 0) {
+        if (hier_maxabs) warp_hier_top<true>(hrc, job, scr, wr);
+      }
+      if constexpr ((FEAT & kSweepHier) != 0) {
+        if (!hier_maxabs) warp_hier_top<false>(hrc, job, scr, wr);
+      }
     }
     if (wr.pend_p != 0)  // odd top left without a partner
       consider(hrc, hier_maxabs ? warp_max(wr.pend) : warp_sum(wr.pend), wr.pend_p, wr.best);
@@ -1413,6 +1426,7 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
       res = Best{k, q};
     }
   }
+  if constexpr ((FEAT & kSweepHierMaxAbs) != 0)
   if (hier && hier_maxabs && res.p != 0) {
     // Exact verification.  A hierarchical sum differs from the sequential one by at most
     // err = 2 N eps sum|x| <= 2 N eps sqrt(N e_res); a candidate whose hierarchical key lies more than 2 err below
