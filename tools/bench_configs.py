@@ -57,8 +57,10 @@ def main():
     dadd_peak = _lib.microbench(1)["per_s"]
     dmma_peak = _lib.microbench(2)["per_s"]
 
-    def timed(fn, reps=2):
-        fn(); torch.cuda.synchronize()
+    def timed(fn, reps=2, warm=3):
+        for _ in range(warm):        # clocks, allocator and the first launches settle
+            fn()
+        torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
