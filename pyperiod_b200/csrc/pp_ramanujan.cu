@@ -107,6 +107,18 @@ constexpr int kGemmN = 64;    // windows per CTA
 constexpr int kGemmK = 32;    // k-chunk staged in shared memory
 constexpr int kLdB = 68;      // padded leading dimension of the staged S chunk (68 mod 16 = 4: conflict-free frags)
 
+// 16-byte asynchronous global -> shared copy; bytes past src_bytes are zero-filled (rows past q, windows past
+// the tile)
+__device__ __forceinline__ void cp_async_16(void* dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
                : "+d"(c[0]), "+d"(c[1])
@@ -123,8 +135,8 @@ ram_gemm_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count,
   const int b0 = blockIdx.x * kGemmN;
   if (b0 >= b_count) return;
   double* cqs = reinterpret_cast<double*>(pp_smem);              // [q]
-  double* Bs = cqs + ((q + 1) & ~1);                               // [kGemmK][kLdB]
-  double* red = Bs + kGemmK * kLdB;                                // [4][kGemmN]
+  double* Bs0 = cqs + ((q + 1) & ~1);                              // [2][kGemmK][kLdB]: double-buffered S chunk
+  double* red = Bs0 + 2 * kGemmK * kLdB;                           // [4][kGemmN]
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int wm = wid >> 1, wn = wid & 1;                           // warp tile: rows wm*32.., cols wn*32..
   const int lr = lane >> 2, lc = lane & 3;
@@ -143,14 +155,28 @@ ram_gemm_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count,
     for (int i = 0; i < 4; ++i)
 #pragma unroll
       for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int l0 = 0; l0 < q; l0 += kGemmK) {
-      __syncthreads();
-      // stage S_q[l0 .. l0+31][b0 .. b0+63] (rows past q and windows past the tile are zero)
-      for (int idx = tid; idx < kGemmK * kGemmN; idx += kThreads) {
-        const int kk = idx >> 6, n = idx & 63;
-        double v = 0.0;
-        if (l0 + kk < q && b0 + n < b_count) v = Sq[(size_t)(l0 + kk) * ldS + n];
-        Bs[kk * kLdB + n] = v;
+    // stage S_q[l0 .. l0+31][b0 .. b0+63] with cp.async (rows past q and windows past the tile are zero-filled);
+    // the copy of chunk l0 + 32 is in flight while chunk l0 feeds the tensor cores
+    auto stage = [&](double* dst, int l0) {
+      for (int idx = tid; idx < kGemmK * kGemmN / 2; idx += kThreads) {
+        const int kk = idx >> 5, n = (idx & 31) * 2;
+        int bytes = 0;
+        if (l0 + kk < q) bytes = min(max(b_count - (b0 + n), 0), 2) * 8;
+        const double* src = bytes ? Sq + (size_t)(l0 + kk) * ldS + n : Sq;
+        cp_async_16(dst + kk * kLdB + n, src, bytes);
+      }
+      cp_async_commit();
+    };
+    __syncthreads();  // the previous row block is done with both buffers
+    stage(Bs0, 0);
+    int buf = 0;
+    for (int l0 = 0; l0 < q; l0 += kGemmK, buf ^= 1) {
+      const double* Bs = Bs0 + buf * (kGemmK * kLdB);
+      if (l0 + kGemmK < q) {
+        stage(Bs0 + (buf ^ 1) * (kGemmK * kLdB), l0 + kGemmK);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
       }
       __syncthreads();
 #pragma unroll
@@ -172,6 +198,7 @@ ram_gemm_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count,
           for (int j = 0; j < 4; ++j) dmma_m8n8k4(acc[i][j], a, bf[j]);
         }
       }
+      __syncthreads();  // everyone is done with this buffer before the next iteration restages it
     }
     // epilogue of this row block: cnt-weighted squares, accumulated per column
 #pragma unroll
@@ -275,7 +302,7 @@ int pp_ramanujan_norms(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   cq_kernel<<<qmax - qmin + 1, 128, 0, st>>>(qmin, qmax, mu, phi, cq);
   const size_t fold_smem = (size_t)kFoldWin * ((N + 1) & ~1) * 8;
   if (int rc = prep_kernel(fold_all_kernel, fold_smem, f)) return rc;
-  const size_t gemm_smem = (size_t)(((qmax + 1) & ~1) + kGemmK * kLdB + 4 * kGemmN) * 8;
+  const size_t gemm_smem = (size_t)(((qmax + 1) & ~1) + 2 * kGemmK * kLdB + 4 * kGemmN) * 8;
   if (int rc = prep_kernel(ram_gemm_kernel, gemm_smem, f)) return rc;
   for (int b_first = 0; b_first < B; b_first += tile_windows) {
     const int b_count = (B - b_first < tile_windows) ? (B - b_first) : tile_windows;
