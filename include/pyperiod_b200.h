@@ -151,7 +151,10 @@ int pp_small_to_large(const double *x, int64_t ldx, int32_t B, int32_t N, double
 
 /* ---- Periods.best_correlation (Periods.py:289-349) ------------------------------------
  * candidates p in [2, max_length) (max_length excluded, :324); rejected rounds leave
- * periods/powers/bases rows at zero. */
+ * periods/powers/bases rows at zero.  With a workspace of pp_workspace_bytes(PP_ALGO_BCORR, N,
+ * max_length, num, orth) bytes the sweep nominates hierarchically and verifies with sequential folds
+ * (bit-identical results, about twice as fast); with workspace == NULL every candidate is folded
+ * sequentially. */
 int pp_best_correlation(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t num, int32_t max_length,
                         double ratio, int32_t trunc, int32_t orth, const int32_t *chain_off,
                         const int32_t *chain_q, int32_t table_pmax, uint32_t *periods, double *powers,

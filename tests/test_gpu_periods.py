@@ -451,6 +451,7 @@ def test_mbest_f32_nomination_mode_is_exact(P):
     stream = synth.synth_stream(B)
     win = torch.as_strided(torch.from_numpy(stream).cuda(), (B, 4096), (512, 1))
     small = synth.synth_batch(16, 1000, 4711)
+    odd = synth.synth_batch(12, 3001, 4712)
     out = {}
     try:
         for mode in (_lib.FOLD_DIRECT, _lib.FOLD_NOMINATE_F32):
@@ -458,9 +459,10 @@ def test_mbest_f32_nomination_mode_is_exact(P):
             out[mode, "m"] = P().m_best(win, num=10, max_length=1024)
             out[mode, "g"] = P().m_best_gamma(win, num=10, max_length=1024)
             out[mode, "s"] = P().m_best(small, num=5)
+            out[mode, "o"] = P().m_best_gamma(odd, num=6, min_length=3, max_length=999)
     finally:
         _lib.set_fold_mode(_lib.FOLD_HIERARCHICAL)
-    for k in ("m", "g", "s"):
+    for k in ("m", "g", "s", "o"):
         a, b = out[_lib.FOLD_DIRECT, k], out[_lib.FOLD_NOMINATE_F32, k]
         g = (lambda t: t.cpu().numpy() if hasattr(t, "cpu") else np.asarray(t))
         assert np.array_equal(g(a.periods), g(b.periods)), k
