@@ -72,7 +72,8 @@ def _pipelined_upload(host_flat: torch.Tensor, b: int, n: int, hop: int, dev: to
     cs.wait_stream(cur)              # the allocation point of dflat is on the current stream
     dflat.record_stream(cs)
     per = -(-b // PIPELINE_PIECES)
-    bounds = [(b0, min(b, b0 + per)) for b0 in range(0, b, per)]
+    first = max(1, per // 4)  # a small first piece: the first kernel starts after ~1 ms of PCIe traffic
+    bounds = [(0, min(b, first))] + [(b0, min(b, b0 + per)) for b0 in range(first, b, per)]
 
     def copy_piece(k):
         b0, b1 = bounds[k]
