@@ -20,6 +20,10 @@
 
 namespace pp {
 
+#ifndef PP_QO_CTAS
+#define PP_QO_CTAS 2
+#endif
+constexpr int kQoCtasPerSm = PP_QO_CTAS;  // persistent CTAs per SM of the QO kernels
 constexpr int kCholNb = 32;    // Cholesky block size
 constexpr int kCholTile = 32;  // trailing-update tile: 32 x 32 outputs per warp, 4 x 8 per lane
 
@@ -172,7 +176,7 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
       const int base = kb + nb;
       const int nt = (R - base + kCholTile - 1) / kCholTile;
       const int npairs = nt * (nt + 1) / 2;
-      const int ty = lane >> 2, tx = lane & 3;  // lane's 4 rows x 8 columns of the tile
+      const int ty = lane >> 2, tx = lane & 3;  // lane's 4 rows x 4 columns of each half tile
       for (int pr = wid; pr < npairs; pr += kWarps) {
         // pr -> (it, jt) with jt <= it
         int it = (int)((sqrtf(8.0f * (float)pr + 1.0f) - 1.0f) * 0.5f);
@@ -181,46 +185,48 @@ __device__ bool cta_cholesky(double* __restrict__ A, int R, int ld, double* __re
         const int jt = pr - it * (it + 1) / 2;
         const int ti = base + it * kCholTile, tj = base + jt * kCholTile;
         if (ti + kCholTile <= row0) continue;  // rows of the previous factor (tiles are 32-aligned, as row0 is)
-        const int i0 = ti + ty * 4, j0 = tj + tx * 8;
-        double acc[4][8];
-#pragma unroll
-        for (int r = 0; r < 4; ++r)
-#pragma unroll
-          for (int c = 0; c < 8; ++c) acc[r][c] = 0.0;
-        const bool full = (ti + kCholTile <= R) && (tj + kCholTile <= R);
-#pragma unroll 2
-        for (int k = 0; k < kCholNb; ++k) {
-          const double* pk = Pt + (size_t)k * ld;
-          double av[4], bv[8];
-          if (full) {
-            const double2 a01 = *reinterpret_cast<const double2*>(pk + i0);
-            const double2 a23 = *reinterpret_cast<const double2*>(pk + i0 + 2);
-            av[0] = a01.x; av[1] = a01.y; av[2] = a23.x; av[3] = a23.y;
-#pragma unroll
-            for (int c = 0; c < 8; c += 2) {
-              const double2 b2 = *reinterpret_cast<const double2*>(pk + j0 + c);
-              bv[c] = b2.x;
-              bv[c + 1] = b2.y;
-            }
-          } else {
-#pragma unroll
-            for (int r = 0; r < 4; ++r) av[r] = (i0 + r < R) ? pk[i0 + r] : 0.0;
-#pragma unroll
-            for (int c = 0; c < 8; ++c) bv[c] = (j0 + c < R) ? pk[j0 + c] : 0.0;
-          }
+        // two 32 x 16 halves, each lane 4 rows x 4 columns: 16 accumulators (the 4 x 8 version spilled)
+#pragma unroll 1
+        for (int half = 0; half < 2; ++half) {
+          const int i0 = ti + ty * 4, j0 = tj + half * 16 + tx * 4;
+          if (j0 > i0 + 3) continue;  // entirely above the diagonal
+          double acc[4][4];
 #pragma unroll
           for (int r = 0; r < 4; ++r)
 #pragma unroll
-            for (int c = 0; c < 8; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
-        }
+            for (int c = 0; c < 4; ++c) acc[r][c] = 0.0;
+          const bool full = (ti + kCholTile <= R) && (tj + kCholTile <= R);
+#pragma unroll 4
+          for (int k = 0; k < kCholNb; ++k) {
+            const double* pk = Pt + (size_t)k * ld;
+            double av[4], bv[4];
+            if (full) {
+              const double2 a01 = *reinterpret_cast<const double2*>(pk + i0);
+              const double2 a23 = *reinterpret_cast<const double2*>(pk + i0 + 2);
+              const double2 b01 = *reinterpret_cast<const double2*>(pk + j0);
+              const double2 b23 = *reinterpret_cast<const double2*>(pk + j0 + 2);
+              av[0] = a01.x; av[1] = a01.y; av[2] = a23.x; av[3] = a23.y;
+              bv[0] = b01.x; bv[1] = b01.y; bv[2] = b23.x; bv[3] = b23.y;
+            } else {
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-          const int i = i0 + r;
-          if (i < R) {
+              for (int r = 0; r < 4; ++r) av[r] = (i0 + r < R) ? pk[i0 + r] : 0.0;
 #pragma unroll
-            for (int c = 0; c < 8; ++c) {
-              const int j = j0 + c;
-              if (j <= i) A[(size_t)i * ld + j] -= acc[r][c];
+              for (int c = 0; c < 4; ++c) bv[c] = (j0 + c < R) ? pk[j0 + c] : 0.0;
+            }
+#pragma unroll
+            for (int r = 0; r < 4; ++r)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) acc[r][c] = fma(av[r], bv[c], acc[r][c]);
+          }
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int i = i0 + r;
+            if (i < R) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int j = j0 + c;
+                if (j <= i) A[(size_t)i * ld + j] -= acc[r][c];
+              }
             }
           }
         }
@@ -812,7 +818,7 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   const int hier = (pp_get_fold_mode() != PP_FOLD_DIRECT && !trunc) ? 1 : 0;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0);
   if (int rc = prep_kernel(qo_find_kernel, pl.bytes(), f)) return rc;
-  const int grid = grid_for(f, pl.bytes(), B, 2);
+  const int grid = grid_for(f, pl.bytes(), B, kQoCtasPerSm);
   size_t off = 0;
   double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.ldg() * 8);
   double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.ldg() * 8);
@@ -847,7 +853,7 @@ int pp_qo_solve(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t kmax
   if (int rc = device_facts(f)) return rc;
   const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
   if (int rc = prep_kernel(qo_solve_kernel, pl.bytes(), f)) return rc;
-  const int grid = grid_for(f, pl.bytes(), B, 2);
+  const int grid = grid_for(f, pl.bytes(), B, kQoCtasPerSm);
   size_t off = 0;
   double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.ldg() * 8);
   double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.ldg() * 8);
@@ -873,7 +879,7 @@ int pp_qo_solve_rows(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t
   if (int rc = device_facts(f)) return rc;
   const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
   if (int rc = prep_kernel(qo_solve_rows_kernel, pl.bytes(), f)) return rc;
-  const int grid = grid_for(f, pl.bytes(), B, 2);
+  const int grid = grid_for(f, pl.bytes(), B, kQoCtasPerSm);
   size_t off = 0;
   double* G = carve(workspace, workspace_bytes, off, (size_t)grid * pl.rmax * pl.ldg() * 8);
   double* Pt = carve(workspace, workspace_bytes, off, (size_t)grid * kCholNb * pl.ldg() * 8);
