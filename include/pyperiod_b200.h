@@ -210,6 +210,13 @@ int pp_ramanujan_norms(const double *x, int64_t ldx, int32_t B, int32_t N, int32
                        const int32_t *mu, const int32_t *phi, int32_t table_qmax, int32_t tile_windows,
                        double *norms, int32_t ld_norms, void *workspace, size_t workspace_bytes, void *stream);
 
+/* TF32 option of the same periodogram (mma.sync m16n8k8, fp32 accumulation): the Ramanujan sums are exact in
+ * TF32, the fold sums are split into hi + lo parts; norms agree with the fp64 path to ~1e-5 relative.  The fold
+ * itself stays fp64. */
+int pp_ramanujan_norms_tf32(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
+                            const int32_t *mu, const int32_t *phi, int32_t table_qmax, int32_t tile_windows,
+                            double *norms, int32_t ld_norms, void *workspace, size_t workspace_bytes, void *stream);
+
 /* periods[b, 0:nper[b]] = ascending q in [0, qlen) with norms[b,q] / |max_q norms[b,q]| > thresh
  * (RamanujanPeriods.py:97-101); nper[b] may exceed kmax, only the first kmax are stored. */
 int pp_ramanujan_select(const double *norms, int32_t B, int32_t ld_norms, int32_t qlen, double thresh,

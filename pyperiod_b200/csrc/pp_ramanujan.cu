@@ -240,6 +240,158 @@ ram_gemm_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count,
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// TF32 option: the same contraction on the 19-bit tensor cores (mma.sync m16n8k8, fp32 accumulate).
+// c_q(n) is an integer with |c_q| <= phi(q) < 2^11, exact in TF32; the fold sums are split into
+// hi + lo TF32 parts (two MMAs per tile), which leaves ~2^-21 relative error per product and the fp32
+// accumulation of q terms: norms agree with the fp64 path to ~1e-5 relative.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+ram_gemm_tf32_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count, int N, int qmin, int qmax,
+                     const double* __restrict__ cq_all, const int32_t* __restrict__ phi, double* __restrict__ norms,
+                     int ld_norms) {
+  const int q = qmax - blockIdx.y;  // big periods first
+  if (q < qmin) return;
+  const int b0 = blockIdx.x * kGemmN;
+  if (b0 >= b_count) return;
+  float* cqs = reinterpret_cast<float*>(pp_smem);                       // [q] (TF32-exact integers)
+  double* Bs0 = reinterpret_cast<double*>(pp_smem) + ((q + 3) / 2 & ~1);  // [2][kGemmK][kLdB] fp64 fold chunk
+  double* red = Bs0 + 2 * kGemmK * kLdB;                                // [4][kGemmN]
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int wm = wid >> 1, wn = wid & 1;   // warp tile: rows wm*32.., cols wn*32..
+  const int gid = lane >> 2, tig = lane & 3;
+  const double* cq = cq_all + cq_offset(q);
+  for (int i = tid; i < q; i += kThreads) cqs[i] = (float)cq[i];
+  const double* Sq = S + s_offset(q, qmin, ldS) + b0;
+  const int Mrows = N / q, r0 = N - Mrows * q;
+
+  double colacc[4][2];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) colacc[j][0] = colacc[j][1] = 0.0;
+
+  for (int m0 = 0; m0 < q; m0 += kGemmM) {
+    float acc[2][4][4];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
+    auto stage = [&](double* dst, int l0) {
+      for (int idx = tid; idx < kGemmK * kGemmN / 2; idx += kThreads) {
+        const int kk = idx >> 5, n = (idx & 31) * 2;
+        int bytes = 0;
+        if (l0 + kk < q) bytes = min(max(b_count - (b0 + n), 0), 2) * 8;
+        const double* src = bytes ? Sq + (size_t)(l0 + kk) * ldS + n : Sq;
+        cp_async_16(dst + kk * kLdB + n, src, bytes);
+      }
+      cp_async_commit();
+    };
+    __syncthreads();
+    stage(Bs0, 0);
+    int buf = 0;
+    for (int l0 = 0; l0 < q; l0 += kGemmK, buf ^= 1) {
+      const double* Bs = Bs0 + buf * (kGemmK * kLdB);
+      if (l0 + kGemmK < q) {
+        stage(Bs0 + (buf ^ 1) * (kGemmK * kLdB), l0 + kGemmK);
+        cp_async_wait<1>();
+      } else {
+        cp_async_wait<0>();
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k8 = 0; k8 < kGemmK / 8; ++k8) {
+        // B fragments (k x n = 8 x 8 per tile j): b0 = (k = tig, n = gid), b1 = (k = tig + 4, n = gid); hi + lo split
+        uint32_t bh[4][2], bl[4][2];
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const double v = Bs[(k8 * 8 + tig + 4 * h) * kLdB + wn * 32 + j * 8 + gid];
+            const float f = (float)v;
+            const uint32_t hi = to_tf32(f);
+            bh[j][h] = hi;
+            bl[j][h] = to_tf32((float)(v - (double)__uint_as_float(hi)));
+          }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          // A fragment (m x k = 16 x 8): a0 = (gid, tig), a1 = (gid + 8, tig), a2 = (gid, tig + 4), a3 = (gid + 8, tig + 4)
+          uint32_t a[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int m = m0 + wm * 32 + i * 16 + gid + 8 * (e & 1);
+            const int l = l0 + k8 * 8 + tig + 4 * (e >> 1);
+            float v = 0.f;
+            if (m < q && l < q) {
+              int d = l - m;
+              if (d < 0) d += q;
+              v = cqs[d];
+            }
+            a[e] = __float_as_uint(v);  // small integers: already TF32-exact
+          }
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            mma_tf32_m16n8k8(acc[i][j], a, bh[j][0], bh[j][1]);
+            mma_tf32_m16n8k8(acc[i][j], a, bl[j][0], bl[j][1]);
+          }
+        }
+      }
+      __syncthreads();
+    }
+    // epilogue: c0,c1 = (row gid, cols 2 tig, 2 tig + 1), c2,c3 = (row gid + 8, same cols)
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        const int m = m0 + wm * 32 + i * 16 + gid + 8 * hrow;
+        const double cnt = (m < q) ? (double)(Mrows + (m < r0 ? 1 : 0)) : 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const double z0 = (double)acc[i][j][2 * hrow], z1 = (double)acc[i][j][2 * hrow + 1];
+          colacc[j][0] = fma(cnt * z0, z0, colacc[j][0]);
+          colacc[j][1] = fma(cnt * z1, z1, colacc[j][1]);
+        }
+      }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      double v = colacc[j][e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      colacc[j][e] = v;
+    }
+  __syncthreads();
+  if (gid == 0) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      red[wm * kGemmN + wn * 32 + j * 8 + 2 * tig] = colacc[j][0];
+      red[wm * kGemmN + wn * 32 + j * 8 + 2 * tig + 1] = colacc[j][1];
+    }
+  }
+  __syncthreads();
+  if (tid < kGemmN && b0 + tid < b_count) {
+    const double ph = (double)phi[q];
+    const double scale = (double)q / (ph * ph);
+    const double t = ((red[tid] + red[kGemmN + tid]) + red[2 * kGemmN + tid]) + red[3 * kGemmN + tid];
+    norms[(size_t)(b_first + b0 + tid) * ld_norms + q] = scale * scale * t;
+  }
+}
+
 // periods whose norm exceeds thresh * |max norm|, ascending (RamanujanPeriods.py:97-101); one warp per window
 __global__ void select_kernel(const double* __restrict__ norms, int B, int ld_norms, int qlen, double thresh, int kmax,
                               int32_t* __restrict__ periods, int32_t* __restrict__ nper) {
@@ -281,9 +433,10 @@ size_t pp_ramanujan_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32
 // norms[b, q] for q in [qmin, qmax] (other entries untouched; the caller zero-fills, RamanujanPeriods.py:71).
 // mu / phi: device int32 tables for 0..table_qmax.  Windows are processed in tiles of `tile_windows`
 // (workspace holds the folds of one tile).
-int pp_ramanujan_norms(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
-                       const int32_t* mu, const int32_t* phi, int32_t table_qmax, int32_t tile_windows,
-                       double* norms, int32_t ld_norms, void* workspace, size_t workspace_bytes, void* stream) {
+static int ramanujan_norms_impl(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
+                                const int32_t* mu, const int32_t* phi, int32_t table_qmax, int32_t tile_windows,
+                                double* norms, int32_t ld_norms, void* workspace, size_t workspace_bytes, void* stream,
+                                bool tf32) {
   if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (x == nullptr || norms == nullptr || B < 0 || N < 2 || ldx < 1) return fail(-1, "bad window arguments%s");
   if (qmin < 1 || qmax < qmin || qmax > N) return fail(-1, "need 1 <= qmin <= qmax <= N%s");
@@ -304,16 +457,35 @@ int pp_ramanujan_norms(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   if (int rc = prep_kernel(fold_all_kernel, fold_smem, f)) return rc;
   const size_t gemm_smem = (size_t)(((qmax + 1) & ~1) + 2 * kGemmK * kLdB + 4 * kGemmN) * 8;
   if (int rc = prep_kernel(ram_gemm_kernel, gemm_smem, f)) return rc;
+  if (int rc = prep_kernel(ram_gemm_tf32_kernel, gemm_smem, f)) return rc;
   for (int b_first = 0; b_first < B; b_first += tile_windows) {
     const int b_count = (B - b_first < tile_windows) ? (B - b_first) : tile_windows;
     int fgrid = (b_count + kFoldWin - 1) / kFoldWin;
     if (fgrid > f.sm_count) fgrid = f.sm_count;
     fold_all_kernel<<<fgrid, kThreads, fold_smem, st>>>(x, ldx, b_first, b_count, N, qmin, qmax, S, ldS);
     dim3 grid((b_count + kGemmN - 1) / kGemmN, qmax - qmin + 1);
-    ram_gemm_kernel<<<grid, kThreads, gemm_smem, st>>>(S, ldS, b_first, b_count, N, qmin, qmax, cq, phi, norms,
-                                                       ld_norms);
+    if (tf32)
+      ram_gemm_tf32_kernel<<<grid, kThreads, gemm_smem, st>>>(S, ldS, b_first, b_count, N, qmin, qmax, cq, phi, norms,
+                                                              ld_norms);
+    else
+      ram_gemm_kernel<<<grid, kThreads, gemm_smem, st>>>(S, ldS, b_first, b_count, N, qmin, qmax, cq, phi, norms,
+                                                         ld_norms);
   }
   return check_cuda(cudaGetLastError(), "ramanujan kernels launch");
+}
+
+int pp_ramanujan_norms(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
+                       const int32_t* mu, const int32_t* phi, int32_t table_qmax, int32_t tile_windows,
+                       double* norms, int32_t ld_norms, void* workspace, size_t workspace_bytes, void* stream) {
+  return ramanujan_norms_impl(x, ldx, B, N, qmin, qmax, mu, phi, table_qmax, tile_windows, norms, ld_norms, workspace,
+                              workspace_bytes, stream, false);
+}
+
+int pp_ramanujan_norms_tf32(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
+                            const int32_t* mu, const int32_t* phi, int32_t table_qmax, int32_t tile_windows,
+                            double* norms, int32_t ld_norms, void* workspace, size_t workspace_bytes, void* stream) {
+  return ramanujan_norms_impl(x, ldx, B, N, qmin, qmax, mu, phi, table_qmax, tile_windows, norms, ld_norms, workspace,
+                              workspace_bytes, stream, true);
 }
 
 // periods[b, 0:nper[b]] = ascending q in [0, qlen) with norms[b, q] / |max_q norms[b, q]| > thresh

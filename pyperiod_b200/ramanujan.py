@@ -21,8 +21,13 @@ TILE_WINDOWS = 2048  # windows whose folds are held at once (7.5 MB per window a
 
 
 class RamanujanPeriods(QOPeriods):
-    def __init__(self, basis_type="natural", device=None):
+    def __init__(self, basis_type="natural", device=None, precision="fp64"):
+        """precision: "fp64" (FP64 tensor cores, default) or "tf32" (split TF32 tensor-core contraction, fp32
+        accumulation: norms to ~1e-5 relative; not part of the reference API)."""
         super().__init__(basis_type, False, False, device=device)
+        if precision not in ("fp64", "tf32"):
+            raise ValueError("precision must be 'fp64' or 'tf32'")
+        self._precision = precision
         self._verbose = None
         self._k = 0
 
@@ -34,9 +39,10 @@ class RamanujanPeriods(QOPeriods):
         tile = min(TILE_WINDOWS, max(4, w.b))
         ws = Workspace.get(w.device, lib.pp_ramanujan_workspace_bytes(w.n, min_length, max_length, tile))
         norms = torch.zeros((w.b, max_length + 1), dtype=torch.float64, device=w.device)
-        _lib.check(lib.pp_ramanujan_norms(ptr(w.tensor), w.ldx, w.b, w.n, int(min_length), int(max_length), ptr(mu),
-                                          ptr(phi), tb.pmax, tile, ptr(norms), max_length + 1, ptr(ws), ws.numel(),
-                                          stream_ptr(w.device)), "pp_ramanujan_norms")
+        fn = lib.pp_ramanujan_norms_tf32 if self._precision == "tf32" else lib.pp_ramanujan_norms
+        _lib.check(fn(ptr(w.tensor), w.ldx, w.b, w.n, int(min_length), int(max_length), ptr(mu),
+                      ptr(phi), tb.pmax, tile, ptr(norms), max_length + 1, ptr(ws), ws.numel(),
+                      stream_ptr(w.device)), "pp_ramanujan_norms")
         return norms
 
     def find_periods(self, x, min_length=2, max_length=None, select_periods=None):

@@ -65,3 +65,22 @@ def test_find_periods_with_weights_vs_golden(R):
         assert list(d["basis_dictionary"].values()) == g2[f"ram_{b}_dict_vals"].tolist()
         np.testing.assert_allclose(d["weights"], g2[f"ram_{b}_weights"], rtol=1e-7, atol=1e-10)
         np.testing.assert_allclose(res, g2[f"ram_{b}_res"], rtol=0, atol=1e-10)
+
+
+def test_tf32_option_tracks_fp64():
+    """precision="tf32": split-TF32 tensor-core contraction (fp32 accumulate); norms within 1e-5 of the fp64 path
+    relative to the largest norm, and the thresholded period selection is unchanged."""
+    from pyperiod_b200 import RamanujanPeriods
+    xb = synth.synth_batch(70, 2048, 61_000)          # 70 windows: a full 64-window tile and a ragged one
+    a = RamanujanPeriods().find_periods(xb, 2, 400)
+    b = RamanujanPeriods(precision="tf32").find_periods(xb, 2, 400)
+    scale = a.max(axis=1, keepdims=True)
+    assert np.max(np.abs(a - b) / scale) < 1e-5
+    assert np.all(b[:, :2] == 0)
+    ra = RamanujanPeriods().find_periods_with_weights(xb[:8], max_length=200, thresh=0.2)
+    rb = RamanujanPeriods(precision="tf32").find_periods_with_weights(xb[:8], max_length=200, thresh=0.2)
+    for i in range(8):
+        if int(ra.status[i]) == 0 and int(rb.status[i]) == 0:
+            da, _ = ra.window(i)
+            db, _ = rb.window(i)
+            assert np.array_equal(np.asarray(da["periods"]), np.asarray(db["periods"]))

@@ -146,6 +146,11 @@ def main():
                        "algorithmic": "2 q^2 flop per period and window (circulant product on the fold sums), "
                                       "q = 2..1365; peak = measured DMMA m8n8k4 rate (pp_microbench kind 2)"},
           "cpu_baseline": cpu_ram})
+    t32, r32 = timed(lambda: RamanujanPeriods(precision="tf32").find_periods(x), reps=2)
+    emit({"config": "5-Ramanujan-tf32", "algo": "RamanujanPeriods(precision='tf32').find_periods (split-TF32 mma.sync)",
+          "N": 4096, "qmax": 1365, "windows": B, "seconds": t32, "windows_per_s": B / t32,
+          "tensor_TFLOPs_nominal": 2 * flops / t32 / 1e12,
+          "max_rel_diff_vs_fp64": float(((r - r32).abs().amax() / r.amax()).item())})
     t, r = timed(lambda: RamanujanPeriods().find_periods_with_weights(x, thresh=0.2, return_res=False), reps=2)
     emit({"config": "5-Ramanujan+QP", "algo": "RamanujanPeriods.find_periods_with_weights(thresh=0.2)",
           "N": 4096, "windows": B, "seconds": t, "windows_per_s": B / t,
