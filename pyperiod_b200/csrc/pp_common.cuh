@@ -253,8 +253,23 @@ __device__ __forceinline__ void cta_subtract_tiled(double* xs, int N, const doub
   }
 }
 
-// out[n] = v[n mod p] for n < len, coalesced (streaming stores; bases are write-once).
+// out[n] = v[n mod p] for n < len, coalesced streaming stores (bases are write-once): 128-bit stores of sample
+// pairs when the destination is 16-byte aligned, 64-bit stores otherwise.
 __device__ __forceinline__ void cta_store_tiled(double* __restrict__ out, int len, const double* v, int p) {
+  if ((reinterpret_cast<uintptr_t>(out) & 15u) == 0 && p >= 2) {
+    const int pairs = len >> 1;
+    int r = (2 * threadIdx.x) % p;
+    const int step = (2 * kThreads) % p;
+    double2* out2 = reinterpret_cast<double2*>(out);
+    for (int i = threadIdx.x; i < pairs; i += kThreads) {
+      const int r1 = (r + 1 == p) ? 0 : r + 1;
+      __stcs(out2 + i, make_double2(v[r], v[r1]));
+      r += step;
+      if (r >= p) r -= p;
+    }
+    if ((len & 1) && threadIdx.x == 0) __stcs(out + len - 1, v[(len - 1) % p]);
+    return;
+  }
   int r = threadIdx.x % p;
   const int step = kThreads % p;
   for (int n = threadIdx.x; n < len; n += kThreads) {
