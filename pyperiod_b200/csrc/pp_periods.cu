@@ -4,7 +4,7 @@
 // One CTA owns one window at a time: the window is staged once into shared memory by a TMA
 // bulk copy, every sweep / projection / residual update happens there, and only the compact
 // periods / powers (and, on request, the bases) go back to HBM.  The grid is persistent:
-// 2 CTAs per SM x SM count, looping over windows.
+// 2 CTAs per SM x SM count, windows handed out through a global counter (WindowQueue).
 #include <cuda_runtime.h>
 #include <stdio.h>
 #include <string.h>

@@ -7,19 +7,23 @@
 // numpy uses -- so MAXABS metrics are bit-exact; energies agree with the reference's BLAS norm to
 // a few ulp.
 //
-// Two tiles per period.  With M = floor(N/p) and rr = N - M p, residues r < rr have M+1 terms and
-// the others M.  Register tiles never straddle rr: tile A = [0, rr) runs M+1 rows, tile B = [rr, p)
+// Direct fold: two tiles per period.  With M = floor(N/p) and rr = N - M p, residues r < rr have M+1 terms
+// and the others M.  Register tiles never straddle rr: tile A = [0, rr) runs M+1 rows, tile B = [rr, p)
 // runs M rows (so the zero padding of the last row is never read), and the energy needs no per-lane
 // count logic:  E = T/M + (1/(M+1) - 1/M) * T_A  with T the plain sum of squares.
 //
 // Hierarchical fold (ranking sweeps only).  Only the "top" periods q in (pmax/2, pmax] are folded
 // from the window; S_p for every smaller candidate follows from S_2p[r] + S_2p[r + p].  A top
 // q = g * 2^L (L <= 3) is folded at base period g with 2^L accumulator sets selected by
-// (row mod 2^L); pairwise in-register adds give q/2 .. g, and if g is still even the chain goes on
-// through a small per-warp scratch.  Because g divides every level period, the boundary in the base
-// residue (rr = N mod g) below which a residue has one more term is the same for all levels; a level
-// only differs in how many sets hold one more complete row.  Half the shared-memory traffic of the
-// direct sweep; sums differ from the sequential ones by rounding only.
+// (row - M0) mod 2^L (so the partial tail row always lands in set 0 and one code path covers the
+// whole residue range); pairwise in-register adds give q/2 .. g, and if g is still even the chain
+// goes on through a small per-warp scratch.  Tops that are 3/2 or 3/4 of an even top ride on its pass
+// (3 * 2^L sets).  Sums differ from the sequential ones by rounding only.
+//
+// Nomination + verification.  Where the reference's result depends on bit-exact sums (MAXABS of
+// best-correlation) or the ranking runs in float (optional), the hierarchical pass only nominates:
+// every candidate whose error bound reaches the best one is folded sequentially in fp64 and ranked with
+// the reference's rule (cta_sweep).
 //
 // Candidates are ranked by the squared metric (energy, or energy / p compared by cross
 // multiplication); the square root and divisions are taken once, for the winner.
