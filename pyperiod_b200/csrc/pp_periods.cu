@@ -612,7 +612,12 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
         double* dst = bases_out + ((size_t)b * num + i) * N;
         const int P = sm.periods[i];
         if (status == PP_STATUS_OK && P > 0) {
-          cta_store_tiled(dst, N, my_slots + (size_t)sm.slot[i] * pl.pv, P);
+          // the residual is dead: stage the one-period basis in shared memory, then stream its tiling out
+          const double* sl = my_slots + (size_t)sm.slot[i] * pl.pv;
+          __syncthreads();
+          for (int r = threadIdx.x; r < P; r += kThreads) sm.xs[r] = sl[r];
+          __syncthreads();
+          cta_store_tiled(dst, N, sm.xs, P);
         } else {
           for (int n = threadIdx.x; n < N; n += kThreads) __stcs(dst + n, 0.0);
         }
