@@ -57,10 +57,13 @@ def main():
     dadd_peak = _lib.microbench(1)["per_s"]
     dmma_peak = _lib.microbench(2)["per_s"]
 
-    def timed(fn, reps=2, warm=3):
-        for _ in range(warm):        # clocks, allocator and the first launches settle
+    def timed(fn, reps=2, warm=3, warm_seconds=1.5):
+        # clocks (the GPU idles during the CPU legs), allocator and the first launches settle
+        t_start, n = time.perf_counter(), 0
+        while n < warm or time.perf_counter() - t_start < warm_seconds:
             fn()
-        torch.cuda.synchronize()
+            torch.cuda.synchronize()
+            n += 1
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(reps):
