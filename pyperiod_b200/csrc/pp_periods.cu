@@ -286,6 +286,10 @@ __device__ __forceinline__ double warp_slot_factor_norm(const double* slot, int 
   return sqrt(warp_sum(e)) / sqrtN;
 }
 
+// F32: the instance that carries the float-nomination sweep (PP_FOLD_NOMINATE_F32); the default instance does not
+// (code that is compiled in but never reached still cost 3 % through layout and register allocation)
+// PLAIN: neither trunc nor orth (the reference's default mode): those branches are compiled out.
+template <bool F32, bool PLAIN>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm)
 mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, int pmin, int pmax, int gamma,
              int trunc_i, int orth_i, int hier, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
@@ -295,7 +299,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
   unsigned char* smem_raw = pp_smem;
   const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0, f32 != 0);
   Smem sm(smem_raw, pl);
-  const bool trunc = trunc_i != 0, orth = orth_i != 0;
+  const bool trunc = !PLAIN && trunc_i != 0, orth = !PLAIN && orth_i != 0;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const double sqrtN = sqrt((double)N);
   double* my_slots = ws_slots + (size_t)blockIdx.x * num * pl.pv;
@@ -375,7 +379,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     const int guard = 12 * (pmax - pmin + 2) + 12 * num;
     while (true) {
       if (misc[0] >= num || misc[4] != PP_STATUS_OK) break;  // uniform: read after a barrier
-      const SweepResult top = cta_sweep<kSweepHier | kSweepF32>(sm.sweep);
+      const SweepResult top = cta_sweep<kSweepHier | (F32 ? kSweepF32 : 0) | (PLAIN ? kSweepPlain : 0)>(sm.sweep);
       ++sweeps;
       { const long long t = clock64(); t_sweep += t - t_mark; t_mark = t; }
       if (top.p == 0 || sweeps > guard) {
@@ -998,7 +1002,9 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   const int hier = hier_applies(gamma ? PP_METRIC_GAMMA : PP_METRIC_NORM, trunc, orth) ? 1 : 0;
   const int f32 = (hier && g_fold_mode == PP_FOLD_NOMINATE_F32) ? 1 : 0;
   const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0, f32 != 0);
-  if (int rc = prep_kernel(mbest_kernel, pl.bytes(), f)) return rc;
+  const bool plain = !trunc && !orth;
+  auto kernel = f32 ? mbest_kernel<true, true> : (plain ? mbest_kernel<false, true> : mbest_kernel<false, false>);
+  if (int rc = prep_kernel(kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B);
   size_t off = 0;
   double* keys = f32 ? carve(workspace, workspace_bytes, off, (size_t)grid * (pmax + 2) * 8) : nullptr;
@@ -1017,7 +1023,7 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
     ntops = build_hier_jobs(N, pmin, pmax, tops, (cudaStream_t)stream);
   }
   Tables tb{chain_off, chain_q, fac_off, fac};
-  mbest_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,
+  kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,
                                                                      hier, tb, periods, powers, bases, sweeps, status,
                                                                      slots, scr, tops, ntops, next_window, g_prof, f32, keys);
   return check_cuda(cudaGetLastError(), "mbest_kernel launch");

@@ -1269,6 +1269,7 @@ __device__ __forceinline__ void sweep_shared_init(SweepShared* sh) {
 constexpr int kSweepHier = 1;        // fp64 hierarchical NORM / GAMMA ranking
 constexpr int kSweepHierMaxAbs = 2;  // hierarchical MAXABS nomination + exact verification
 constexpr int kSweepF32 = 4;         // float nomination + exact verification
+constexpr int kSweepPlain = 8;       // the caller never sweeps with trunc / orth / MAXABS / IMPOSED: energy folds only
 template <int FEAT>
 static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   const SweepParams* sp = &sh->params;
@@ -1398,7 +1399,7 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
         const int hp = *reinterpret_cast<volatile int*>(&sh->hit_p);
         if (p > hp) break;
       }
-      const double key = warp_period_key_any(sp, p);
+      const double key = (FEAT & kSweepPlain) != 0 ? warp_period_key<kPassEnergy>(sp, p) : warp_period_key_any(sp, p);
       if (first_hit) {
         if (rc.metric_out != nullptr && lane == 0) rc.metric_out[p] = key;
         if (key > thresh) {
