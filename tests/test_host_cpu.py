@@ -105,3 +105,74 @@ def test_gcds_extracted_layout_matches_oracle_and_golden():
         lay = gcds_extracted_layout(q)
         _, ref = oq.get_subspaces_gcds_extracted(q, 200)
         assert list(lay.items()) == list(ref.items())
+
+
+def _job_cover(pmin, pmax):
+    """Independent restatement of the hierarchical job table (pp_sweep.cuh: hier_level, hier_rider_of): returns
+    (jobs, how often each candidate period is evaluated)."""
+    from collections import Counter
+
+    def ctz(v):
+        c = 0
+        while v % 2 == 0 and c < 30:
+            v //= 2
+            c += 1
+        return c
+
+    lo = max(pmin, (pmax >> 1) + 1)
+
+    def level(t):
+        lv = min(ctz(t), 3)
+        while lv > 0 and (t >> lv) < pmin:
+            lv -= 1
+        return lv
+
+    def rider_of(q):
+        lv = level(q)
+        if lv < 1 or lv > 2 or ctz(q) != lv:
+            return 0
+        if 3 * q <= 2 * pmax:
+            r = 3 * q // 2
+        elif lv == 2:
+            r = 3 * q // 4
+        else:
+            return 0
+        if r < lo or r > pmax or level(r) != ctz(r):
+            return 0
+        return r
+
+    riders = {rider_of(q) for q in range(lo, pmax + 1)} - {0}
+    seen, jobs = Counter(), 0
+    for q in range(lo, pmax + 1):
+        if q in riders:
+            continue
+        jobs += 1
+        lv, g = level(q), q >> level(q)
+        for i in range(lv + 1):
+            seen[g << i] += 1
+        if rider_of(q):
+            for i in range(lv):
+                p = (3 * g) << i
+                if pmin <= p <= pmax:
+                    seen[p] += 1
+        if lv == 3:
+            h = g
+            while h % 2 == 0 and (h >> 1) >= pmin:
+                h >>= 1
+                seen[h] += 1
+    return jobs, seen
+
+
+def test_hierarchical_job_table_covers_every_candidate_once(lib_path):
+    """Host mirror of the job table: pp_sweep_passes equals an independent restatement, and that restatement
+    evaluates every candidate period exactly once (hosts, riders, chains)."""
+    from pyperiod_b200 import _lib
+    lib = _lib.load()
+    assert lib.pp_get_fold_mode() == _lib.FOLD_HIERARCHICAL
+    for pmin, pmax in [(2, 1024), (2, 1365), (2, 300), (2, 682), (5, 64), (40, 64), (2, 2729), (3, 999), (17, 1000),
+                       (2, 100), (2, 7), (600, 1024)]:
+        jobs, seen = _job_cover(pmin, pmax)
+        assert _lib.sweep_passes(pmin, pmax) == jobs, (pmin, pmax)
+        assert all(seen[p] == 1 for p in range(pmin, pmax + 1)), (pmin, pmax)
+        assert all(pmin <= p <= pmax for p in seen), (pmin, pmax)
+    assert _lib.sweep_passes(2, 1024) == 405
