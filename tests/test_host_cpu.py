@@ -176,3 +176,30 @@ def test_hierarchical_job_table_covers_every_candidate_once(lib_path):
         assert all(seen[p] == 1 for p in range(pmin, pmax + 1)), (pmin, pmax)
         assert all(pmin <= p <= pmax for p in seen), (pmin, pmax)
     assert _lib.sweep_passes(2, 1024) == 405
+
+
+def test_float_nomination_error_bound_holds():
+    """The bound behind PP_FOLD_NOMINATE_F32 (pp_sweep.cuh: f32_energy_tol): |float energy - fp64 energy| of a
+    candidate never exceeds 2 (2 ceil(N/p) + 40) 2^-24 sum x^2 (numpy emulation of a float fold)."""
+    from pyperiod_b200 import synth
+    n, u = 4096, 2.0 ** -24
+    worst = 0.0
+    for seed in range(2):
+        x = synth.synth(n, 31_000 + seed)
+        e_res = float((x * x).sum())
+        xf = x.astype(np.float32)
+        for p in list(range(2, 1025, 29)) + [2, 3, 5, 1023, 1024]:
+            idx = np.arange(n) % p
+            cnt = np.bincount(idx, minlength=p).astype(np.float64)
+            s64 = np.bincount(idx, weights=x, minlength=p)
+            e64 = float((s64 * s64 / cnt).sum())
+            s32 = np.zeros(p, np.float32)
+            m = n // p
+            for k in range(m):
+                s32 += xf[k * p:(k + 1) * p]
+            if n - m * p:
+                s32[: n - m * p] += xf[m * p:]
+            e32 = float(((s32 * s32).astype(np.float64) / cnt).sum())
+            tol = 2.0 * (2.0 * ((n + p - 1) // p) + 40.0) * u * e_res
+            worst = max(worst, abs(e32 - e64) / tol)
+    assert worst < 0.1, worst
