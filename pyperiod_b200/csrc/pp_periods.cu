@@ -379,7 +379,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     const int guard = 12 * (pmax - pmin + 2) + 12 * num;
     while (true) {
       if (misc[0] >= num || misc[4] != PP_STATUS_OK) break;  // uniform: read after a barrier
-      const SweepResult top = cta_sweep<kSweepHier | (F32 ? kSweepF32 : 0) | (PLAIN ? kSweepPlain : 0)>(sm.sweep);
+      const SweepResult top = cta_sweep<kSweepHier | kSweepNoMetricOut | (F32 ? kSweepF32 : 0) | (PLAIN ? kSweepPlain : 0)>(sm.sweep);
       ++sweeps;
       { const long long t = clock64(); t_sweep += t - t_mark; t_mark = t; }
       if (top.p == 0 || sweeps > guard) {

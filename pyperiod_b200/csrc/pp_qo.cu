@@ -630,7 +630,7 @@ qo_find_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num,
         }
       }
       const long long t0 = clock64();
-      const SweepResult top = cta_sweep<kSweepHier>(sweep);
+      const SweepResult top = cta_sweep<kSweepHier | kSweepNoMetricOut>(sweep);
       t_sweep += clock64() - t0;
       if (tid == 0) {
         round_norms[i] = top.val;

@@ -241,8 +241,11 @@ __device__ __forceinline__ Best warp_best(int metric, Best b) {
 }
 
 // 1 / m: table for the small row counts every large period has, a real division otherwise
+// (the division is kept out of line: it is almost never taken, and an inlined DDIV sequence at every ranking site
+// costs more in code layout than the call)
+static __device__ __noinline__ double rcp_slow(int m) { return 1.0 / (double)m; }
 __device__ __forceinline__ double rcp_of(const double* rcp, int m) {
-  return m < kRcpTab ? rcp[m] : 1.0 / (double)m;
+  return m < kRcpTab ? rcp[m] : rcp_slow(m);
 }
 
 // Register tiles are deliberately small and come in exactly two shapes -- kTileCols columns for the
@@ -1270,6 +1273,8 @@ constexpr int kSweepHier = 1;        // fp64 hierarchical NORM / GAMMA ranking
 constexpr int kSweepHierMaxAbs = 2;  // hierarchical MAXABS nomination + exact verification
 constexpr int kSweepF32 = 4;         // float nomination + exact verification
 constexpr int kSweepPlain = 8;       // the caller never sweeps with trunc / orth / MAXABS / IMPOSED: energy folds only
+constexpr int kSweepNoMetricOut = 16;  // the caller never asks for per-candidate metrics (drops the sqrt / divide of
+                                       // key_to_value from every ranking site)
 template <int FEAT>
 static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   const SweepParams* sp = &sh->params;
@@ -1279,7 +1284,9 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
     sh->hit_p = 0x7fffffff;
   }
   __syncthreads();  // also publishes params written by thread 0 just before the call
-  const RankCtx rc = rank_ctx(sp);
+  RankCtx rc_init = rank_ctx(sp);
+  if constexpr ((FEAT & kSweepNoMetricOut) != 0) rc_init.metric_out = nullptr;
+  const RankCtx rc = rc_init;
   const int metric = rc.metric;
   const int pmin = sp->pmin, pmax = sp->pmax;
   const double thresh = sp->thresh;
