@@ -277,7 +277,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         # passes/(Pmax-1) of the canonical figure; both are reported so the algorithmic saving is visible
         # rather than hidden.
         adds_per_launch = (sweeps_all / world) * (PMAX - 1) * N_WIN
-        passes = _lib.sweep_passes(2, PMAX)   # window passes per sweep actually executed (tops minus riders)
+        passes = _lib.sweep_passes(N_WIN, 2, PMAX)   # window passes per sweep actually executed (tops minus riders)
         exec_adds_per_launch = (sweeps_all / world) * passes * N_WIN
         launch_s = secs / args.steps
         smem_bps = adds_per_launch * 8 / launch_s

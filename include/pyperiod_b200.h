@@ -79,9 +79,9 @@ const char *pp_last_error(void);
 #define PP_FOLD_NOMINATE_F32 3
 int pp_set_fold_mode(int32_t mode);
 int pp_get_fold_mode(void);
-/* Passes over the window one ranking sweep of [pmin, pmax] executes under the current fold mode
+/* Passes over a window of N samples one ranking sweep of [pmin, pmax] executes under the current fold mode
  * (pmax - pmin + 1 for PP_FOLD_DIRECT; tops minus riders for PP_FOLD_HIERARCHICAL). */
-int pp_sweep_passes(int32_t pmin, int32_t pmax);
+int pp_sweep_passes(int32_t N, int32_t pmin, int32_t pmax);
 
 /* Development aid: when set to a device buffer of 8 uint64, pp_mbest adds per-window SM-cycle
  * counts to it: [0] sweeps, [1] exact winner projections, [2] bookkeeping + residual update,

@@ -31,7 +31,7 @@ SIGNATURES = {
     "pp_last_error": (C.c_char_p, []),
     "pp_set_fold_mode": (C.c_int, [_i32]),
     "pp_get_fold_mode": (C.c_int, []),
-    "pp_sweep_passes": (C.c_int, [_i32, _i32]),
+    "pp_sweep_passes": (C.c_int, [_i32, _i32, _i32]),
     "pp_set_profile_buffer": (C.c_int, [_p]),
     "pp_get_profile_buffer": (C.c_void_p, []),
     "pp_device_info": (C.c_int, [_p, _p, _p, _p, _p]),
@@ -101,9 +101,9 @@ def set_fold_mode(mode: int):
     check(load().pp_set_fold_mode(int(mode)), "pp_set_fold_mode")
 
 
-def sweep_passes(pmin: int, pmax: int) -> int:
-    """Passes over the window per ranking sweep under the current fold mode."""
-    return int(load().pp_sweep_passes(int(pmin), int(pmax)))
+def sweep_passes(n: int, pmin: int, pmax: int) -> int:
+    """Passes over a window of n samples per ranking sweep under the current fold mode."""
+    return int(load().pp_sweep_passes(int(n), int(pmin), int(pmax)))
 
 
 def microbench(kind: int, iters: int = 4000) -> dict:

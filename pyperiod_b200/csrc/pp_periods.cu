@@ -854,10 +854,10 @@ int pp_set_fold_mode(int32_t mode) {
   return 0;
 }
 int pp_get_fold_mode(void) { return g_fold_mode; }
-int pp_sweep_passes(int32_t pmin, int32_t pmax) {
+int pp_sweep_passes(int32_t N, int32_t pmin, int32_t pmax) {
   if (pmax < pmin) return 0;
   if (g_fold_mode == PP_FOLD_DIRECT) return pmax - pmin + 1;
-  return hier_job_count(pmin, pmax, g_fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS);
+  return hier_job_count(N, pmin, pmax, g_fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS);
 }
 int pp_set_profile_buffer(void* dev_u64x8) {
   g_prof = reinterpret_cast<unsigned long long*>(dev_u64x8);

@@ -517,23 +517,31 @@ __device__ __forceinline__ void hier_accumulate(const double* __restrict__ xs, i
       ptr += g;
     }
   } else {
+    // the first complete group of S rows (rows head .. head + S - 1) initialises the sets, the other groups add,
+    // the `head` rows before the first group (sets S - head .. S - 1) come last: no zero fill, no add to zero
+    // (every job has at least one complete group: plain tops have N / g >= 2^L, riders are only formed when
+    // N / g >= 3 * 2^L, see hier_rider_of)
+    const double* hptr = ptr;
+    ptr += head * g;
 #pragma unroll
-    for (int s = 0; s < S; ++s)
+    for (int s = 0; s < S; ++s) {
 #pragma unroll
-      for (int j = 0; j < J; ++j) acc[s][j] = 0.0;
-#pragma unroll
-    for (int s = 1; s < S; ++s) {  // rows before the first complete group of S
-      if (s >= S - head) {
-        add_row<J>(acc[s], ptr);
-        ptr += g;
-      }
+      for (int j = 0; j < J; ++j) acc[s][j] = ptr[32 * j];
+      ptr += g;
     }
 #pragma unroll 1
-    for (int i = groups; i > 0; --i) {
+    for (int i = groups - 1; i > 0; --i) {
 #pragma unroll
       for (int s = 0; s < S; ++s) {
         add_row<J>(acc[s], ptr);
         ptr += g;
+      }
+    }
+#pragma unroll
+    for (int s = 1; s < S; ++s) {
+      if (s >= S - head) {
+        add_row<J>(acc[s], hptr);
+        hptr += g;
       }
     }
   }
@@ -1149,10 +1157,11 @@ __host__ __device__ inline int hier_level(int t, int pmin) {
   return L;
 }
 // the top that rides on host q, or 0
-__host__ __device__ inline int hier_rider_of(int q, int pmin, int pmax, bool riders) {
+__host__ __device__ inline int hier_rider_of(int N, int q, int pmin, int pmax, bool riders) {
   if (!riders) return 0;
   const int L = hier_level(q, pmin);
   if (L < 1 || L > 2 || hier_ctz(q) != L) return 0;  // host classes: q = 2 g or 4 g, g odd
+  if (N / (q >> L) < (3 << L)) return 0;             // fewer rows than accumulator sets: no complete group
   int R;
   if (3 * q <= 2 * pmax) R = 3 * q / 2;
   else if (L == 2) R = 3 * q / 4;
@@ -1164,13 +1173,13 @@ __host__ __device__ inline int hier_rider_of(int q, int pmin, int pmax, bool rid
 constexpr int kHierRiderMaxTops = 4096;  // rider matching runs in one CTA with two ints of shared memory per top
 
 // number of jobs the table will hold (host-side mirror of tops_kernel)
-inline int hier_job_count(int pmin, int pmax, bool riders) {
+inline int hier_job_count(int N, int pmin, int pmax, bool riders) {
   const int n = hier_top_count(pmin, pmax);
   if (!riders || n > kHierRiderMaxTops) return n;
   const int lo = hier_top_lo(pmin, pmax);
   int jobs = n;
   for (int q = lo; q <= pmax; ++q)
-    if (hier_rider_of(q, pmin, pmax, true)) --jobs;
+    if (hier_rider_of(N, q, pmin, pmax, true)) --jobs;
   return jobs;
 }
 
@@ -1182,7 +1191,7 @@ static __global__ void tops_kernel(int N, int pmin, int pmax, int riders, uint2*
   int* rider = tk_smem;      // rider[t - lo]: the top riding on t (0: none)
   int* cls = tk_smem + n;    // cls[t - lo]: hand-out class of t, -1 if t rides on another top
   for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    rider[i] = hier_rider_of(lo + i, pmin, pmax, riders != 0);
+    rider[i] = hier_rider_of(N, lo + i, pmin, pmax, riders != 0);
     cls[i] = 0;
   }
   __syncthreads();
@@ -1217,7 +1226,7 @@ inline int build_hier_jobs(int N, int pmin, int pmax, uint2* tops, cudaStream_t 
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(tops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   tops_kernel<<<1, 512, smem, stream>>>(N, pmin, pmax, riders ? 1 : 0, tops);
-  return hier_job_count(pmin, pmax, riders);
+  return hier_job_count(N, pmin, pmax, riders);
 }
 
 template <bool MAXABS>

@@ -107,7 +107,7 @@ def test_gcds_extracted_layout_matches_oracle_and_golden():
         assert list(lay.items()) == list(ref.items())
 
 
-def _job_cover(pmin, pmax):
+def _job_cover(n, pmin, pmax):
     """Independent restatement of the hierarchical job table (pp_sweep.cuh: hier_level, hier_rider_of): returns
     (jobs, how often each candidate period is evaluated)."""
     from collections import Counter
@@ -129,7 +129,7 @@ def _job_cover(pmin, pmax):
 
     def rider_of(q):
         lv = level(q)
-        if lv < 1 or lv > 2 or ctz(q) != lv:
+        if lv < 1 or lv > 2 or ctz(q) != lv or n // (q >> lv) < (3 << lv):
             return 0
         if 3 * q <= 2 * pmax:
             r = 3 * q // 2
@@ -169,13 +169,15 @@ def test_hierarchical_job_table_covers_every_candidate_once(lib_path):
     from pyperiod_b200 import _lib
     lib = _lib.load()
     assert lib.pp_get_fold_mode() == _lib.FOLD_HIERARCHICAL
-    for pmin, pmax in [(2, 1024), (2, 1365), (2, 300), (2, 682), (5, 64), (40, 64), (2, 2729), (3, 999), (17, 1000),
-                       (2, 100), (2, 7), (600, 1024)]:
-        jobs, seen = _job_cover(pmin, pmax)
-        assert _lib.sweep_passes(pmin, pmax) == jobs, (pmin, pmax)
+    for n, pmin, pmax in [(4096, 2, 1024), (4096, 2, 1365), (2000, 2, 300), (4096, 2, 682), (512, 5, 64), (128, 40, 64),
+                          (8192, 2, 2729), (3001, 3, 999), (2000, 17, 1000), (1000, 17, 500), (300, 2, 100),
+                          (64, 2, 7), (4096, 600, 1024), (1024, 2, 512)]:
+        jobs, seen = _job_cover(n, pmin, pmax)
+        assert _lib.sweep_passes(n, pmin, pmax) == jobs, (n, pmin, pmax)
         assert all(seen[p] == 1 for p in range(pmin, pmax + 1)), (pmin, pmax)
         assert all(pmin <= p <= pmax for p in seen), (pmin, pmax)
-    assert _lib.sweep_passes(2, 1024) == 405
+    assert _lib.sweep_passes(4096, 2, 1024) == 405
+    assert _lib.sweep_passes(1000, 17, 500) > _lib.sweep_passes(4096, 17, 500)   # short windows: fewer riders
 
 
 def test_float_nomination_error_bound_holds():

@@ -133,7 +133,7 @@ def main():
                        "frac": B * canon / t / smem_peak,
                        "algorithmic": "10 rounds x 2728 periods x 8192 sequential adds x 8 B (canonical); executed: hierarchical "
                                       "nomination (%d passes per round) + exact sequential folds of the near-maximal "
-                                      "candidates" % _lib.sweep_passes(2, 2729)},
+                                      "candidates" % _lib.sweep_passes(8192, 2, 2729)},
           "cpu_baseline": cpu(_cpu_bcorr, base, 40, "oracle best_correlation(num=10, trunc, orth)")})
 
     # config 5a: QOPeriods.find_periods(num=4, thresh=0.05), N=4096 (65,536 windows in the config; a slice here)
