@@ -60,6 +60,15 @@ PIPELINE_PIECES = 8
 _copy_streams: dict = {}
 
 
+def pipeline_bounds(b: int, pieces: int = None) -> list:
+    """[(first window, end window)] of the upload pieces of a b-window batch: a small first piece (the first kernel
+    starts after ~1 ms of PCIe traffic), then `pieces` equal ones."""
+    pieces = PIPELINE_PIECES if pieces is None else pieces
+    per = -(-b // pieces)
+    first = max(1, per // 4)
+    return [(0, min(b, first))] + [(b0, min(b, b0 + per)) for b0 in range(first, b, per)]
+
+
 def _pipelined_upload(host_flat: torch.Tensor, b: int, n: int, hop: int, dev: torch.device) -> Windows:
     """Upload a host sample stream in pieces on a side stream; window chunk k may be launched as soon as
     its piece has landed, so the PCIe copy of piece k+1 overlaps the kernel on piece k."""
@@ -71,9 +80,7 @@ def _pipelined_upload(host_flat: torch.Tensor, b: int, n: int, hop: int, dev: to
         cs = _copy_streams[str(dev)] = torch.cuda.Stream(dev)
     cs.wait_stream(cur)              # the allocation point of dflat is on the current stream
     dflat.record_stream(cs)
-    per = -(-b // PIPELINE_PIECES)
-    first = max(1, per // 4)  # a small first piece: the first kernel starts after ~1 ms of PCIe traffic
-    bounds = [(0, min(b, first))] + [(b0, min(b, b0 + per)) for b0 in range(first, b, per)]
+    bounds = pipeline_bounds(b)
 
     def copy_piece(k):
         b0, b1 = bounds[k]

@@ -205,3 +205,14 @@ def test_float_nomination_error_bound_holds():
             tol = 2.0 * (2.0 * ((n + p - 1) // p) + 40.0) * u * e_res
             worst = max(worst, abs(e32 - e64) / tol)
     assert worst < 0.1, worst
+
+
+def test_pipeline_bounds_partition_the_batch():
+    """Upload pieces of the pipelined host path (pyperiod_b200/_device.py) tile [0, B) without gaps or overlap."""
+    from pyperiod_b200._device import pipeline_bounds
+    for b in (1, 2, 7, 16384, 16385, 131072, 1_000_003):
+        bounds = pipeline_bounds(b)
+        assert bounds[0][0] == 0 and bounds[-1][1] == b
+        assert all(lo < hi for lo, hi in bounds)
+        assert all(bounds[i][1] == bounds[i + 1][0] for i in range(len(bounds) - 1))
+        assert len(bounds) <= 10
