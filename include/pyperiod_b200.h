@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 1
+#define PP_ABI_VERSION 2
 
 /* sweep metrics */
 #define PP_METRIC_NORM 0   /* ||proj_p|| / sqrt(N)                 Periods.py:221-241, 507-508 */
@@ -72,24 +72,21 @@ const char *pp_last_error(void);
  *       traffic), then folds every candidate whose error bound reaches the best one sequentially in fp64:
  *       the selected periods and norms are those of the exact fold.
  * Outputs that must be bit-exact (project(), the bases, MAXABS metrics) never use the
- * hierarchical sums.  Process-wide setting. */
+ * hierarchical sums.  The mode is an argument of every call that sweeps (`fold_mode`): the library keeps no
+ * process-wide state, so calls on different streams / threads do not influence each other. */
 #define PP_FOLD_HIERARCHICAL 0
 #define PP_FOLD_DIRECT 1
 #define PP_FOLD_HIERARCHICAL_NO_RIDERS 2
 #define PP_FOLD_NOMINATE_F32 3
-int pp_set_fold_mode(int32_t mode);
-int pp_get_fold_mode(void);
-/* Passes over a window of N samples one ranking sweep of [pmin, pmax] executes under the current fold mode
+/* Passes over a window of N samples one ranking sweep of [pmin, pmax] executes under `fold_mode`
  * (pmax - pmin + 1 for PP_FOLD_DIRECT; tops minus riders for PP_FOLD_HIERARCHICAL). */
-int pp_sweep_passes(int32_t N, int32_t pmin, int32_t pmax);
+int pp_sweep_passes(int32_t N, int32_t pmin, int32_t pmax, int32_t fold_mode);
 
-/* Development aid: when set to a device buffer of 8 uint64, pp_mbest adds per-window SM-cycle
- * counts to it: [0] sweeps, [1] exact winner projections, [2] bookkeeping + residual update,
- * [3] step 2 + outputs, [4] windows.  pp_qo_find_periods adds: [0] sweeps, [1] dictionary layout,
- * [2] W + Gram build, [3] Cholesky, [5] solves + reconstruction, [4] windows.
- * Pass NULL to disable (default). */
-int pp_set_profile_buffer(void *dev_u64x8);
-void *pp_get_profile_buffer(void);
+/* `profile` arguments (development aid, nullable): a device buffer of 8 uint64 to which the call adds
+ * SM-cycle counts.  pp_mbest: [0] sweeps, [1] exact winner projections, [2] bookkeeping + residual update,
+ * [3] step 2 + outputs, [4] windows.  pp_qo_find_periods: [0] sweeps, [1] dictionary layout, [2] right-hand
+ * side + pair tables, [3] Cholesky factorisation (tensor cores), [5] triangular solves + reconstruction (+
+ * refinement), [4] windows. */
 
 /* Device facts the host uses for grid sizing / roofline arithmetic (current device). */
 int pp_device_info(int32_t *sm_count, int32_t *smem_optin_bytes, int32_t *cc_major, int32_t *cc_minor,
@@ -127,18 +124,22 @@ int pp_periodic_norm(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t
  * when no metric is positive.  PP_METRIC_IMPOSED is evaluated against the window itself
  * as both residual and data (thresholding is done by pp_small_to_large). */
 int pp_sweep(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, int32_t pmax, int32_t metric,
-             int32_t trunc, int32_t orth, const int32_t *chain_off, const int32_t *chain_q, int32_t table_pmax,
-             double *metric_out, int32_t *best_p, double *best_val, void *workspace, size_t workspace_bytes,
-             void *stream);
+             int32_t trunc, int32_t orth, int32_t fold_mode, const int32_t *chain_off, const int32_t *chain_q,
+             int32_t table_pmax, double *metric_out, int32_t *best_p, double *best_val, void *workspace,
+             size_t workspace_bytes, void *stream);
 
 /* ---- Periods.m_best / m_best_gamma (Periods.py:408-601) -------------------------------
  * periods[B,num] u32, powers[B,num] f64, bases[B,num,N] f64 (nullable: bases stay on chip /
- * in the workspace), sweeps[B] = step-1 sweeps executed (nullable), status[B]. */
+ * in the workspace), sweeps[B] = step-1 sweeps executed (nullable), status[B].
+ * near_ties[B] (nullable) = number of step-1 sweeps in which more than one candidate lay within the rounding
+ * bound of the best ranking value; those sweeps are decided by the exact re-ranking (sequential fold, IEEE
+ * mean, fixed-order sum of squares of the tiled base, strict '>' in ascending p -- Periods.py:507-515), so the
+ * selected period does not depend on the fold mode.  On inputs with a noise floor it is 0. */
 int pp_mbest(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t num, int32_t pmin, int32_t pmax,
-             int32_t gamma, int32_t trunc, int32_t orth, const int32_t *chain_off, const int32_t *chain_q,
-             const int32_t *fac_off, const int32_t *fac, int32_t table_pmax, uint32_t *periods, double *powers,
-             double *bases, int32_t *sweeps, int32_t *status, void *workspace, size_t workspace_bytes,
-             void *stream);
+             int32_t gamma, int32_t trunc, int32_t orth, int32_t fold_mode, const int32_t *chain_off,
+             const int32_t *chain_q, const int32_t *fac_off, const int32_t *fac, int32_t table_pmax,
+             uint32_t *periods, double *powers, double *bases, int32_t *sweeps, int32_t *near_ties,
+             int32_t *status, void *workspace, size_t workspace_bytes, void *profile, void *stream);
 
 /* ---- Periods.small_to_large (Periods.py:246-287) --------------------------------------
  * p runs 2..n_periods; periods[B,kmax] u32, powers[B,kmax], bases[B,kmax,N] (nullable),
@@ -156,7 +157,7 @@ int pp_small_to_large(const double *x, int64_t ldx, int32_t B, int32_t N, double
  * (bit-identical results, about twice as fast); with workspace == NULL every candidate is folded
  * sequentially. */
 int pp_best_correlation(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t num, int32_t max_length,
-                        double ratio, int32_t trunc, int32_t orth, const int32_t *chain_off,
+                        double ratio, int32_t trunc, int32_t orth, int32_t fold_mode, const int32_t *chain_off,
                         const int32_t *chain_q, int32_t table_pmax, uint32_t *periods, double *powers,
                         double *bases, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 
@@ -164,39 +165,61 @@ int pp_best_correlation(const double *x, int64_t ldx, int32_t B, int32_t N, int3
  * Per window up to `num` rounds: gamma-norm sweep of the residual over [pmin, pmax]
  * (trunc = the instance's trunc_to_integer_multiple, orthogonalize False, :470-478); dictionary
  * rows per period = sum of phi over newly seen divisors (:830-840, a repeated period gets 0 and
- * then contributes all its rows, :972); normal equations against the ORIGINAL data solved by
- * Cholesky (reference: LU, np.linalg.solve); residual = data - reconstruction; stop when
- * rms(reconstruction) <= rms(data) * thresh (:391), in which case the last period is not
- * reported (:585-588).  A non-positive pivot (reference: LinAlgError) or more than rmax rows keeps
- * the previous round's outputs (status PP_STATUS_SINGULAR / PP_STATUS_TOO_LARGE).
+ * then contributes all its rows, :972); normal equations against the ORIGINAL data (:781-794);
+ * residual = data - reconstruction; stop when rms(reconstruction) <= rms(data) * thresh (:391), in
+ * which case the last period is not reported (:585-588).
+ *
+ * Normal equations.  G = A A^T is integer valued and never stored: its entries have a closed form
+ * (Chinese remainder theorem) evaluated where the factorisation consumes them.  The Cholesky factor
+ * (reference: LU, np.linalg.solve) is computed left-looking on the FP64 tensor cores (mma.sync m8n8k4,
+ * SASS DMMA), packed by block rows, for ANY number of dictionary rows R <= N; `refine` steps of
+ * iterative refinement with the implicit Gram product (W - G w = A (x - A^T w): a fold of the signal
+ * residual) follow.  R > N makes the system singular by rank (status PP_STATUS_SINGULAR, as a
+ * non-positive pivot does: the reference raises LinAlgError or returns rounding noise there); a window
+ * with R > rmax reports PP_STATUS_TOO_LARGE (rows needed in n_weights) and keeps the previous round's
+ * outputs, so the caller can re-run just those windows (`order`) with a larger rmax.
+ *
+ * Workspace: pp_qo_workspace_bytes(N, pmax, num, rmax, ctas) holds the factors of `ctas` concurrent windows
+ * (0 = one per CTA of the full persistent grid); a smaller workspace only lowers the number of CTAs launched.
+ * order (nullable): n_order window indices to process instead of all B (outputs stay indexed by window).
  * phi: device int32 table of Euler's totient for 0..table_pmax.
  * Outputs: periods u32[B,num] (found order, duplicates possible), norms f64[B,num], n_periods[B];
- * dictionary dict_q/dict_keep i32[B,num] in insertion order with n_dict[B]; weights f64[B,rmax]
- * with n_weights[B]; res f64[B,N] (nullable); status[B]. */
-size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax);
+ * dictionary dict_q/dict_keep i32[B,num] in insertion order with n_dict[B]; weights f64[B,ldw]
+ * (ldw >= rmax rounded up to 32) with n_weights[B]; res f64[B,N] (nullable); status[B]. */
+size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax, int32_t ctas);
 int pp_qo_find_periods(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t num, double thresh,
-                       int32_t pmin, int32_t pmax, int32_t trunc, const int32_t *phi, int32_t table_pmax,
-                       int32_t rmax, uint32_t *periods, double *norms, int32_t *n_periods, int32_t *dict_q,
-                       int32_t *dict_keep, int32_t *n_dict, int32_t *n_weights, double *weights, double *res,
-                       int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+                       int32_t pmin, int32_t pmax, int32_t trunc, int32_t fold_mode, int32_t refine,
+                       const int32_t *phi, int32_t table_pmax, int32_t rmax, const int32_t *order,
+                       int32_t n_order, uint32_t *periods, double *norms, int32_t *n_periods, int32_t *dict_q,
+                       int32_t *dict_keep, int32_t *n_dict, int32_t *n_weights, double *weights, int64_t ldw,
+                       double *res, int32_t *status, void *workspace, size_t workspace_bytes, void *profile,
+                       void *stream);
 
 /* ---- get_subspaces + solve_quadratic for given periods (QOPeriods.py:743-852; used by
  *      RamanujanPeriods.find_periods_with_weights, RamanujanPeriods.py:106-112) ---------------
- * periods i32[B,kmax] with nper[B] valid entries each, in the caller's order. */
+ * periods i32[B,kmax] with nper[B] valid entries each, in the caller's order.  weights of window b go to
+ * weights + weights_off[b] when weights_off is given (a ragged layout sized by pp_qo_dictionary_rows),
+ * else to weights + b * ldw. */
 int pp_qo_solve(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t kmax, const int32_t *periods,
-                const int32_t *nper, int32_t pmax, const int32_t *phi, int32_t table_pmax, int32_t rmax,
-                int32_t *dict_q, int32_t *dict_keep, int32_t *n_dict, int32_t *n_weights, double *weights,
+                const int32_t *nper, int32_t pmax, int32_t refine, const int32_t *phi, int32_t table_pmax,
+                int32_t rmax, const int32_t *order, int32_t n_order, int32_t *dict_q, int32_t *dict_keep,
+                int32_t *n_dict, int32_t *n_weights, double *weights, int64_t ldw, const int64_t *weights_off,
                 double *res, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
+
+/* rows[b] = rows of the dictionary get_subspaces (QOPeriods.py:830-840) lays out for periods[b, 0:nper[b]):
+ * lets the caller size rmax, the ragged weights array and the workspace before pp_qo_solve. */
+int pp_qo_dictionary_rows(int32_t B, int32_t kmax, const int32_t *periods, const int32_t *nper, int32_t pmax,
+                          const int32_t *phi, int32_t table_pmax, int32_t *rows, void *stream);
 
 /* Solve stage for a caller-supplied dictionary layout: entry k of window b is the period dict_q[b,k] with its
  * first dict_rows[b,k] natural-basis rows (0 = all rows).  Replaces get_subspaces + solve_quadratic of the
  * QOPeriodsWithGCDsExtracted subclass (QOPeriodsWithGCDsExtracted.py:98-143, QOPeriods.py:743-805), whose
- * layout depends on CPython set order and is therefore built by the host layer.  weights[B, rmax],
+ * layout depends on CPython set order and is therefore built by the host layer.  weights[B, ldw],
  * res[B, N] (nullable), status: PP_STATUS_OK / SINGULAR / TOO_LARGE. */
 int pp_qo_solve_rows(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t kmax, const int32_t *dict_q,
-                     const int32_t *dict_rows, const int32_t *n_dict, int32_t pmax, int32_t rmax,
-                     int32_t *n_weights, double *weights, double *res, int32_t *status, void *workspace,
-                     size_t workspace_bytes, void *stream);
+                     const int32_t *dict_rows, const int32_t *n_dict, int32_t pmax, int32_t refine, int32_t rmax,
+                     int32_t *n_weights, double *weights, int64_t ldw, double *res, int32_t *status,
+                     void *workspace, size_t workspace_bytes, void *stream);
 
 /* ---- RamanujanPeriods.find_periods (RamanujanPeriods.py:67-86, 124-169) ------------------
  * norms[b, q] = sum_n (sum_i <x, r_i> r_i)[n]^2 over the q-row Ramanujan dictionary of period q,

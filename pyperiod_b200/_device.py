@@ -177,21 +177,44 @@ def stage_windows(data, device=None, pipeline: bool = False) -> Windows:
 
 
 class Workspace:
-    """Per-device growable scratch buffer handed to the library (caller-owned workspace)."""
+    """Growable scratch buffers handed to the library (caller-owned workspace), one per (device, stream, thread):
+    a launch owns its workspace until the stream has run it, so calls issued on different CUDA streams or from
+    different Python threads never share window counters, job tables or Cholesky factors."""
     _bufs: dict = {}
+    KEEP_BYTES = 1 << 30   # larger buffers are not cached (the caching allocator keeps them instead)
 
     @classmethod
     def get(cls, device: torch.device, nbytes: int) -> torch.Tensor:
-        key = str(device)
+        import threading
+        stream = torch.cuda.current_stream(device)
+        key = (str(device), int(stream.cuda_stream), threading.get_ident())
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
-            buf = torch.zeros(max(nbytes, 1 << 20), dtype=torch.uint8, device=device)
-            cls._bufs[key] = buf
+            with torch.cuda.device(device):
+                buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+            if buf.numel() <= cls.KEEP_BYTES:
+                cls._bufs[key] = buf
+            elif key in cls._bufs:
+                del cls._bufs[key]
         return buf
 
 
 def stream_ptr(device: torch.device) -> C.c_void_p:
     return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def workspace_for(device: torch.device, size_fn, *args) -> torch.Tensor:
+    """Workspace sized by one of the library's *_workspace_bytes queries (which read the current device)."""
+    with torch.cuda.device(device):
+        nbytes = int(size_fn(*args))
+    return Workspace.get(device, nbytes)
+
+
+def call(fn, what: str, device: torch.device, *args):
+    """Run one C-ABI entry point with `device` current: the library sizes its grids, sets kernel attributes and
+    launches on the CUDA runtime's current device, which must be the one that owns the pointers and the stream."""
+    with torch.cuda.device(device):
+        _lib.check(fn(*args), what)
 
 
 def ptr(t) -> C.c_void_p:

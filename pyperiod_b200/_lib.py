@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # PYPERIOD_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("PYPERIOD_B200_LIB") or os.path.join(HERE, "libpyperiod_b200.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 METRIC_NORM, METRIC_GAMMA, METRIC_MAXABS, METRIC_IMPOSED = 0, 1, 2, 3
 STATUS_OK, STATUS_NO_PERIOD, STATUS_OVERFLOW, STATUS_SINGULAR, STATUS_GUARD = 0, 1, 2, 3, 4
@@ -29,34 +29,33 @@ _sz = C.c_size_t
 SIGNATURES = {
     "pp_abi_version": (C.c_int, []),
     "pp_last_error": (C.c_char_p, []),
-    "pp_set_fold_mode": (C.c_int, [_i32]),
-    "pp_get_fold_mode": (C.c_int, []),
-    "pp_sweep_passes": (C.c_int, [_i32, _i32, _i32]),
-    "pp_set_profile_buffer": (C.c_int, [_p]),
-    "pp_get_profile_buffer": (C.c_void_p, []),
+    "pp_sweep_passes": (C.c_int, [_i32, _i32, _i32, _i32]),
     "pp_device_info": (C.c_int, [_p, _p, _p, _p, _p]),
     "pp_grid_size": (C.c_int, [_i32, _i32, _i32, _i32]),
     "pp_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "pp_project": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _p, _i64, _i32, _p]),
     "pp_periodic_norm": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p]),
-    "pp_sweep": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _sz, _p]),
-    "pp_mbest": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i32,
-                           _p, _p, _p, _p, _p, _p, _sz, _p]),
+    "pp_sweep": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _p, _sz,
+                           _p]),
+    "pp_mbest": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _p, _p, _p, _p, _i32,
+                           _p, _p, _p, _p, _p, _p, _p, _sz, _p, _p]),
     "pp_small_to_large": (C.c_int, [_p, _i64, _i32, _i32, _f64, _i32, _i32, _i32, _p, _p, _i32, _i32,
                                     _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "pp_best_correlation": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _f64, _i32, _i32, _p, _p, _i32,
+    "pp_best_correlation": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _f64, _i32, _i32, _i32, _p, _p, _i32,
                                       _p, _p, _p, _p, _p, _sz, _p]),
     "pp_microbench": (C.c_int, [_i32, _i32, _p]),
     "pp_ramanujan_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "pp_ramanujan_norms": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _p, _sz, _p]),
     "pp_ramanujan_norms_tf32": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _p, _sz, _p]),
     "pp_ramanujan_select": (C.c_int, [_p, _i32, _i32, _i32, _f64, _i32, _p, _p, _p]),
-    "pp_qo_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
-    "pp_qo_find_periods": (C.c_int, [_p, _i64, _i32, _i32, _i32, _f64, _i32, _i32, _i32, _p, _i32, _i32,
-                                     _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "pp_qo_solve": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _i32, _p, _i32, _i32,
-                              _p, _p, _p, _p, _p, _p, _p, _p, _sz, _p]),
-    "pp_qo_solve_rows": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _p, _p, _p, _p, _p, _sz, _p]),
+    "pp_qo_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
+    "pp_qo_find_periods": (C.c_int, [_p, _i64, _i32, _i32, _i32, _f64, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32,
+                                     _p, _i32, _p, _p, _p, _p, _p, _p, _p, _p, _i64, _p, _p, _p, _sz, _p, _p]),
+    "pp_qo_solve": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _i32, _p, _i32,
+                              _p, _p, _p, _p, _p, _i64, _p, _p, _p, _p, _sz, _p]),
+    "pp_qo_dictionary_rows": (C.c_int, [_i32, _i32, _p, _p, _i32, _p, _i32, _p, _p]),
+    "pp_qo_solve_rows": (C.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _i32, _i32, _i32, _p, _p, _i64, _p, _p, _p,
+                                   _sz, _p]),
 }
 
 _lib = None
@@ -96,14 +95,50 @@ def check(rc: int, what: str):
 FOLD_HIERARCHICAL, FOLD_DIRECT, FOLD_HIERARCHICAL_NO_RIDERS, FOLD_NOMINATE_F32 = 0, 1, 2, 3
 
 
+FOLD_NAMES = {"hierarchical": FOLD_HIERARCHICAL, "direct": FOLD_DIRECT, "no_riders": FOLD_HIERARCHICAL_NO_RIDERS,
+              "f32": FOLD_NOMINATE_F32}
+
+# The C library keeps no process-wide state: the fold mode and the optional profile buffer are arguments of every
+# call.  These two module variables are only the DEFAULTS the Python classes pass when an instance does not set
+# its own (`Periods(..., fold_mode=...)`); tests and the tuning tools use them to switch whole scripts.
+_default_fold_mode = FOLD_HIERARCHICAL
+_profile_ptr = 0
+
+
 def set_fold_mode(mode: int):
-    """FOLD_HIERARCHICAL (default) or FOLD_DIRECT; see include/pyperiod_b200.h."""
-    check(load().pp_set_fold_mode(int(mode)), "pp_set_fold_mode")
+    """Default fold mode of instances that do not choose one (FOLD_*; see include/pyperiod_b200.h)."""
+    global _default_fold_mode
+    if int(mode) not in FOLD_NAMES.values():
+        raise PPError("unknown fold mode")
+    _default_fold_mode = int(mode)
 
 
-def sweep_passes(n: int, pmin: int, pmax: int) -> int:
-    """Passes over a window of n samples per ranking sweep under the current fold mode."""
-    return int(load().pp_sweep_passes(int(n), int(pmin), int(pmax)))
+def default_fold_mode() -> int:
+    return _default_fold_mode
+
+
+def resolve_fold_mode(mode) -> int:
+    """None -> the module default; a FOLD_* value or one of FOLD_NAMES."""
+    if mode is None:
+        return _default_fold_mode
+    if isinstance(mode, str):
+        return FOLD_NAMES[mode]
+    return int(mode)
+
+
+def set_profile_buffer(tensor_or_none):
+    """Device buffer of 8 uint64 the M-best / QO kernels add phase cycle counts to (development aid)."""
+    global _profile_ptr
+    _profile_ptr = 0 if tensor_or_none is None else int(tensor_or_none.data_ptr())
+
+
+def profile_ptr() -> C.c_void_p:
+    return C.c_void_p(_profile_ptr)
+
+
+def sweep_passes(n: int, pmin: int, pmax: int, fold_mode=None) -> int:
+    """Passes over a window of n samples per ranking sweep under `fold_mode` (default: the module default)."""
+    return int(load().pp_sweep_passes(int(n), int(pmin), int(pmax), resolve_fold_mode(fold_mode)))
 
 
 def microbench(kind: int, iters: int = 4000) -> dict:

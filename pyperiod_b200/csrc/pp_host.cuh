@@ -12,6 +12,12 @@ namespace pp {
 int fail(int code, const char* fmt, const char* a = "");
 int check_cuda(cudaError_t e, const char* what);
 
+// fold modes are per-call arguments (include/pyperiod_b200.h)
+static inline int check_fold_mode(int mode) {
+  if (mode < 0 || mode > 3) return fail(-1, "unknown fold mode%s");
+  return 0;
+}
+
 struct DeviceFacts {
   int sm_count = 0, smem_optin = 0, major = 0, minor = 0, clock_khz = 0;
 };

@@ -40,6 +40,7 @@ struct SmemPlan {
   int skip_words;
   int hier_len; // doubles per warp of hierarchical-sweep scratch (0 = none)
   int xf_len;   // floats per fp32 copy of the window (0 = none; two copies, see SweepParams::xf0)
+  int tie_len;  // doubles of per-candidate ranking keys for the near-tie audit (0 = none)
   __host__ __device__ size_t off_vwin() const { return (size_t)xs_len * 8; }
   __host__ __device__ size_t off_utmp() const { return off_vwin() + (size_t)pv * 8; }
   // the hierarchical-sweep scratch is only live inside a sweep, vwin/utmp only between sweeps: they share bytes
@@ -59,14 +60,17 @@ struct SmemPlan {
   __host__ __device__ size_t off_skip() const { return off_slot() + (size_t)num * 4; }
   __host__ __device__ size_t off_misc() const { return off_skip() + (size_t)skip_words * 4; }
   __host__ __device__ size_t off_xf() const { return (off_misc() + 64 + 15) & ~(size_t)15; }
-  __host__ __device__ size_t bytes() const { return off_xf() + 2 * (size_t)xf_len * 4; }
+  __host__ __device__ size_t off_tie() const { return off_xf() + 2 * (size_t)xf_len * 4; }
+  __host__ __device__ size_t off_nom() const { return off_tie() + (size_t)tie_len * 8; }
+  __host__ __device__ size_t bytes() const { return off_nom() + (tie_len ? (size_t)skip_words * 4 : 0) + 16; }
 };
 
 constexpr int kF32Pad = 320;  // floats after the window in the fp32 copies: masked 64-wide tiles read past N
 
 __host__ __device__ inline SmemPlan make_plan(int N, int pmax, int num, bool sweep_pad, bool hier = false,
-                                              bool f32 = false) {
+                                              bool f32 = false, bool tie = false) {
   SmemPlan pl;
+  pl.tie_len = tie ? ((pmax + 2) & ~1) : 0;
   pl.hier_len = hier ? hier_scratch_len(pmax) : 0;
   pl.xf_len = (hier && f32) ? ((N + kF32Pad + 3) & ~3) : 0;
   pl.xs_len = sweep_pad ? ((N + kSweepPad + 1) & ~1) : ((N + 1) & ~1);
@@ -93,7 +97,11 @@ struct Smem {
   int* misc;
   float* xf0;
   float* xf1;
+  double* tie_keys;
+  uint32_t* tie_nom;
   __device__ Smem(unsigned char* base, const SmemPlan& pl) {
+    tie_keys = pl.tie_len ? reinterpret_cast<double*>(base + pl.off_tie()) : nullptr;
+    tie_nom = pl.tie_len ? reinterpret_cast<uint32_t*>(base + pl.off_nom()) : nullptr;
     xs = reinterpret_cast<double*>(base);
     vwin = reinterpret_cast<double*>(base + pl.off_vwin());
     utmp = reinterpret_cast<double*>(base + pl.off_utmp());
@@ -181,7 +189,8 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
              int orth, int hier, Tables tb, double* __restrict__ metric_out, int32_t* __restrict__ best_p,
              double* __restrict__ best_val, double* __restrict__ warp_scr, const uint2* __restrict__ tops, int ntops, int* __restrict__ next_window) {
   unsigned char* smem_raw = pp_smem;
-  const SmemPlan pl = make_plan(N, pmax, 0, true, hier != 0);
+  const bool tie = metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA;
+  const SmemPlan pl = make_plan(N, pmax, 0, true, hier != 0, false, tie);
   Smem sm(smem_raw, pl);
   WindowLoader loader;
   loader.init(sm.bar);
@@ -191,7 +200,7 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
     const int b = wq.b;
     loader.load(sm.xs, x + (size_t)b * ldx, N);
     double e_res = 0.0;
-    if (metric == PP_METRIC_IMPOSED) e_res = cta_sum_sq(sm.xs, N, sm.red);
+    if (metric == PP_METRIC_IMPOSED || tie) e_res = cta_sum_sq(sm.xs, N, sm.red);
     if (threadIdx.x == 0) {
       SweepParams& sp = sm.sweep->params;
       sp.N = N;
@@ -219,8 +228,12 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
       sp.xf0_off = 0;
       sp.xf1_off = 0;
       sp.metric_out = metric_out ? metric_out + (size_t)b * (pmax + 1) : nullptr;
+      sp.tie_keys = sm.tie_keys;
+      sp.tie_nom = sm.tie_nom;
+      sp.canon_v = sm.vwin;
+      sp.canon_u = sm.utmp;
     }
-    const SweepResult r = cta_sweep<kSweepHier>(sm.sweep);
+    const SweepResult r = cta_sweep<kSweepHier | kSweepTieAudit>(sm.sweep);
     if (threadIdx.x == 0) {
       best_p[b] = r.p;
       best_val[b] = r.val;
@@ -295,9 +308,10 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
              int trunc_i, int orth_i, int hier, Tables tb, uint32_t* __restrict__ periods_out, double* __restrict__ powers_out,
              double* __restrict__ bases_out, int32_t* __restrict__ sweeps_out, int32_t* __restrict__ status_out,
              double* __restrict__ ws_slots, double* __restrict__ ws_scr, const uint2* __restrict__ tops, int ntops,
-             int* __restrict__ next_window, unsigned long long* __restrict__ prof, int f32, double* __restrict__ ws_keys) {
+             int* __restrict__ next_window, unsigned long long* __restrict__ prof, int f32, double* __restrict__ ws_keys,
+             int32_t* __restrict__ near_ties_out) {
   unsigned char* smem_raw = pp_smem;
-  const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0, f32 != 0);
+  const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0, f32 != 0, true);
   Smem sm(smem_raw, pl);
   const bool trunc = !PLAIN && trunc_i != 0, orth = !PLAIN && orth_i != 0;
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -370,17 +384,22 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.verify_keys = sm.xf0 != nullptr ? ws_keys + (size_t)blockIdx.x * (pmax + 2) : nullptr;
       sp.xf0_off = sm.xf0 != nullptr ? (int)pl.off_xf() : 0;
       sp.xf1_off = sm.xf0 != nullptr ? (int)(pl.off_xf() + (size_t)pl.xf_len * 4) : 0;
+      sp.tie_keys = sm.tie_keys;
+      sp.tie_nom = sm.tie_nom;
+      sp.canon_v = sm.vwin;
+      sp.canon_u = sm.utmp;
     }
     __syncthreads();
 
     // ---------------- step 1 (Periods.py:494-537)
     long long t_sweep = 0, t_proj = 0, t_upd = 0, t_step2 = 0, t_fac = 0, t_swap = 0, t_copy = 0, t_dec = 0, t_blk = 0, t_mark = clock64();
-    int sweeps = 0;
+    int sweeps = 0, tie_sweeps = 0;
     const int guard = 12 * (pmax - pmin + 2) + 12 * num;
     while (true) {
       if (misc[0] >= num || misc[4] != PP_STATUS_OK) break;  // uniform: read after a barrier
-      const SweepResult top = cta_sweep<kSweepHier | kSweepNoMetricOut | (F32 ? kSweepF32 : 0) | (PLAIN ? kSweepPlain : 0)>(sm.sweep);
+      const SweepResult top = cta_sweep<kSweepHier | kSweepNoMetricOut | kSweepTieAudit | (F32 ? kSweepF32 : 0) | (PLAIN ? kSweepPlain : 0)>(sm.sweep);
       ++sweeps;
+      if (sm.sweep->tie_count > 1) ++tie_sweeps;  // decided by the exact re-ranking
       { const long long t = clock64(); t_sweep += t - t_mark; t_mark = t; }
       if (top.p == 0 || sweeps > guard) {
         if (threadIdx.x == 0) misc[4] = top.p == 0 ? PP_STATUS_NO_PERIOD : PP_STATUS_GUARD;
@@ -610,6 +629,7 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     if (threadIdx.x == 0) {
       status_out[b] = status;
       if (sweeps_out) sweeps_out[b] = sweeps;
+      if (near_ties_out) near_ties_out[b] = tie_sweeps;
     }
     if (bases_out != nullptr) {
       for (int i = 0; i < num; ++i) {
@@ -685,6 +705,10 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
       sp.verify_keys = nullptr;
       sp.xf0_off = 0;
       sp.xf1_off = 0;
+      sp.tie_keys = nullptr;
+      sp.tie_nom = nullptr;
+      sp.canon_v = nullptr;
+      sp.canon_u = nullptr;
     }
     int count = 0;
     int pstart = 2;
@@ -775,6 +799,10 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
       sp.verify_keys = hier ? ws_keys + (size_t)blockIdx.x * (max_length + 1) : nullptr;
       sp.xf0_off = 0;
       sp.xf1_off = 0;
+      sp.tie_keys = nullptr;
+      sp.tie_nom = nullptr;
+      sp.canon_v = nullptr;
+      sp.canon_u = nullptr;
     }
     for (int i = 0; i < num; ++i) {
       uint32_t out_p = 0u;
@@ -824,17 +852,15 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
-// 0 = hierarchical ranking sweeps where they apply (default), 1 = always fold every period directly
-static int g_fold_mode = 0;
-// optional device buffer of 8 uint64 phase-cycle counters (development aid; see pp_set_profile_buffer)
-static unsigned long long* g_prof = nullptr;
-
-static bool hier_applies(int metric, int trunc, int orth) {
-  return g_fold_mode != PP_FOLD_DIRECT && !trunc && !orth && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
+// hierarchical ranking sweeps where they apply, unless the call asks for direct folds
+static bool hier_applies(int fold_mode, int metric, int trunc, int orth) {
+  return fold_mode != PP_FOLD_DIRECT && !trunc && !orth && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
 }
 
+// plan used for grid / workspace sizing: the largest any fold mode of the algorithm needs
 static int plan_for(int algo, int N, int pmax, int num, SmemPlan& pl) {
-  pl = make_plan(N, pmax, algo == PP_ALGO_MBEST ? num : 0, true, g_fold_mode != PP_FOLD_DIRECT && (algo == PP_ALGO_MBEST || algo == PP_ALGO_SWEEP || algo == PP_ALGO_BCORR));
+  pl = make_plan(N, pmax, algo == PP_ALGO_MBEST ? num : 0, true, algo == PP_ALGO_MBEST || algo == PP_ALGO_SWEEP || algo == PP_ALGO_BCORR,
+                 false, algo == PP_ALGO_MBEST || algo == PP_ALGO_SWEEP);
   return 0;
 }
 
@@ -846,24 +872,11 @@ extern "C" {
 
 int pp_abi_version(void) { return PP_ABI_VERSION; }
 
-int pp_set_fold_mode(int32_t mode) {
-  if (mode != PP_FOLD_HIERARCHICAL && mode != PP_FOLD_DIRECT && mode != PP_FOLD_HIERARCHICAL_NO_RIDERS &&
-      mode != PP_FOLD_NOMINATE_F32)
-    return fail(-1, "unknown fold mode%s");
-  g_fold_mode = mode;
-  return 0;
-}
-int pp_get_fold_mode(void) { return g_fold_mode; }
-int pp_sweep_passes(int32_t N, int32_t pmin, int32_t pmax) {
+int pp_sweep_passes(int32_t N, int32_t pmin, int32_t pmax, int32_t fold_mode) {
   if (pmax < pmin) return 0;
-  if (g_fold_mode == PP_FOLD_DIRECT) return pmax - pmin + 1;
-  return hier_job_count(N, pmin, pmax, g_fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS);
+  if (fold_mode == PP_FOLD_DIRECT) return pmax - pmin + 1;
+  return hier_job_count(N, pmin, pmax, fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS);
 }
-int pp_set_profile_buffer(void* dev_u64x8) {
-  g_prof = reinterpret_cast<unsigned long long*>(dev_u64x8);
-  return 0;
-}
-void* pp_get_profile_buffer(void) { return g_prof; }
 const char* pp_last_error(void) { return g_err; }
 
 int pp_device_info(int32_t* sm_count, int32_t* smem_optin_bytes, int32_t* cc_major, int32_t* cc_minor,
@@ -946,9 +959,9 @@ int pp_periodic_norm(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t
 }
 
 int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, int32_t pmax, int32_t metric,
-             int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q, int32_t table_pmax,
-             double* metric_out, int32_t* best_p, double* best_val, void* workspace, size_t workspace_bytes,
-             void* stream) {
+             int32_t trunc, int32_t orth, int32_t fold_mode, const int32_t* chain_off, const int32_t* chain_q,
+             int32_t table_pmax, double* metric_out, int32_t* best_p, double* best_val, void* workspace,
+             size_t workspace_bytes, void* stream) {
   if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (int rc = check_common(x, ldx, B, N)) return rc;
   if (pmin < 1 || pmax < pmin || pmax > N) return fail(-1, "need 1 <= pmin <= pmax <= N%s");
@@ -956,11 +969,11 @@ int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, i
   if (metric == PP_METRIC_MAXABS && (trunc || orth)) return fail(-1, "MAXABS ignores trunc/orth; pass 0%s");
   if (orth && (chain_off == nullptr || chain_q == nullptr || table_pmax < pmax)) return fail(-1, "orth needs tables covering pmax%s");
   if (best_p == nullptr || best_val == nullptr) return fail(-1, "best_p/best_val are null%s");
-  if (B == 0) return 0;
+  if (int rc = check_fold_mode(fold_mode)) return rc;
   DeviceFacts f;
   if (int rc = device_facts(f)) return rc;
-  const int hier = hier_applies(metric, trunc, orth) ? 1 : 0;
-  const SmemPlan pl = make_plan(N, pmax, 0, true, hier != 0);
+  const int hier = hier_applies(fold_mode, metric, trunc, orth) ? 1 : 0;
+  const SmemPlan pl = make_plan(N, pmax, 0, true, hier != 0, false, metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
   if (int rc = prep_kernel(sweep_kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B);
   size_t off = 0;
@@ -974,7 +987,7 @@ int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, i
   if (ntops > 0) {
     tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)ntops * sizeof(uint2)));
     if (!tops) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
-    ntops = build_hier_jobs(N, pmin, pmax, tops, (cudaStream_t)stream);
+    ntops = build_hier_jobs(N, pmin, pmax, fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS, tops, (cudaStream_t)stream);
   }
   Tables tb{chain_off, chain_q, nullptr, nullptr};
   int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
@@ -985,9 +998,10 @@ int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, i
 }
 
 int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, int32_t pmin, int32_t pmax,
-             int32_t gamma, int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q,
-             const int32_t* fac_off, const int32_t* fac, int32_t table_pmax, uint32_t* periods, double* powers,
-             double* bases, int32_t* sweeps, int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
+             int32_t gamma, int32_t trunc, int32_t orth, int32_t fold_mode, const int32_t* chain_off,
+             const int32_t* chain_q, const int32_t* fac_off, const int32_t* fac, int32_t table_pmax, uint32_t* periods,
+             double* powers, double* bases, int32_t* sweeps, int32_t* near_ties, int32_t* status, void* workspace,
+             size_t workspace_bytes, void* profile, void* stream) {
   if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (int rc = check_common(x, ldx, B, N)) return rc;
   if (num < 1 || num > 4096) return fail(-1, "need 1 <= num <= 4096%s");
@@ -996,12 +1010,12 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   if (fac_off == nullptr || fac == nullptr || table_pmax < pmax) return fail(-1, "factor tables must cover pmax%s");
   if (orth && (chain_off == nullptr || chain_q == nullptr)) return fail(-1, "orth needs chain tables%s");
   if (!periods || !powers || !status) return fail(-1, "output pointers are null%s");
-  if (B == 0) return 0;
+  if (int rc = check_fold_mode(fold_mode)) return rc;
   DeviceFacts f;
   if (int rc = device_facts(f)) return rc;
-  const int hier = hier_applies(gamma ? PP_METRIC_GAMMA : PP_METRIC_NORM, trunc, orth) ? 1 : 0;
-  const int f32 = (hier && g_fold_mode == PP_FOLD_NOMINATE_F32) ? 1 : 0;
-  const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0, f32 != 0);
+  const int hier = hier_applies(fold_mode, gamma ? PP_METRIC_GAMMA : PP_METRIC_NORM, trunc, orth) ? 1 : 0;
+  const int f32 = (hier && fold_mode == PP_FOLD_NOMINATE_F32) ? 1 : 0;
+  const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0, f32 != 0, true);
   const bool plain = !trunc && !orth;
   auto kernel = f32 ? mbest_kernel<true, true> : (plain ? mbest_kernel<false, true> : mbest_kernel<false, false>);
   if (int rc = prep_kernel(kernel, pl.bytes(), f)) return rc;
@@ -1020,12 +1034,14 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   if (ntops > 0) {
     tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)ntops * sizeof(uint2)));
     if (!tops) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
-    ntops = build_hier_jobs(N, pmin, pmax, tops, (cudaStream_t)stream);
+    ntops = build_hier_jobs(N, pmin, pmax, fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS, tops, (cudaStream_t)stream);
   }
   Tables tb{chain_off, chain_q, fac_off, fac};
   kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,
                                                                      hier, tb, periods, powers, bases, sweeps, status,
-                                                                     slots, scr, tops, ntops, next_window, g_prof, f32, keys);
+                                                                     slots, scr, tops, ntops, next_window,
+                                                                     reinterpret_cast<unsigned long long*>(profile), f32, keys,
+                                                                     near_ties);
   return check_cuda(cudaGetLastError(), "mbest_kernel launch");
 }
 
@@ -1061,22 +1077,22 @@ int pp_small_to_large(const double* x, int64_t ldx, int32_t B, int32_t N, double
 }
 
 int pp_best_correlation(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, int32_t max_length,
-                        double ratio, int32_t trunc, int32_t orth, const int32_t* chain_off, const int32_t* chain_q,
-                        int32_t table_pmax, uint32_t* periods, double* powers, double* bases, int32_t* status,
-                        void* workspace, size_t workspace_bytes, void* stream) {
+                        double ratio, int32_t trunc, int32_t orth, int32_t fold_mode, const int32_t* chain_off,
+                        const int32_t* chain_q, int32_t table_pmax, uint32_t* periods, double* powers, double* bases,
+                        int32_t* status, void* workspace, size_t workspace_bytes, void* stream) {
   if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (int rc = check_common(x, ldx, B, N)) return rc;
   if (num < 1) return fail(-1, "num must be >= 1%s");
   if (max_length < 3 || max_length > N + 1) return fail(-1, "need 3 <= max_length <= N+1%s");
   if (orth && (chain_off == nullptr || chain_q == nullptr || table_pmax < max_length - 1)) return fail(-1, "orth needs tables covering max_length%s");
   if (!periods || !powers || !status) return fail(-1, "output pointers are null%s");
-  if (B == 0) return 0;
+  if (int rc = check_fold_mode(fold_mode)) return rc;
   DeviceFacts f;
   if (int rc = device_facts(f)) return rc;
   // hierarchical ranking needs room for the per-CTA key arrays and the job table; without it: sequential folds
   size_t off = 0;
   int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
-  int hier = g_fold_mode != PP_FOLD_DIRECT && max_length - 1 >= 4 ? 1 : 0;
+  int hier = fold_mode != PP_FOLD_DIRECT && max_length - 1 >= 4 ? 1 : 0;
   const size_t grid_max = (size_t)f.sm_count * kCtasPerSm;
   double* keys = nullptr;
   uint2* tops = nullptr;
@@ -1090,7 +1106,7 @@ int pp_best_correlation(const double* x, int64_t ldx, int32_t B, int32_t N, int3
   const SmemPlan pl = make_plan(N, max_length, 0, true, hier != 0);
   if (int rc = prep_kernel(bcorr_kernel, pl.bytes(), f)) return rc;
   const int grid = grid_for(f, pl.bytes(), B);
-  if (hier) ntops = build_hier_jobs(N, 2, max_length - 1, tops, (cudaStream_t)stream);
+  if (hier) ntops = build_hier_jobs(N, 2, max_length - 1, fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS, tops, (cudaStream_t)stream);
   Tables tb{chain_off, chain_q, nullptr, nullptr};
   bcorr_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, max_length, ratio, trunc, orth,
                                                                      tb, periods, powers, bases, status, next_window,

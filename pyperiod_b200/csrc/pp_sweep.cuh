@@ -68,6 +68,14 @@ struct SweepParams {
   // (byte offsets into the kernel's dynamic shared memory, so that the loads stay LDS; 0 = none)
   int xf0_off;
   int xf1_off;
+  // near-tie audit of NORM / GAMMA ranking sweeps (kSweepTieAudit): every candidate's ranking key is kept in
+  // tie_keys (shared, [pmax + 1]); candidates inside the rounding bound of the best one (e_res >= sum x^2 of the
+  // swept signal) are re-evaluated exactly.  tie_nom: shared bitmap, (pmax + 32) / 32 words.  canon_v / canon_u:
+  // shared scratch of the exact projection, >= pmax + 2 doubles each (may alias hier_scr: dead by then).
+  double* tie_keys;
+  uint32_t* tie_nom;
+  double* canon_v;
+  double* canon_u;
 };
 
 struct SweepResult {
@@ -102,6 +110,7 @@ __device__ __forceinline__ double key_to_value(int metric, double key, int p, do
 struct RankCtx {
   const uint32_t* skip;
   double* metric_out;
+  double* tie_keys;
   const double* rcp;
   double sqrtN;
   int metric;
@@ -110,12 +119,13 @@ struct RankCtx {
   int pmax;
 };
 __device__ __forceinline__ RankCtx rank_ctx(const SweepParams* sp) {
-  return RankCtx{sp->nskip > 0 ? sp->skip : nullptr, sp->metric_out, sp->rcp, sp->sqrtN, sp->metric, sp->N, sp->pmin, sp->pmax};
+  return RankCtx{sp->nskip > 0 ? sp->skip : nullptr, sp->metric_out, sp->tie_keys, sp->rcp, sp->sqrtN, sp->metric, sp->N, sp->pmin, sp->pmax};
 }
 
 __device__ __forceinline__ void consider(const RankCtx& rc, double key, int p, Best& best) {
   const int metric = rc.metric;
   if (rc.metric_out != nullptr && (threadIdx.x & 31) == 0) rc.metric_out[p] = key_to_value(metric, key, p, rc.sqrtN);
+  if (rc.tie_keys != nullptr && (threadIdx.x & 31) == 0) rc.tie_keys[p] = key;
   const uint32_t* skip = rc.skip;
   if (skip != nullptr && ((skip[p >> 5] >> (p & 31)) & 1u)) return;
   if (better(metric, key, p, best)) {
@@ -129,6 +139,7 @@ __device__ __forceinline__ void consider_lane(const RankCtx& rc, double key, int
   if (p == 0) return;
   const int metric = rc.metric;
   if (rc.metric_out != nullptr && writer) rc.metric_out[p] = key_to_value(metric, key, p, rc.sqrtN);
+  if (rc.tie_keys != nullptr && writer) rc.tie_keys[p] = key;
   const uint32_t* skip = rc.skip;
   if (skip != nullptr && ((skip[p >> 5] >> (p & 31)) & 1u)) return;
   if (better(metric, key, p, best)) {
@@ -1218,10 +1229,10 @@ static __global__ void tops_kernel(int N, int pmin, int pmax, int riders, uint2*
 
 // Build the job table in the caller-provided buffer (>= hier_top_count entries) on `stream`; returns the
 // number of jobs.
-inline int build_hier_jobs(int N, int pmin, int pmax, uint2* tops, cudaStream_t stream) {
+inline int build_hier_jobs(int N, int pmin, int pmax, bool want_riders, uint2* tops, cudaStream_t stream) {
   const int n = hier_top_count(pmin, pmax);
   if (n <= 0) return 0;
-  const bool riders = n <= kHierRiderMaxTops && pp_get_fold_mode() != PP_FOLD_HIERARCHICAL_NO_RIDERS;
+  const bool riders = n <= kHierRiderMaxTops && want_riders;
   const size_t smem = (size_t)2 * n * sizeof(int);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(tops_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -1260,6 +1271,7 @@ struct SweepShared {
   unsigned long long stat_nominated, stat_fallback;  // fp32 nomination statistics (development aid)
   int cand[kMaxVerify];
   int hit_p;    // first-hit mode: lowest period over threshold so far
+  int tie_count;  // near-tie audit: candidates inside the rounding bound of the best (1 = a clear winner)
   double wkey[kWarps];
   int wp[kWarps];
 };
@@ -1284,6 +1296,21 @@ constexpr int kSweepF32 = 4;         // float nomination + exact verification
 constexpr int kSweepPlain = 8;       // the caller never sweeps with trunc / orth / MAXABS / IMPOSED: energy folds only
 constexpr int kSweepNoMetricOut = 16;  // the caller never asks for per-candidate metrics (drops the sqrt / divide of
                                        // key_to_value from every ranking site)
+constexpr int kSweepTieAudit = 32;     // NORM / GAMMA argmax sweeps: exact re-ranking of near-tied candidates
+
+// Rounding bound of a ranking key (an energy sum_r S_r^2 / cnt_r evaluated by any of the folds: sequential,
+// hierarchical, reciprocal weights) against the exactly rounded one, relative to e >= sum x^2 of the swept signal:
+// ceil(N/p) additions per residue, the squares, the reciprocal weights and the reductions (<= 40 u), doubled.
+__device__ __forceinline__ double tie_tol(int N, int p, double e) {
+  const double u = 1.1102230246251565e-16;  // 2^-53
+  return 2.0 * (2.0 * (double)((N + p - 1) / p) + 40.0) * u * e;
+}
+
+// The reference's own evaluation of candidate p (Periods.py:504-510): the projection with sequential sums and IEEE
+// means (bit-identical base vector), then the sum of squares of the tiled base over n < N in an order that does not
+// depend on p -- so candidates with identical base vectors (p, 2p, 3p of an exactly periodic integer-valued input)
+// tie EXACTLY, as they do in numpy.  Returns the ranking VALUE (norm, or gamma norm).  All threads call; barriers inside.
+static __device__ __noinline__ double cta_canonical_value(const SweepParams* sp, SweepShared* sh, int p);
 template <int FEAT>
 static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   const SweepParams* sp = &sh->params;
@@ -1365,6 +1392,9 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
       sh->stat_nominated += (unsigned long long)nc;
       sh->stat_fallback += nc > kMaxVerify ? 1ull : 0ull;
     }
+    if (rc.tie_keys != nullptr)   // near-tie audit: only the candidates verified below carry a key
+      for (int p = pmin + threadIdx.x; p <= pmax; p += kThreads) rc.tie_keys[p] = 0.0;
+    __syncthreads();
     if (nc <= kMaxVerify) {
       RankCtx vrc = rc;
       vrc.skip = nullptr;  // skipped periods were not nominated
@@ -1491,8 +1521,87 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   }
   SweepResult out{0.0, res.p};
   if (res.p != 0) out.val = key_to_value(metric, res.key, res.p, rc.sqrtN);
+  if constexpr ((FEAT & kSweepTieAudit) != 0) {
+    if (!first_hit && sp->tie_keys != nullptr && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA)) {
+      // Near-tie audit.  The keys above are energies rebuilt from reciprocal weights (and, hierarchically, from
+      // derived sums): a few ulp from the reference's norm of the tiled base, which is enough to rank a multiple
+      // of the true period above it when the input is exactly periodic.  Every candidate whose key can reach the
+      // best one within the rounding bound is therefore re-evaluated the reference's way and ranked by VALUE with
+      // strict '>' in ascending p (Periods.py:512-515).  On inputs with a noise floor exactly one candidate
+      // qualifies and nothing is recomputed.
+      int nnom = 0;
+      if (res.p != 0) {
+        const double* keys = sp->tie_keys;
+        uint32_t* nom = sp->tie_nom;
+        const int words = (pmax + 32) / 32;
+        for (int i = threadIdx.x; i < words; i += kThreads) nom[i] = 0u;
+        if (threadIdx.x == 0) sh->ncand = 0;
+        __syncthreads();
+        const double e_bound = sp->e_res;
+        const bool gam = metric == PP_METRIC_GAMMA;
+        const double lo_best = res.key - tie_tol(rc.N, res.p, e_bound);
+        const uint32_t* skip = rc.skip;
+        for (int p = pmin + threadIdx.x; p <= pmax; p += kThreads) {
+          if (skip != nullptr && ((skip[p >> 5] >> (p & 31)) & 1u)) continue;
+          const double hi = keys[p] + tie_tol(rc.N, p, e_bound);
+          const bool in = gam ? hi * (double)res.p >= lo_best * (double)p : hi >= lo_best;
+          if (in) {
+            atomicOr(&nom[p >> 5], 1u << (p & 31));
+            atomicAdd(&sh->ncand, 1);
+          }
+        }
+        __syncthreads();
+        nnom = sh->ncand;
+        if (nnom > 1) {
+          double best_v = 0.0;
+          int best_p = 0;
+          for (int wd = 0; wd < words; ++wd) {
+            uint32_t bits = nom[wd];  // uniform
+            while (bits) {
+              const int p = wd * 32 + __ffs(bits) - 1;
+              bits &= bits - 1;
+              const double v = cta_canonical_value(sp, sh, p);
+              if (v > best_v) {  // ascending p, strict '>': the lowest period keeps an exact tie
+                best_v = v;
+                best_p = p;
+              }
+            }
+          }
+          out.p = best_p;
+          out.val = best_v;
+        }
+      }
+      if (threadIdx.x == 0) sh->tie_count = nnom;
+    }
+  }
   __syncthreads();  // wkey/wp may be rewritten by the next sweep
   return out;
+}
+
+static __device__ __noinline__ double cta_canonical_value(const SweepParams* sp, SweepShared* sh, int p) {
+  const int N = sp->N;
+  const bool orth = sp->orth != 0;
+  const int clen = orth ? sp->chain_off[p + 1] - sp->chain_off[p] : 0;
+  __syncthreads();  // the scratch may still be read by the previous candidate's reduction
+  cta_project_exact<false>(staged_window(), 0, N, p, sp->trunc != 0, orth ? sp->chain_q + sp->chain_off[p] : nullptr, clen,
+                           sp->canon_v, sp->canon_u);
+  const double* v = sp->canon_v;
+  double a = 0.0;
+  int r = threadIdx.x % p;
+  const int step = kThreads % p;
+  for (int n = threadIdx.x; n < N; n += kThreads) {
+    const double b = v[r];
+    a = fma(b, b, a);
+    r += step;
+    if (r >= p) r -= p;
+  }
+  a = warp_sum(a);
+  if ((threadIdx.x & 31) == 0) sh->wkey[threadIdx.x >> 5] = a;
+  __syncthreads();
+  double t = 0.0;
+#pragma unroll
+  for (int w = 0; w < kWarps; ++w) t += sh->wkey[w];
+  return key_to_value(sp->metric, t, p, sp->sqrtN);
 }
 
 }  // namespace pp

@@ -23,7 +23,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._device import Windows, Workspace, ptr, stage_windows, stream_ptr, to_host
+from ._device import Windows, call, ptr, stage_windows, stream_ptr, to_host, workspace_for
 from .tables import get_tables, orth_chain
 
 
@@ -36,6 +36,7 @@ class BatchResult:
     status: object           # (B,) int32, _lib.STATUS_*
     count: object = None     # (B,) int32 -- small_to_large only: periods accepted
     sweeps: object = None    # (B,) int32 -- M-best only: step-1 sweeps executed
+    near_ties: object = None  # (B,) int32 -- M-best only: sweeps decided by the exact re-ranking of near-tied candidates
 
     def __iter__(self):
         yield self.periods
@@ -76,7 +77,12 @@ def _export(w: Windows, t, as_u32=False):
 class Periods:
     """Sethares-Staley periodicity transforms, B200-native.  See module docstring."""
 
-    def __init__(self, *args, trunc_to_integer_multiple=None, orthogonalize=None, device=None):
+    def __init__(self, *args, trunc_to_integer_multiple=None, orthogonalize=None, device=None, dtype="fp64",
+                 fold_mode=None):
+        """dtype / fold_mode are not part of the reference API.  dtype="fp32" ranks the M-best sweeps in float
+        (half the shared-memory traffic) and re-folds every candidate inside the float error bound in fp64, so the
+        period lists and norms are those of the fp64 path (the north star's fp32 option).  fold_mode (a
+        _lib.FOLD_* value or name) picks how ranking sweeps obtain the residue sums; None = the module default."""
         args = list(args)
         self._data = None
         if args and _is_data(args[0]):
@@ -92,7 +98,17 @@ class Periods:
         self._trunc_to_integer_multiple = bool(trunc)
         self._orthogonalize = bool(orth)
         self._device = device
+        if dtype not in ("fp64", "fp32"):
+            raise ValueError("dtype must be 'fp64' or 'fp32'")
+        self._dtype = dtype
+        self._fold_mode = fold_mode
         _lib.load()  # fail loudly now if the CUDA library is missing
+
+    def _fold(self) -> int:
+        """Fold mode of this instance's calls (per-call argument of the C ABI)."""
+        if self._fold_mode is None and self._dtype == "fp32":
+            return _lib.FOLD_NOMINATE_F32
+        return _lib.resolve_fold_mode(self._fold_mode)
 
     # ------------------------------------------------------------------ argument plumbing
     def _split(self, args, names):
@@ -119,14 +135,25 @@ class Periods:
         lib = _lib.load()
         w = stage_windows(data, device)
         p = int(p)
-        if not 1 <= p <= w.n:
-            raise ValueError("need 1 <= p <= len(data)")
-        chain = np.asarray(orth_chain(p) if orthogonalize else [], dtype=np.int32)
+        if p < 1:
+            raise ValueError("need p >= 1")
         out_len = p if return_single_period else w.n
+        if p > w.n:
+            # The reference pads the window to ONE row of p samples (Periods.py:172-176): without truncation the
+            # projection is the data itself (divisor 1; tile(...)[:N], and the "single period" is that length-N
+            # vector sliced [0:p]); with truncation the mean runs over zero complete rows: nan (Periods.py:178-184).
+            if orthogonalize:
+                raise ValueError("orthogonalize with p > len(data) is not supported")
+            out = torch.full((w.b, w.n), float("nan"), dtype=torch.float64, device=w.device)
+            if not trunc_to_integer_multiple:
+                out[:, :] = torch.as_strided(w.tensor, (w.b, w.n), (w.ldx, 1))
+            res = _export(w, out)
+            return res[0] if w.was_1d else res
+        chain = np.asarray(orth_chain(p) if orthogonalize else [], dtype=np.int32)
         out = torch.empty((w.b, out_len), dtype=torch.float64, device=w.device)
-        _lib.check(lib.pp_project(ptr(w.tensor), w.ldx, w.b, w.n, p, int(bool(trunc_to_integer_multiple)),
-                                  chain.ctypes.data_as(C.c_void_p), len(chain), ptr(out), out_len, out_len,
-                                  stream_ptr(w.device)), "pp_project")
+        call(lib.pp_project, "pp_project", w.device, ptr(w.tensor), w.ldx, w.b, w.n, p,
+             int(bool(trunc_to_integer_multiple)), chain.ctypes.data_as(C.c_void_p), len(chain), ptr(out), out_len,
+             out_len, stream_ptr(w.device))
         res = _export(w, out)
         return res[0] if w.was_1d else res
 
@@ -136,8 +163,8 @@ class Periods:
         lib = _lib.load()
         w = stage_windows(x, device)
         out = torch.empty((w.b,), dtype=torch.float64, device=w.device)
-        _lib.check(lib.pp_periodic_norm(ptr(w.tensor), w.ldx, w.b, w.n, int(p) if p else 0, ptr(out),
-                                        stream_ptr(w.device)), "pp_periodic_norm")
+        call(lib.pp_periodic_norm, "pp_periodic_norm", w.device, ptr(w.tensor), w.ldx, w.b, w.n, int(p) if p else 0,
+             ptr(out), stream_ptr(w.device))
         res = _export(w, out)
         return float(res[0]) if w.was_1d else res
 
@@ -160,14 +187,13 @@ class Periods:
         orth = self._orthogonalize and metric != 2
         tb = get_tables(pmax)
         co, cq, _, _ = tb.device(w.device)
-        ws_bytes = lib.pp_workspace_bytes(_lib.ALGO_SWEEP, w.n, pmax, 0, int(orth))
-        ws = Workspace.get(w.device, ws_bytes)
+        ws = workspace_for(w.device, lib.pp_workspace_bytes, _lib.ALGO_SWEEP, w.n, pmax, 0, int(orth))
         metrics = torch.zeros((w.b, pmax + 1), dtype=torch.float64, device=w.device)
         best_p = torch.empty((w.b,), dtype=torch.int32, device=w.device)
         best_v = torch.empty((w.b,), dtype=torch.float64, device=w.device)
-        _lib.check(lib.pp_sweep(ptr(w.tensor), w.ldx, w.b, w.n, pmin, pmax, metric, int(trunc), int(orth),
-                                ptr(co), ptr(cq), tb.pmax, ptr(metrics), ptr(best_p), ptr(best_v), ptr(ws),
-                                ws.numel(), stream_ptr(w.device)), "pp_sweep")
+        call(lib.pp_sweep, "pp_sweep", w.device, ptr(w.tensor), w.ldx, w.b, w.n, pmin, pmax, metric, int(trunc),
+             int(orth), self._fold(), ptr(co), ptr(cq), tb.pmax, ptr(metrics), ptr(best_p), ptr(best_v), ptr(ws),
+             ws.numel(), stream_ptr(w.device))
         return _export(w, metrics), _export(w, best_p), _export(w, best_v)
 
     # ------------------------------------------------------------------ M-best family
@@ -200,24 +226,25 @@ class Periods:
         tb = get_tables(pmax)
         co, cq, fo, fc = tb.device(w.device)
         orth = int(self._orthogonalize)
-        ws_bytes = lib.pp_workspace_bytes(_lib.ALGO_MBEST, w.n, pmax, num, orth)
-        ws = Workspace.get(w.device, ws_bytes)
+        ws = workspace_for(w.device, lib.pp_workspace_bytes, _lib.ALGO_MBEST, w.n, pmax, num, orth)
         periods = torch.empty((w.b, num), dtype=torch.int32, device=w.device)
         powers = torch.empty((w.b, num), dtype=torch.float64, device=w.device)
         bases = torch.empty((w.b, num, w.n), dtype=torch.float64, device=w.device) if return_bases else None
         sweeps = torch.empty((w.b,), dtype=torch.int32, device=w.device)
+        near = torch.empty((w.b,), dtype=torch.int32, device=w.device)
         status = torch.empty((w.b,), dtype=torch.int32, device=w.device)
         cur = torch.cuda.current_stream(w.device)
+        fold = self._fold()
         for b0, b1, ready in w.launch_plan():
             if ready is not None:
                 cur.wait_event(ready)
-            _lib.check(lib.pp_mbest(C.c_void_p(w.ptr + b0 * w.ldx * 8), w.ldx, b1 - b0, w.n, num, min_length, pmax,
-                                    int(gamma), int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq), ptr(fo),
-                                    ptr(fc), tb.pmax, ptr(periods[b0:b1]), ptr(powers[b0:b1]),
-                                    ptr(None if bases is None else bases[b0:b1]), ptr(sweeps[b0:b1]), ptr(status[b0:b1]),
-                                    ptr(ws), ws.numel(), stream_ptr(w.device)), "pp_mbest")
+            call(lib.pp_mbest, "pp_mbest", w.device, C.c_void_p(w.ptr + b0 * w.ldx * 8), w.ldx, b1 - b0, w.n, num,
+                 min_length, pmax, int(gamma), int(self._trunc_to_integer_multiple), orth, fold, ptr(co), ptr(cq),
+                 ptr(fo), ptr(fc), tb.pmax, ptr(periods[b0:b1]), ptr(powers[b0:b1]),
+                 ptr(None if bases is None else bases[b0:b1]), ptr(sweeps[b0:b1]), ptr(near[b0:b1]),
+                 ptr(status[b0:b1]), ptr(ws), ws.numel(), _lib.profile_ptr(), stream_ptr(w.device))
         res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases), _export(w, status),
-                          sweeps=_export(w, sweeps))
+                          sweeps=_export(w, sweeps), near_ties=_export(w, near))
         if w.was_1d:
             if int(res.status[0]) == _lib.STATUS_NO_PERIOD:
                 # the reference dies on `bases[i] = None` when no period has a positive norm
@@ -247,17 +274,17 @@ class Periods:
         tb = get_tables(n_periods)
         co, cq, _, _ = tb.device(w.device)
         orth = int(self._orthogonalize)
-        ws = Workspace.get(w.device, lib.pp_workspace_bytes(_lib.ALGO_S2L, w.n, n_periods, 0, orth))
+        ws = workspace_for(w.device, lib.pp_workspace_bytes, _lib.ALGO_S2L, w.n, n_periods, 0, orth)
         while True:
             periods = torch.empty((w.b, kmax), dtype=torch.int32, device=w.device)
             powers = torch.empty((w.b, kmax), dtype=torch.float64, device=w.device)
             bases = torch.empty((w.b, kmax, w.n), dtype=torch.float64, device=w.device) if return_bases else None
             count = torch.empty((w.b,), dtype=torch.int32, device=w.device)
             status = torch.empty((w.b,), dtype=torch.int32, device=w.device)
-            _lib.check(lib.pp_small_to_large(ptr(w.tensor), w.ldx, w.b, w.n, thresh, n_periods,
-                                             int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq), tb.pmax,
-                                             kmax, ptr(periods), ptr(powers), ptr(bases), ptr(count), ptr(status),
-                                             ptr(ws), ws.numel(), stream_ptr(w.device)), "pp_small_to_large")
+            call(lib.pp_small_to_large, "pp_small_to_large", w.device, ptr(w.tensor), w.ldx, w.b, w.n, thresh,
+                 n_periods, int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq), tb.pmax, kmax,
+                 ptr(periods), ptr(powers), ptr(bases), ptr(count), ptr(status), ptr(ws), ws.numel(),
+                 stream_ptr(w.device))
             need = int(count.max()) if w.b else 0
             if need <= kmax or not w.was_1d:
                 break
@@ -288,12 +315,12 @@ class Periods:
         powers = torch.empty((w.b, num), dtype=torch.float64, device=w.device)
         bases = torch.empty((w.b, num, w.n), dtype=torch.float64, device=w.device) if return_bases else None
         status = torch.empty((w.b,), dtype=torch.int32, device=w.device)
-        ws = Workspace.get(w.device, lib.pp_workspace_bytes(_lib.ALGO_BCORR, w.n, max_length, num,
-                                                            int(self._orthogonalize)))
-        _lib.check(lib.pp_best_correlation(ptr(w.tensor), w.ldx, w.b, w.n, num, max_length, ratio,
-                                           int(self._trunc_to_integer_multiple), int(self._orthogonalize), ptr(co),
-                                           ptr(cq), tb.pmax, ptr(periods), ptr(powers), ptr(bases), ptr(status),
-                                           ptr(ws), ws.numel(), stream_ptr(w.device)), "pp_best_correlation")
+        ws = workspace_for(w.device, lib.pp_workspace_bytes, _lib.ALGO_BCORR, w.n, max_length, num,
+                           int(self._orthogonalize))
+        call(lib.pp_best_correlation, "pp_best_correlation", w.device, ptr(w.tensor), w.ldx, w.b, w.n, num,
+             max_length, ratio, int(self._trunc_to_integer_multiple), int(self._orthogonalize), self._fold(), ptr(co),
+             ptr(cq), tb.pmax, ptr(periods), ptr(powers), ptr(bases), ptr(status), ptr(ws), ws.numel(),
+             stream_ptr(w.device))
         res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases), _export(w, status))
         if w.was_1d:
             if int(res.status[0]) == _lib.STATUS_NO_PERIOD:

@@ -19,11 +19,24 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._device import Workspace, ptr, stage_windows, stream_ptr, to_host
+from ._device import Workspace, call, ptr, stage_windows, stream_ptr, to_host
 from .periods import Periods, _export
 from .tables import get_tables
 
 MAX_ROUNDS = 64  # device-side cap on `num` (the reference's default num = len(data) is "way too many", :377)
+RMAX_FIRST = 1024      # dictionary rows the first launch holds factors for; larger windows get a second launch
+WORKSPACE_FRACTION = 0.5   # share of the free device memory the Cholesky factors of one launch may take
+
+
+def qo_workspace(lib, dev, n, pmax, num, rmax):
+    """Workspace for the QO kernels: factors for the full persistent grid, or as many CTAs as the memory budget holds
+    (the launch shrinks its grid to the workspace it is given; one factor of 4096 rows is 68 MB)."""
+    with torch.cuda.device(dev):
+        full = int(lib.pp_qo_workspace_bytes(n, pmax, num, rmax, 0))
+        one = int(lib.pp_qo_workspace_bytes(n, pmax, num, rmax, 1))
+        free, _ = torch.cuda.mem_get_info(dev)
+    budget = max(one, int(free * WORKSPACE_FRACTION))
+    return Workspace.get(dev, min(full, budget))   # a cached buffer that is already large enough is reused
 
 
 def indicator_rows(q: int, n: int, keep) -> np.ndarray:
@@ -48,11 +61,23 @@ class QOBatchResult:
     dict_q: object       # (B, num) int32: dictionary keys in insertion order
     dict_keep: object    # (B, num) int32: rows kept per key (0 = repeated period)
     n_dict: object       # (B,)
-    weights: object      # (B, rmax) float64, first n_weights[b] valid
+    weights: object      # (B, ldw) float64, first n_weights[b] valid -- or, with weights_off, the flat ragged array
     n_weights: object    # (B,)
     res: object          # (B, N) float64 or None
     status: object       # (B,) int32
     n: int = 0
+    weights_off: object = None   # (B,) int64 start of window b in the flat `weights` (ragged layout)
+    big: object = None           # {window: 1-D weights} of windows whose dictionary outgrew the first launch
+
+    def weights_of(self, b: int) -> np.ndarray:
+        g = (lambda t: t.cpu().numpy() if isinstance(t, torch.Tensor) else t)
+        nw = int(g(self.n_weights)[b])
+        if self.big is not None and b in self.big:
+            return np.array(g(self.big[b])[:nw])
+        if self.weights_off is not None:
+            o = int(g(self.weights_off)[b])
+            return np.array(g(self.weights[o:o + nw]))
+        return np.array(g(self.weights[b, :nw]))
 
     def window(self, b: int, data_row=None):
         """(dict, res) of window b in the reference's form."""
@@ -70,7 +95,7 @@ class QOBatchResult:
         per = np.array(g(self.periods)[b, :npd]).view(np.uint32) if g(self.periods).dtype != np.uint32 \
             else np.array(g(self.periods)[b, :npd])
         out = {"periods": per, "norms": np.array(g(self.norms)[b, :npd]),
-               "subspaces": build_subspaces(dq, dk, self.n), "weights": np.array(g(self.weights)[b, :nw]),
+               "subspaces": build_subspaces(dq, dk, self.n), "weights": self.weights_of(b),
                "basis_dictionary": {str(int(q)): int(k) for q, k in zip(dq, dk)}}
         return out, res
 
@@ -90,8 +115,12 @@ class QOPeriods(Periods):
 
     # ------------------------------------------------------------------ detection
     def find_periods(self, data, num=None, thresh=None, min_length=2, max_length=None, update_weights=True,
-                     return_res=True, rmax=None, **kwargs):
-        """QOPeriods.find_periods (QOPeriods.py:313-596)."""
+                     return_res=True, rmax=None, refine=1, **kwargs):
+        """QOPeriods.find_periods (QOPeriods.py:313-596).
+
+        Not in the reference: rmax (dictionary rows the first launch holds factors for; windows that outgrow it are
+        re-run with room for N rows, so no window is dropped), refine (steps of iterative refinement of the normal
+        equations, default 1), return_res."""
         if "test_function" in kwargs:
             raise NotImplementedError("custom test_function is evaluated on the device only in its default form")
         if kwargs:
@@ -111,29 +140,51 @@ class QOPeriods(Periods):
             if num > 1:
                 raise TypeError("thresh is None: the reference's default test multiplies it (QOPeriods.py:391)")
             thresh = 0.0
-        if rmax is None:
-            rmax = min(n, 1024)
+        retry_big = rmax is None
+        rmax = min(n, RMAX_FIRST) if rmax is None else int(rmax)
         tb = get_tables(max_length)
-        phi = tb.phi_device(w.device)
-        ws = Workspace.get(w.device, lib.pp_qo_workspace_bytes(n, max_length, num, rmax))
         dev = w.device
-        i32 = dict(dtype=torch.int32, device=dev)
-        f64 = dict(dtype=torch.float64, device=dev)
-        periods = torch.zeros((w.b, num), **i32)
-        norms = torch.zeros((w.b, num), **f64)
-        n_periods, n_dict, n_weights, status = (torch.zeros((w.b,), **i32) for _ in range(4))
-        dict_q, dict_keep = torch.zeros((w.b, num), **i32), torch.zeros((w.b, num), **i32)
-        weights = torch.zeros((w.b, (rmax + 1) & ~1), **f64)
-        res = torch.empty((w.b, n), **f64) if return_res else None
-        _lib.check(lib.pp_qo_find_periods(ptr(w.tensor), w.ldx, w.b, n, num, float(thresh), int(min_length),
-                                          int(max_length), int(self._trunc_to_integer_multiple), ptr(phi), tb.pmax,
-                                          int(rmax), ptr(periods), ptr(norms), ptr(n_periods), ptr(dict_q),
-                                          ptr(dict_keep), ptr(n_dict), ptr(n_weights), ptr(weights), ptr(res),
-                                          ptr(status), ptr(ws), ws.numel(), stream_ptr(dev)), "pp_qo_find_periods")
-        out = QOBatchResult(_export(w, periods, True), _export(w, norms), _export(w, n_periods), _export(w, dict_q),
-                            _export(w, dict_keep), _export(w, n_dict), _export(w, weights), _export(w, n_weights),
-                            _export(w, res), _export(w, status), n=n)
+        phi = tb.phi_device(dev)
+
+        def launch(x_ptr, ldx, count, rmax_l):
+            ldw = (rmax_l + 31) // 32 * 32
+            i32 = dict(dtype=torch.int32, device=dev)
+            f64 = dict(dtype=torch.float64, device=dev)
+            o = dict(periods=torch.zeros((count, num), **i32), norms=torch.zeros((count, num), **f64),
+                     n_periods=torch.zeros((count,), **i32), dict_q=torch.zeros((count, num), **i32),
+                     dict_keep=torch.zeros((count, num), **i32), n_dict=torch.zeros((count,), **i32),
+                     n_weights=torch.zeros((count,), **i32), weights=torch.zeros((count, ldw), **f64),
+                     res=torch.empty((count, n), **f64) if return_res else None, status=torch.zeros((count,), **i32))
+            ws = qo_workspace(lib, dev, n, int(max_length), num, rmax_l)
+            call(lib.pp_qo_find_periods, "pp_qo_find_periods", dev, x_ptr, ldx, count, n, num, float(thresh),
+                 int(min_length), int(max_length), int(self._trunc_to_integer_multiple), self._fold(), int(refine),
+                 ptr(phi), tb.pmax, int(rmax_l), ptr(None), 0, ptr(o["periods"]), ptr(o["norms"]), ptr(o["n_periods"]),
+                 ptr(o["dict_q"]), ptr(o["dict_keep"]), ptr(o["n_dict"]), ptr(o["n_weights"]), ptr(o["weights"]), ldw,
+                 ptr(o["res"]), ptr(o["status"]), ptr(ws), ws.numel(), _lib.profile_ptr(), stream_ptr(dev))
+            return o
+
+        o = launch(ptr(w.tensor), w.ldx, w.b, rmax)
+        big = None
+        if retry_big and rmax < n:
+            idx = torch.nonzero(o["status"] == _lib.STATUS_TOO_LARGE).flatten()
+            if idx.numel():
+                # dictionaries of more than rmax rows: re-run just those windows with room for N rows (more rows than
+                # samples is singular by rank); their padded outputs replace the first launch's
+                xb = torch.as_strided(w.tensor, (w.b, n), (w.ldx, 1))[idx].contiguous()
+                o2 = launch(ptr(xb), n, int(idx.numel()), n)
+                for key in ("periods", "norms", "n_periods", "dict_q", "dict_keep", "n_dict", "n_weights", "status"):
+                    o[key][idx] = o2[key]
+                if return_res:
+                    o["res"][idx] = o2["res"]
+                w2 = o2["weights"] if not w.from_host else o2["weights"].cpu()
+                big = {int(b): w2[i] for i, b in enumerate(idx.tolist())}
+        out = QOBatchResult(_export(w, o["periods"], True), _export(w, o["norms"]), _export(w, o["n_periods"]),
+                            _export(w, o["dict_q"]), _export(w, o["dict_keep"]), _export(w, o["n_dict"]),
+                            _export(w, o["weights"]), _export(w, o["n_weights"]), _export(w, o["res"]),
+                            _export(w, o["status"]), n=n, big=big)
         if w.was_1d:
+            if int(out.status[0]) == _lib.STATUS_TOO_LARGE:
+                raise ValueError("dictionary has more rows than rmax; pass a larger rmax")
             pair = out.window(0)
             self._output = self._output_bases = pair[0]
             return pair
@@ -323,12 +374,12 @@ class QOPeriodsWithGCDsExtracted(QOPeriods):
         return build_subspaces([int(k) for k in lay], list(lay.values()), N), lay
 
     def find_periods(self, data, num=None, thresh=None, min_length=2, max_length=None, update_weights=True,
-                     rmax=None, kmax=64, **kwargs):
+                     rmax=None, kmax=64, refine=1, **kwargs):
         arr = data if isinstance(data, torch.Tensor) else np.asarray(data, dtype=np.float64)
         was_1d = arr.ndim == 1
         batch = arr.reshape(1, -1) if was_1d else arr
         base = QOPeriods.find_periods(self, batch, num, thresh, min_length, max_length, update_weights,
-                                      return_res=True, rmax=rmax, **kwargs)
+                                      return_res=True, rmax=rmax, refine=refine, **kwargs)
         g = (lambda t: t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t))
         dq, nd, st = g(base.dict_q), g(base.n_dict), g(base.status)
         bsz, n = dq.shape[0], base.n
@@ -351,17 +402,20 @@ class QOPeriodsWithGCDsExtracted(QOPeriods):
         w = stage_windows(batch, self._device)
         dev = w.device
         if rmax is None:
-            rmax = min(n, 1024)
+            # rows of the largest layout (0 = all rows of that period), capped at N (more is singular by rank)
+            need = max([sum(v if v else int(k) for k, v in lay.items()) for lay in layouts if lay] + [32])
+            rmax = min(n, need)
         pmax = int(max(int(lq.max()), 2))
-        ws = Workspace.get(dev, lib.pp_qo_workspace_bytes(n, pmax, kmax, rmax))
+        ws = qo_workspace(lib, dev, n, pmax, kmax, int(rmax))
         t_lq, t_lr, t_ln = (torch.from_numpy(a).to(dev) for a in (lq, lr, ln))
-        weights = torch.zeros((bsz, (rmax + 1) & ~1), dtype=torch.float64, device=dev)
+        ldw = (int(rmax) + 31) // 32 * 32
+        weights = torch.zeros((bsz, ldw), dtype=torch.float64, device=dev)
         res = torch.empty((bsz, n), dtype=torch.float64, device=dev)
         n_weights = torch.zeros((bsz,), dtype=torch.int32, device=dev)
         status = torch.zeros((bsz,), dtype=torch.int32, device=dev)
-        _lib.check(lib.pp_qo_solve_rows(ptr(w.tensor), w.ldx, bsz, n, kmax, ptr(t_lq), ptr(t_lr), ptr(t_ln), pmax,
-                                        int(rmax), ptr(n_weights), ptr(weights), ptr(res), ptr(status), ptr(ws),
-                                        ws.numel(), stream_ptr(dev)), "pp_qo_solve_rows")
+        call(lib.pp_qo_solve_rows, "pp_qo_solve_rows", dev, ptr(w.tensor), w.ldx, bsz, n, kmax, ptr(t_lq), ptr(t_lr),
+             ptr(t_ln), pmax, int(refine), int(rmax), ptr(n_weights), ptr(weights), ldw, ptr(res), ptr(status),
+             ptr(ws), ws.numel(), stream_ptr(dev))
         out = QOGcdBatchResult(base, layouts, to_host(weights), to_host(n_weights), to_host(res), to_host(status), n=n)
         if was_1d:
             pair = out.window(0)

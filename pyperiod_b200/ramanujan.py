@@ -12,9 +12,9 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._device import Workspace, ptr, stage_windows, stream_ptr
+from ._device import Workspace, call, ptr, stage_windows, stream_ptr, workspace_for
 from .periods import _export
-from .qoperiods import QOBatchResult, QOPeriods
+from .qoperiods import RMAX_FIRST, QOBatchResult, QOPeriods, qo_workspace
 from .tables import get_tables
 
 TILE_WINDOWS = 2048  # windows whose folds are held at once (7.5 MB per window at qmax = 1365)
@@ -37,12 +37,11 @@ class RamanujanPeriods(QOPeriods):
         tb = get_tables(max_length)
         mu, phi = tb.mu_device(w.device), tb.phi_device(w.device)
         tile = min(TILE_WINDOWS, max(4, w.b))
-        ws = Workspace.get(w.device, lib.pp_ramanujan_workspace_bytes(w.n, min_length, max_length, tile))
+        ws = workspace_for(w.device, lib.pp_ramanujan_workspace_bytes, w.n, min_length, max_length, tile)
         norms = torch.zeros((w.b, max_length + 1), dtype=torch.float64, device=w.device)
         fn = lib.pp_ramanujan_norms_tf32 if self._precision == "tf32" else lib.pp_ramanujan_norms
-        _lib.check(fn(ptr(w.tensor), w.ldx, w.b, w.n, int(min_length), int(max_length), ptr(mu),
-                      ptr(phi), tb.pmax, tile, ptr(norms), max_length + 1, ptr(ws), ws.numel(),
-                      stream_ptr(w.device)), "pp_ramanujan_norms")
+        call(fn, "pp_ramanujan_norms", w.device, ptr(w.tensor), w.ldx, w.b, w.n, int(min_length), int(max_length),
+             ptr(mu), ptr(phi), tb.pmax, tile, ptr(norms), max_length + 1, ptr(ws), ws.numel(), stream_ptr(w.device))
         return norms
 
     def find_periods(self, x, min_length=2, max_length=None, select_periods=None):
@@ -60,10 +59,15 @@ class RamanujanPeriods(QOPeriods):
 
     # ------------------------------------------------------------------ periodogram + quadratic program
     def find_periods_with_weights(self, x, min_length=2, max_length=None, thresh=0.2, kmax=32, rmax=None,
-                                  return_res=True, **kwargs):
-        """RamanujanPeriods.py:88-122: periods over thresh * max norm -> dictionary -> normal equations."""
-        if "test_function" in kwargs:
-            raise NotImplementedError("custom test_function is not evaluated on the device")
+                                  return_res=True, refine=1, **kwargs):
+        """RamanujanPeriods.py:88-122: periods over thresh * max norm -> dictionary -> normal equations.
+
+        `test_function(norms) -> periods` replaces the threshold rule as in the reference (:94-101); it is a host
+        callable, evaluated between the periodogram kernel and the solve kernel (per window for a batch).
+        Every window is solved whatever the size of its dictionary (up to N rows; more is singular by rank): the
+        rows are counted first (pp_qo_dictionary_rows), windows above RMAX_FIRST rows go to a second launch sized
+        for the largest of them, and the weights come back in a ragged array."""
+        test_function = kwargs.pop("test_function", None)
         if kwargs:
             raise TypeError(f"unexpected arguments {sorted(kwargs)}")
         lib = _lib.load()
@@ -73,38 +77,64 @@ class RamanujanPeriods(QOPeriods):
             max_length = n // 3
         norms = self._norms_device(w, min_length, max_length)
         i32 = dict(dtype=torch.int32, device=dev)
-        while True:
-            periods = torch.zeros((w.b, kmax), **i32)
-            nper = torch.zeros((w.b,), **i32)
-            _lib.check(lib.pp_ramanujan_select(ptr(norms), w.b, max_length + 1, max_length + 1, float(thresh), kmax,
-                                               ptr(periods), ptr(nper), stream_ptr(dev)), "pp_ramanujan_select")
-            need = int(nper.max()) if w.b else 0
-            if need <= kmax:
-                break
-            kmax = need
-        if rmax is None:
-            rmax = min(n, 1024)
-        tb = get_tables(max_length)
+        if test_function is not None:
+            picked = [np.asarray(test_function(row), dtype=np.int64).flatten() for row in norms.cpu().numpy()]
+            kmax = max([len(v) for v in picked] + [1])
+            per_h = np.zeros((w.b, kmax), np.int32)
+            for b, v in enumerate(picked):
+                if len(v) and (v.min() < 1 or v.max() > n):
+                    raise ValueError("test_function must return periods in [1, len(x)]")
+                per_h[b, : len(v)] = v
+            periods = torch.from_numpy(per_h).to(dev)
+            nper = torch.tensor([len(v) for v in picked], **i32)
+        else:
+            while True:
+                periods = torch.zeros((w.b, kmax), **i32)
+                nper = torch.zeros((w.b,), **i32)
+                call(lib.pp_ramanujan_select, "pp_ramanujan_select", dev, ptr(norms), w.b, max_length + 1,
+                     max_length + 1, float(thresh), kmax, ptr(periods), ptr(nper), stream_ptr(dev))
+                need = int(nper.max()) if w.b else 0
+                if need <= kmax:
+                    break
+                kmax = need
+        pmax = int(max(int(periods.max()) if w.b else 2, max_length, 2))
+        tb = get_tables(pmax)
         phi = tb.phi_device(dev)
-        ws = Workspace.get(dev, lib.pp_qo_workspace_bytes(n, max_length, kmax, rmax))
+        # rows of every window's dictionary: sizes the factor storage and the ragged weights
+        rows = torch.zeros((w.b,), **i32)
+        call(lib.pp_qo_dictionary_rows, "pp_qo_dictionary_rows", dev, w.b, kmax, ptr(periods), ptr(nper), pmax, ptr(phi),
+             tb.pmax, ptr(rows), stream_ptr(dev))
+        solvable = rows <= n                              # more rows than samples: singular by rank, no storage
+        kept = torch.where(solvable, rows, torch.zeros_like(rows)).long()
+        woff = torch.cumsum(kept, 0) - kept               # exclusive prefix sum
+        total = int(kept.sum()) if w.b else 0
+        weights = torch.zeros((max(total, 1),), dtype=torch.float64, device=dev)
         dict_q, dict_keep = torch.zeros((w.b, kmax), **i32), torch.zeros((w.b, kmax), **i32)
         n_dict, n_weights, status = (torch.zeros((w.b,), **i32) for _ in range(3))
-        weights = torch.zeros((w.b, (rmax + 1) & ~1), dtype=torch.float64, device=dev)
         res = torch.empty((w.b, n), dtype=torch.float64, device=dev) if return_res else None
-        _lib.check(lib.pp_qo_solve(ptr(w.tensor), w.ldx, w.b, n, kmax, ptr(periods), ptr(nper), int(max_length),
-                                   ptr(phi), tb.pmax, int(rmax), ptr(dict_q), ptr(dict_keep), ptr(n_dict),
-                                   ptr(n_weights), ptr(weights), ptr(res), ptr(status), ptr(ws), ws.numel(),
-                                   stream_ptr(dev)), "pp_qo_solve")
-        sel_norms = torch.gather(norms, 1, periods.long())  # norms[periods] (:116), padded entries unused
+        first = RMAX_FIRST if rmax is None else int(rmax)
+        small = torch.nonzero(~solvable | (rows <= first)).flatten().int()
+        bigw = torch.nonzero(solvable & (rows > first)).flatten()
+        launches = [(small, min(first, max(int(kept[small.long()].max()) if small.numel() else 32, 32)))]
+        if bigw.numel():
+            order = bigw[torch.argsort(rows[bigw], descending=True)].int()   # longest factorisations first
+            launches.append((order, int(rows[bigw].max())))
+        for order, rmax_l in launches:
+            if order.numel() == 0:
+                continue
+            ws = qo_workspace(lib, dev, n, pmax, kmax, rmax_l)
+            call(lib.pp_qo_solve, "pp_qo_solve", dev, ptr(w.tensor), w.ldx, w.b, n, kmax, ptr(periods), ptr(nper), pmax,
+                 int(refine), ptr(phi), tb.pmax, int(rmax_l), ptr(order), int(order.numel()), ptr(dict_q), ptr(dict_keep),
+                 ptr(n_dict), ptr(n_weights), ptr(weights), 0, ptr(woff), ptr(res), ptr(status), ptr(ws), ws.numel(),
+                 stream_ptr(dev))
+        sel_norms = torch.gather(norms, 1, periods.long().clamp(max=max_length))  # norms[periods] (:116), padded entries unused
         out = QOBatchResult(_export(w, periods), _export(w, sel_norms), _export(w, nper), _export(w, dict_q),
                             _export(w, dict_keep), _export(w, n_dict), _export(w, weights), _export(w, n_weights),
-                            _export(w, res), _export(w, status), n=n)
+                            _export(w, res), _export(w, status), n=n, weights_off=_export(w, woff))
         if w.was_1d:
             st = int(out.status[0])
             if st == _lib.STATUS_SINGULAR:
                 raise np.linalg.LinAlgError("Singular matrix")  # the reference's np.linalg.solve raises here
-            if st == _lib.STATUS_TOO_LARGE:
-                raise ValueError("dictionary has more rows than rmax; pass a larger rmax")
             d, r = out.window(0)
             d["periods"] = np.asarray(d["periods"]).astype(np.int64)  # np.argwhere indices (:97-101)
             self._output = d

@@ -210,7 +210,61 @@ def gen_qo_gcd():
     save("qo_gcd", **out)
 
 
+# ------------------------------------------------------------------ 8. config 5 at its own shape (N = 4096, q <= 1365)
+CFG5_WINDOWS = (6, 14, 16)   # dictionaries of 1234, 2896 and 1324 rows (more than the 1024 the first launch holds)
+
+
+def _ram_cfg5_one(b):
+    x = synth.synth(4096, 50_000 + b)
+    r = RamanujanPeriods()
+    d, res = quiet(r.find_periods_with_weights, x, thresh=0.2)   # q = 2..1365; about 25 minutes per window
+    return b, d, res
+
+
+def gen_ram_cfg5():
+    """RamanujanPeriods.find_periods_with_weights(thresh=0.2) on three config-5 windows whose dictionaries have more
+    than 1024 rows (about 25 minutes per window for the reference; the windows run in parallel processes)."""
+    import multiprocessing as mp
+    out = {"windows": np.array(CFG5_WINDOWS)}
+    with mp.get_context("fork").Pool(len(CFG5_WINDOWS)) as pool:
+        for b, d, res in pool.map(_ram_cfg5_one, CFG5_WINDOWS):
+            out[f"w{b}_periods"], out[f"w{b}_sel_norms"] = np.array(d["periods"]), np.array(d["norms"])
+            out[f"w{b}_weights"], out[f"w{b}_res"] = d["weights"], res
+            out[f"w{b}_dict_keys"] = np.array([int(k) for k in d["basis_dictionary"]])
+            out[f"w{b}_dict_vals"] = np.array(list(d["basis_dictionary"].values()))
+    save("ram_cfg5", **out)
+
+
+# ------------------------------------------------------------------ 9. tie-heavy inputs (exactly periodic, integer valued)
+def tie_inputs(n=4096):
+    """Inputs on which p, 2p, 3p ... give bit-identical projections, so the reference's norms tie EXACTLY and its
+    strict '>' keeps the lowest period (Periods.py:512-515).  Regenerated from seeds by the tests."""
+    idx = np.arange(n)
+    out = {}
+    for p in (3, 7, 10, 12, 25):
+        rng = np.random.default_rng(900 + p)
+        out[f"binary{p}"] = np.tile(rng.integers(0, 2, p).astype(float), n // p + 1)[:n]
+        out[f"int{p}"] = np.tile(rng.integers(-5, 6, p).astype(float), n // p + 1)[:n]
+    out["square8"] = np.sign(np.sin(2 * np.pi * (idx + 0.5) / 8))
+    imp = np.zeros(n)
+    imp[::9] = 1.0
+    out["impulse9"] = imp
+    return out
+
+
+def gen_ties():
+    out = {}
+    for name, x in tie_inputs().items():
+        if not x.any():
+            continue
+        for tag, fn in (("norm", Periods().m_best), ("gamma", Periods().m_best_gamma)):
+            per, pw, bs = quiet(fn, x, num=1, max_length=1024)
+            out[f"{name}_{tag}_period"], out[f"{name}_{tag}_power"] = np.array(per), np.array(pw)
+            out[f"{name}_{tag}_base_sha"] = np.array(sha(bs))
+    save("ties", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["project", "readme", "mbest_stream", "s2l", "bcorr", "qo_ram", "qo_gcd"]
+    which = sys.argv[1:] or ["project", "readme", "mbest_stream", "s2l", "bcorr", "qo_ram", "qo_gcd"]   # + "ram_cfg5" (slow)
     for w in which:
         globals()["gen_" + w]()

@@ -317,8 +317,11 @@ def test_empty_batch_and_minimal_sizes(P):
             assert np.array_equal(got, op.project(x, p)), p
         else:
             np.testing.assert_allclose(got, op.project(x, p), rtol=1e-15)
+    # p > N: the reference pads to one row -- the projection is the data itself, nan with truncation
+    assert np.array_equal(P.project(x, 8), x) and np.array_equal(P.project(x, 8, return_single_period=True), x)
+    assert np.isnan(P.project(x, 8, True)).all()
     with pytest.raises(ValueError):
-        P.project(x, 8)
+        P.project(x, 0)
 
 
 def test_scaled_and_offset_windows(P):
@@ -468,3 +471,62 @@ def test_mbest_f32_nomination_mode_is_exact(P):
         assert np.array_equal(g(a.periods), g(b.periods)), k
         assert np.array_equal(g(a.sweeps), g(b.sweeps)), k
         np.testing.assert_allclose(g(b.powers), g(a.powers), rtol=1e-12)
+
+
+# ------------------------------------------------------------------ near-tie audit (exact re-ranking)
+def test_mbest_exact_ties_vs_reference_fixture(P):
+    """Exactly periodic integer-valued inputs: the projections onto p, 2p, 3p ... are bit-identical, the reference's
+    norms tie exactly and strict '>' keeps the lowest period (Periods.py:507-515).  Energies rebuilt from reciprocal
+    weights differ by an ulp there, so the device re-ranks every candidate inside the rounding bound the reference's
+    way.  Fixture: tests/golden/ties.npz (generated from the reference), every fold mode, m_best and m_best_gamma."""
+    from conftest import tie_inputs
+    from pyperiod_b200 import _lib
+    g = load_golden("ties")
+    inputs = tie_inputs()
+    names = sorted(inputs)
+    xb = np.stack([inputs[k] for k in names])
+    for mode in (_lib.FOLD_HIERARCHICAL, _lib.FOLD_DIRECT, _lib.FOLD_NOMINATE_F32, _lib.FOLD_HIERARCHICAL_NO_RIDERS):
+        for tag, gamma in (("norm", False), ("gamma", True)):
+            algo = P(fold_mode=mode)
+            res = (algo.m_best_gamma if gamma else algo.m_best)(xb, num=1, max_length=1024, return_bases=True)
+            assert res.status.tolist() == [0] * len(names)
+            for i, k in enumerate(names):
+                assert int(res.periods[i, 0]) == int(g[f"{k}_{tag}_period"][0]), (mode, tag, k, res.periods[i])
+                np.testing.assert_allclose(res.powers[i, 0], g[f"{k}_{tag}_power"][0], rtol=1e-12)
+                assert sha(res.bases[i]) == str(g[f"{k}_{tag}_base_sha"]), (mode, tag, k)
+            if not gamma:
+                assert (np.asarray(res.near_ties) >= 1).all()   # the multiples of the period are flagged as ties
+    # 1-D call (drop-in form) on one of them
+    per, pw, bs = P().m_best(inputs["binary7"], num=1, max_length=1024)
+    assert per.tolist() == [7] and abs(pw[0] - 1.0) < 1e-12
+
+
+def test_sweep_exact_ties_pick_the_lowest_period(P):
+    from conftest import tie_inputs
+    inputs = tie_inputs(2000)
+    for k in ("int7", "binary10", "square8", "impulse9"):
+        x = inputs[k]
+        _, bp, bv = P().sweep(x, metric="norm", max_length=600)
+        want = max(range(2, 601), key=lambda p: (op.periodic_norm(op.project(x, p)), -p))
+        assert int(bp[0]) == want == int("".join(c for c in k if c.isdigit())), (k, int(bp[0]), want)
+        np.testing.assert_allclose(bv[0], op.periodic_norm(op.project(x, want)), rtol=1e-13)
+
+
+def test_near_ties_are_zero_on_noisy_windows_and_flagged_on_clean_sines(P):
+    """Inputs with a noise floor never have two candidates inside the rounding bound (near_ties == 0: the exact-list
+    claim covers them).  A clean sine is the excluded class: p, 2p, 3p ... agree to rounding, the reference's own pick
+    among them depends on its BLAS; the device reports the tie and returns a multiple of the true period whose power
+    is 1 to rounding.  With the gamma norm (energy / p) there is no tie and the fundamental wins as in the reference."""
+    xb = synth.synth_batch(32, 4096, 30_000)
+    res = P().m_best(xb, num=10, max_length=1024)
+    assert np.asarray(res.near_ties).tolist() == [0] * 32
+    n = np.arange(4096)
+    for p0 in (10, 12, 25):
+        x = np.sin(2 * np.pi * n / p0)
+        r = P().m_best(x[None, :], num=1, max_length=1024)
+        assert int(r.periods[0, 0]) % p0 == 0 and int(r.near_ties[0]) == 1
+        assert abs(float(r.powers[0, 0]) - 1.0) < 1e-12
+        rg = P().m_best_gamma(x[None, :], num=1, max_length=1024)
+        per0, pw0, _ = op.m_best_gamma(x, 1, 1024)
+        assert int(rg.periods[0, 0]) == int(per0[0]) == p0
+        np.testing.assert_allclose(rg.powers[0, 0], pw0[0], rtol=1e-12)

@@ -121,3 +121,58 @@ def test_qo_gcds_extracted_vs_golden():
         db, rb = out.window(b)
         assert db["basis_dictionary"] == d1["basis_dictionary"]
         assert np.array_equal(db["weights"], d1["weights"]) and np.array_equal(rb, r1)
+
+
+# ------------------------------------------------------------------ dictionaries of any size (no row cap)
+def _weights_close(got, want, gram_cond, what):
+    """Normwise agreement of two fp64 solutions of the same normal equations: both carry a forward error of
+    about cond(G) * eps, so that is the floor; 1e-10 relative is asked wherever the conditioning allows it."""
+    err = np.max(np.abs(got - want)) / np.max(np.abs(want))
+    tol = max(1e-10, 50 * gram_cond * 2.2e-16)
+    assert err <= tol, (what, err, tol, gram_cond)
+
+
+def test_qo_weights_normwise_1e10(QO):
+    """North-star tolerance: weights within 1e-10 (relative to the largest weight) of the reference's LU solution on
+    the golden config-5 QO windows (cond(G) of a few thousand), residuals to 1e-12."""
+    g = load_golden("qo_ram_synth")
+    xb = synth.synth_batch(2, 4096, 50_000)
+    out = QO().find_periods(xb, num=4, thresh=0.05)
+    for b in range(2):
+        d, res = out.window(b)
+        w0 = g[f"qo_{b}_weights"]
+        assert np.max(np.abs(d["weights"] - w0)) / np.max(np.abs(w0)) <= 1e-10
+        np.testing.assert_allclose(res, g[f"qo_{b}_res"], rtol=0, atol=1e-12)
+
+
+def test_qo_second_launch_for_large_dictionaries(QO, monkeypatch):
+    """Windows whose dictionary outgrows the first launch are re-run with room for N rows: same results as a single
+    launch that had the room from the start, and as the oracle."""
+    from pyperiod_b200 import qoperiods
+    xb = synth.synth_batch(6, 1500, 8800)
+    ref = QO().find_periods(xb, num=4, thresh=0.05, max_length=400)
+    monkeypatch.setattr(qoperiods, "RMAX_FIRST", 96)
+    out = QO().find_periods(xb, num=4, thresh=0.05, max_length=400)
+    assert out.big is not None and len(out.big) >= 1
+    assert out.status.tolist() == ref.status.tolist() == [0] * 6
+    for b in range(6):
+        d, res = out.window(b)
+        d1, res1 = ref.window(b)
+        assert np.array_equal(np.asarray(d["periods"]), np.asarray(d1["periods"]))
+        assert d["basis_dictionary"] == d1["basis_dictionary"]
+        np.testing.assert_allclose(d["weights"], d1["weights"], rtol=0, atol=1e-12 * np.max(np.abs(d1["weights"])))
+        np.testing.assert_allclose(res, res1, rtol=0, atol=1e-13)
+        d0, res0 = oq.find_periods(xb[b], num=4, thresh=0.05, max_length=400)
+        assert np.array_equal(np.asarray(d["periods"]), np.asarray(d0["periods"]))
+        np.testing.assert_allclose(res, res0, rtol=0, atol=1e-11)
+
+
+def test_qo_rows_beyond_samples_are_singular(QO):
+    """More dictionary rows than samples: A A^T is singular by rank.  The reference's LU either raises LinAlgError or
+    returns rounding noise; the device reports SINGULAR and keeps the previous round's outputs (QOPeriods.py:552-559)."""
+    x = synth.synth(240, 77)
+    out = QO().find_periods(x[None, :], num=6, thresh=0.0, max_length=119)
+    st = int(out.status[0])
+    assert st in (0, 3)
+    if st == 3:
+        assert int(out.n_weights[0]) <= 240

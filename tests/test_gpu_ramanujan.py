@@ -84,3 +84,93 @@ def test_tf32_option_tracks_fp64():
             da, _ = ra.window(i)
             db, _ = rb.window(i)
             assert np.array_equal(np.asarray(da["periods"]), np.asarray(db["periods"]))
+
+
+# ------------------------------------------------------------------ config 5 at its own shape (N = 4096, q <= 1365)
+CFG5_PERIODS = {   # what thresh = 0.2 selects on these config-5 windows (fp64 periodogram), and the dictionary rows
+    6: ([23, 24, 75, 252, 390, 528], 1234),
+    14: None,      # 14 periods, 2896 rows: taken from the periodogram in the test
+    18: ([80, 132, 134, 135, 136, 138, 152, 336, 396, 406, 672], 2170),   # cond(G) = 3.8e12
+}
+
+
+def test_cfg5_shape_periodogram_vs_closed_form(R):
+    """RamanujanPeriods.find_periods at config 5's own shape (N = 4096, q = 2..1365) against the fp64 closed form."""
+    x = synth.synth(4096, 50_006)
+    got = R().find_periods(x)
+    want = oram.norms_closed_form_f64(x)
+    assert got.shape == want.shape == (1366,)
+    np.testing.assert_allclose(got[2:], want[2:], rtol=1e-10, atol=0)
+
+
+def _check_against_refined(x, d, res, w_ref=None, res_ref=None):
+    """The device solves the reference's normal equations at least as accurately as the reference's own LU: both are
+    compared with a solution refined in extended precision.  (cond(G) reaches 1e14 on config-5 dictionaries: the LU
+    weights are then good to 3e-4 only, so 'equal to the reference' can mean no more than 'within its own error'.)"""
+    from conftest import refined_normal_equations
+    from oracle import qo as oq
+    a, layout = oq.get_subspaces(np.asarray(d["periods"]), len(x))
+    assert d["basis_dictionary"] == layout
+    w_star, res_star, w_lu = refined_normal_equations(a, x)
+    if w_ref is None:
+        w_ref, res_ref = w_lu, x - a.T @ w_lu
+    scale = float(np.max(np.abs(w_star)))
+    err_gpu = float(np.max(np.abs(d["weights"] - w_star))) / scale
+    err_ref = float(np.max(np.abs(w_ref - w_star))) / scale
+    assert err_gpu <= max(1e-10, err_ref), (err_gpu, err_ref)
+    assert float(np.max(np.abs(d["weights"] - w_ref))) / scale <= max(1e-10, 2.0 * err_ref)
+    rerr_gpu = float(np.max(np.abs(res - res_star)))
+    rerr_ref = float(np.max(np.abs(res_ref - res_star)))
+    assert rerr_gpu <= max(1e-11, rerr_ref), (rerr_gpu, rerr_ref)
+    assert float(np.max(np.abs(res - res_ref))) <= max(1e-11, 2.0 * rerr_ref)
+    return err_gpu, err_ref
+
+
+def test_cfg5_large_dictionaries_are_solved(R):
+    """Dictionaries of more than 1024 rows (a quarter of config 5's windows) are solved like any other."""
+    xb = np.stack([synth.synth(4096, 50_000 + b) for b in (6, 14, 18, 2)])
+    out = R().find_periods_with_weights(xb, thresh=0.2)
+    assert out.status.tolist() == [0, 0, 0, 0]
+    rows = [int(v) for v in out.n_weights]
+    assert rows[0] == 1234 and rows[1] == 2896 and rows[2] == 2170 and rows[3] == 396
+    assert np.asarray(out.periods[0][: int(out.n_periods[0])]).tolist() == CFG5_PERIODS[6][0]
+    assert np.asarray(out.periods[2][: int(out.n_periods[2])]).tolist() == CFG5_PERIODS[18][0]
+    for i in range(4):
+        d, res = out.window(i)
+        _check_against_refined(xb[i], d, res)
+
+
+def test_cfg5_reference_fixture(R):
+    """Reference-generated fixture (tests/golden/ram_cfg5.npz, make_golden.py ram_cfg5): find_periods_with_weights at
+    config 5's shape on windows whose dictionaries have 1234 / 2896 / 1324 rows.  Periods, dictionary layout and norms
+    as the reference returns them; weights and residual within the reference's own distance from the refined
+    solution of its normal equations."""
+    import os
+    from conftest import GOLDEN
+    if not os.path.exists(os.path.join(GOLDEN, "ram_cfg5.npz")):
+        pytest.skip("ram_cfg5.npz not generated")
+    g = load_golden("ram_cfg5")
+    for b in g["windows"].tolist():
+        x = synth.synth(4096, 50_000 + b)
+        d, res = R().find_periods_with_weights(x, thresh=0.2)
+        assert np.asarray(d["periods"]).tolist() == g[f"w{b}_periods"].tolist()
+        assert [int(k) for k in d["basis_dictionary"]] == g[f"w{b}_dict_keys"].tolist()
+        assert list(d["basis_dictionary"].values()) == g[f"w{b}_dict_vals"].tolist()
+        np.testing.assert_allclose(d["norms"], g[f"w{b}_sel_norms"], rtol=2e-6)
+        _check_against_refined(x, d, res, g[f"w{b}_weights"], g[f"w{b}_res"])
+
+
+def test_test_function_replaces_threshold(R):
+    """test_function(norms) -> periods (RamanujanPeriods.py:94-101), a host callable between the two kernels."""
+    from oracle import qo as oq
+    x = synth.synth(1024, 50_001)
+    pick = lambda norms: np.argsort(norms)[-3:][::-1]
+    d, res = R().find_periods_with_weights(x, test_function=pick)
+    norms = R().find_periods(x)
+    want = pick(norms)
+    assert np.asarray(d["periods"]).tolist() == want.tolist()
+    a, layout = oq.get_subspaces(want, 1024)
+    w0, rec0 = oq.solve_quadratic(x, a)
+    assert d["basis_dictionary"] == layout
+    np.testing.assert_allclose(d["weights"], w0, rtol=0, atol=1e-10 * np.max(np.abs(w0)))
+    np.testing.assert_allclose(res, x - rec0, rtol=0, atol=1e-12)

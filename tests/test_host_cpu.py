@@ -168,7 +168,7 @@ def test_hierarchical_job_table_covers_every_candidate_once(lib_path):
     evaluates every candidate period exactly once (hosts, riders, chains)."""
     from pyperiod_b200 import _lib
     lib = _lib.load()
-    assert lib.pp_get_fold_mode() == _lib.FOLD_HIERARCHICAL
+    assert _lib.default_fold_mode() == _lib.FOLD_HIERARCHICAL
     for n, pmin, pmax in [(4096, 2, 1024), (4096, 2, 1365), (2000, 2, 300), (4096, 2, 682), (512, 5, 64), (128, 40, 64),
                           (8192, 2, 2729), (3001, 3, 999), (2000, 17, 1000), (1000, 17, 500), (300, 2, 100),
                           (64, 2, 7), (4096, 600, 1024), (1024, 2, 512)]:

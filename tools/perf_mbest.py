@@ -11,7 +11,7 @@ dev = torch.from_numpy(stream).cuda()
 win = torch.as_strided(dev, (B, 4096), (512, 1))
 P = Periods()
 prof = torch.zeros(8, dtype=torch.int64, device="cuda")
-_lib.load().pp_set_profile_buffer(prof.data_ptr())
+_lib.set_profile_buffer(prof)
 for mode in modes:
     _lib.set_fold_mode({"direct": _lib.FOLD_DIRECT, "norider": _lib.FOLD_HIERARCHICAL_NO_RIDERS, "f32": _lib.FOLD_NOMINATE_F32}.get(mode, _lib.FOLD_HIERARCHICAL))
     for name, fn in (("m_best", P.m_best), ("m_best_gamma", P.m_best_gamma)):
