@@ -267,7 +267,7 @@ class Periods:
         if kw:
             raise TypeError(f"unexpected arguments {sorted(kw)}")
         lib = _lib.load()
-        w = stage_windows(data, self._device)
+        w = stage_windows(data, self._device, pipeline=True)
         if return_bases is None:
             return_bases = w.was_1d
         n_periods = math.floor(w.n / 2) if n_periods is None else int(n_periods)
@@ -275,16 +275,21 @@ class Periods:
         co, cq, _, _ = tb.device(w.device)
         orth = int(self._orthogonalize)
         ws = workspace_for(w.device, lib.pp_workspace_bytes, _lib.ALGO_S2L, w.n, n_periods, 0, orth)
+        cur = torch.cuda.current_stream(w.device)
+        plan = list(w.launch_plan()) if w.plan is None else None   # a pipelined plan issues its copies as it is walked
         while True:
             periods = torch.empty((w.b, kmax), dtype=torch.int32, device=w.device)
             powers = torch.empty((w.b, kmax), dtype=torch.float64, device=w.device)
             bases = torch.empty((w.b, kmax, w.n), dtype=torch.float64, device=w.device) if return_bases else None
             count = torch.empty((w.b,), dtype=torch.int32, device=w.device)
             status = torch.empty((w.b,), dtype=torch.int32, device=w.device)
-            call(lib.pp_small_to_large, "pp_small_to_large", w.device, ptr(w.tensor), w.ldx, w.b, w.n, thresh,
-                 n_periods, int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq), tb.pmax, kmax,
-                 ptr(periods), ptr(powers), ptr(bases), ptr(count), ptr(status), ptr(ws), ws.numel(),
-                 stream_ptr(w.device))
+            for b0, b1, ready in (plan if plan is not None else w.launch_plan()):
+                if ready is not None:
+                    cur.wait_event(ready)
+                call(lib.pp_small_to_large, "pp_small_to_large", w.device, C.c_void_p(w.ptr + b0 * w.ldx * 8), w.ldx,
+                     b1 - b0, w.n, thresh, n_periods, int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq),
+                     tb.pmax, kmax, ptr(periods[b0:b1]), ptr(powers[b0:b1]), ptr(None if bases is None else bases[b0:b1]),
+                     ptr(count[b0:b1]), ptr(status[b0:b1]), ptr(ws), ws.numel(), stream_ptr(w.device))
             need = int(count.max()) if w.b else 0
             if need <= kmax or not w.was_1d:
                 break
@@ -305,7 +310,7 @@ class Periods:
         if kw:
             raise TypeError(f"unexpected arguments {sorted(kw)}")
         lib = _lib.load()
-        w = stage_windows(data, self._device)
+        w = stage_windows(data, self._device, pipeline=True)
         if return_bases is None:
             return_bases = w.was_1d
         max_length = math.floor(w.n / 3) if max_length is None else int(max_length)
@@ -317,10 +322,15 @@ class Periods:
         status = torch.empty((w.b,), dtype=torch.int32, device=w.device)
         ws = workspace_for(w.device, lib.pp_workspace_bytes, _lib.ALGO_BCORR, w.n, max_length, num,
                            int(self._orthogonalize))
-        call(lib.pp_best_correlation, "pp_best_correlation", w.device, ptr(w.tensor), w.ldx, w.b, w.n, num,
-             max_length, ratio, int(self._trunc_to_integer_multiple), int(self._orthogonalize), self._fold(), ptr(co),
-             ptr(cq), tb.pmax, ptr(periods), ptr(powers), ptr(bases), ptr(status), ptr(ws), ws.numel(),
-             stream_ptr(w.device))
+        cur = torch.cuda.current_stream(w.device)
+        for b0, b1, ready in w.launch_plan():
+            if ready is not None:
+                cur.wait_event(ready)
+            call(lib.pp_best_correlation, "pp_best_correlation", w.device, C.c_void_p(w.ptr + b0 * w.ldx * 8), w.ldx,
+                 b1 - b0, w.n, num, max_length, ratio, int(self._trunc_to_integer_multiple), int(self._orthogonalize),
+                 self._fold(), ptr(co), ptr(cq), tb.pmax, ptr(periods[b0:b1]), ptr(powers[b0:b1]),
+                 ptr(None if bases is None else bases[b0:b1]), ptr(status[b0:b1]), ptr(ws), ws.numel(),
+                 stream_ptr(w.device))
         res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases), _export(w, status))
         if w.was_1d:
             if int(res.status[0]) == _lib.STATUS_NO_PERIOD:

@@ -12,6 +12,7 @@ Deviation from the reference: the stray `print(nonzero_periods)` at QOPeriods.py
 """
 from __future__ import annotations
 
+import ctypes as C
 import itertools
 from dataclasses import dataclass
 
@@ -129,7 +130,7 @@ class QOPeriods(Periods):
             raise NotImplementedError("only the reference's default branch (orthogonalize=False, "
                                       "update_weights=True, basis_type='natural') is implemented")
         lib = _lib.load()
-        w = stage_windows(data, self._device)
+        w = stage_windows(data, self._device, pipeline=True)
         n = w.n
         if max_length is None:
             max_length = int(np.floor(n / 3))
@@ -145,8 +146,11 @@ class QOPeriods(Periods):
         tb = get_tables(max_length)
         dev = w.device
         phi = tb.phi_device(dev)
+        cur = torch.cuda.current_stream(dev)
 
-        def launch(x_ptr, ldx, count, rmax_l):
+        def launch(x_ptr, ldx, count, rmax_l, plan):
+            """One pp_qo_find_periods call per piece of `plan` ((first, end, upload event) triples) into one set of
+            batch outputs."""
             ldw = (rmax_l + 31) // 32 * 32
             i32 = dict(dtype=torch.int32, device=dev)
             f64 = dict(dtype=torch.float64, device=dev)
@@ -156,14 +160,19 @@ class QOPeriods(Periods):
                      n_weights=torch.zeros((count,), **i32), weights=torch.zeros((count, ldw), **f64),
                      res=torch.empty((count, n), **f64) if return_res else None, status=torch.zeros((count,), **i32))
             ws = qo_workspace(lib, dev, n, int(max_length), num, rmax_l)
-            call(lib.pp_qo_find_periods, "pp_qo_find_periods", dev, x_ptr, ldx, count, n, num, float(thresh),
-                 int(min_length), int(max_length), int(self._trunc_to_integer_multiple), self._fold(), int(refine),
-                 ptr(phi), tb.pmax, int(rmax_l), ptr(None), 0, ptr(o["periods"]), ptr(o["norms"]), ptr(o["n_periods"]),
-                 ptr(o["dict_q"]), ptr(o["dict_keep"]), ptr(o["n_dict"]), ptr(o["n_weights"]), ptr(o["weights"]), ldw,
-                 ptr(o["res"]), ptr(o["status"]), ptr(ws), ws.numel(), _lib.profile_ptr(), stream_ptr(dev))
+            for b0, b1, ready in plan:
+                if ready is not None:
+                    cur.wait_event(ready)
+                sl = lambda t: ptr(None if t is None else t[b0:b1])
+                call(lib.pp_qo_find_periods, "pp_qo_find_periods", dev, C.c_void_p(x_ptr + b0 * ldx * 8), ldx, b1 - b0,
+                     n, num, float(thresh), int(min_length), int(max_length), int(self._trunc_to_integer_multiple),
+                     self._fold(), int(refine), ptr(phi), tb.pmax, int(rmax_l), ptr(None), 0, sl(o["periods"]),
+                     sl(o["norms"]), sl(o["n_periods"]), sl(o["dict_q"]), sl(o["dict_keep"]), sl(o["n_dict"]),
+                     sl(o["n_weights"]), sl(o["weights"]), ldw, sl(o["res"]), sl(o["status"]), ptr(ws), ws.numel(),
+                     _lib.profile_ptr(), stream_ptr(dev))
             return o
 
-        o = launch(ptr(w.tensor), w.ldx, w.b, rmax)
+        o = launch(w.ptr, w.ldx, w.b, rmax, w.launch_plan())
         big = None
         if retry_big and rmax < n:
             idx = torch.nonzero(o["status"] == _lib.STATUS_TOO_LARGE).flatten()
@@ -171,7 +180,7 @@ class QOPeriods(Periods):
                 # dictionaries of more than rmax rows: re-run just those windows with room for N rows (more rows than
                 # samples is singular by rank); their padded outputs replace the first launch's
                 xb = torch.as_strided(w.tensor, (w.b, n), (w.ldx, 1))[idx].contiguous()
-                o2 = launch(ptr(xb), n, int(idx.numel()), n)
+                o2 = launch(xb.data_ptr(), n, int(idx.numel()), n, [(0, int(idx.numel()), None)])
                 for key in ("periods", "norms", "n_periods", "dict_q", "dict_keep", "n_dict", "n_weights", "status"):
                     o[key][idx] = o2[key]
                 if return_res:
