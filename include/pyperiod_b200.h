@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 2
+#define PP_ABI_VERSION 3
 
 /* sweep metrics */
 #define PP_METRIC_NORM 0   /* ||proj_p|| / sqrt(N)                 Periods.py:221-241, 507-508 */
@@ -179,16 +179,27 @@ int pp_best_correlation(const double *x, int64_t ldx, int32_t B, int32_t N, int3
  * with R > rmax reports PP_STATUS_TOO_LARGE (rows needed in n_weights) and keeps the previous round's
  * outputs, so the caller can re-run just those windows (`order`) with a larger rmax.
  *
- * Workspace: pp_qo_workspace_bytes(N, pmax, num, rmax, ctas) holds the factors of `ctas` concurrent windows
+ * Workspace: pp_qo_workspace_bytes(N, pmax, num, rmax, ctas, basis) holds the factors of `ctas` concurrent windows
  * (0 = one per CTA of the full persistent grid); a smaller workspace only lowers the number of CTAs launched.
  * order (nullable): n_order window indices to process instead of all B (outputs stay indexed by window).
  * phi: device int32 table of Euler's totient for 0..table_pmax.
  * Outputs: periods u32[B,num] (found order, duplicates possible), norms f64[B,num], n_periods[B];
  * dictionary dict_q/dict_keep i32[B,num] in insertion order with n_dict[B]; weights f64[B,ldw]
  * (ldw >= rmax rounded up to 32) with n_weights[B]; res f64[B,N] (nullable); status[B]. */
-size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax, int32_t ctas);
+/* basis (QOPeriods(basis_type=...), QOPeriods.py:153-155, 940-974):
+ *   PP_BASIS_NATURAL    rows 1[n = i (mod q)] (default; Cholesky on the FP64 tensor cores as described above)
+ *   PP_BASIS_RAMANUJAN  rows c_q((n - i) mod q) (QOPeriods.py:970-971, 1005-1052).  The q shifted rows of a period span
+ *       only phi(q) dimensions, so G is singular by construction; the reference's LU of the rounding-perturbed matrix
+ *       yields a reconstruction equal to the orthogonal projection onto the row space (to 1e-14, measured), which is
+ *       computed here by conjugate gradients with the rows applied implicitly (folds and circular correlations).
+ *       Periods, dictionary, norms and residual match the reference; the weights are the minimum-norm solution (the
+ *       reference's are one arbitrary solution of a singular system).  rmax is then only the capacity of `weights`
+ *       (rows <= sum of the periods); a window that does not converge reports PP_STATUS_GUARD. */
+#define PP_BASIS_NATURAL 0
+#define PP_BASIS_RAMANUJAN 1
+size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax, int32_t ctas, int32_t basis);
 int pp_qo_find_periods(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t num, double thresh,
-                       int32_t pmin, int32_t pmax, int32_t trunc, int32_t fold_mode, int32_t refine,
+                       int32_t pmin, int32_t pmax, int32_t trunc, int32_t fold_mode, int32_t refine, int32_t basis,
                        const int32_t *phi, int32_t table_pmax, int32_t rmax, const int32_t *order,
                        int32_t n_order, uint32_t *periods, double *norms, int32_t *n_periods, int32_t *dict_q,
                        int32_t *dict_keep, int32_t *n_dict, int32_t *n_weights, double *weights, int64_t ldw,
@@ -220,6 +231,22 @@ int pp_qo_solve_rows(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t
                      const int32_t *dict_rows, const int32_t *n_dict, int32_t pmax, int32_t refine, int32_t rmax,
                      int32_t *n_weights, double *weights, int64_t ldw, double *res, int32_t *status,
                      void *workspace, size_t workspace_bytes, void *stream);
+
+/* ---- QOPeriods.get_periods (QOPeriods.py:719-741 with concatenate_periods :854-887 and
+ *      stack_pairwise_gcd_subspaces :889-938), batched ------------------------------------------------------
+ * Window b: dictionary entries dict_q[b, 0:n_dict[b]) with dict_keep[b, k] weights each (as pp_qo_find_periods /
+ * pp_qo_solve return them; weights at weights + weights_off[b], or + b * ldw when weights_off is null).  The
+ * weights are zero padded to one period each and concatenated (sum of q entries); out + out_off[b] receives that
+ * vector minus its orthogonal projection onto the row space of the pairwise-GCD matrix (+-comb rows of every
+ * pair's gcd, all shifts) -- what every decomp_type of the reference computes ("row reduction", "lu", "qr" and
+ * lstsq differ only in how they get rid of the dependent rows).  Conjugate gradients on the normal equations with
+ * the rows applied implicitly; iters[b] = steps taken.  tmax / rmax: the largest sum of q and the largest number
+ * of rows (sum of the pairs' gcds) in the batch; 2 * tmax + 3 * rmax doubles must fit in shared memory.
+ * status: PP_STATUS_OK, PP_STATUS_GUARD (not converged), PP_STATUS_TOO_LARGE (window exceeds tmax / rmax). */
+int pp_qo_get_periods(int32_t B, int32_t kmax, int32_t tmax, int32_t rmax, const int32_t *dict_q,
+                      const int32_t *dict_keep, const int32_t *n_dict, const double *weights, int64_t ldw,
+                      const int64_t *weights_off, double *out, const int64_t *out_off, int32_t *iters,
+                      int32_t *status, void *stream);
 
 /* ---- RamanujanPeriods.find_periods (RamanujanPeriods.py:67-86, 124-169) ------------------
  * norms[b, q] = sum_n (sum_i <x, r_i> r_i)[n]^2 over the q-row Ramanujan dictionary of period q,

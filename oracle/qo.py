@@ -4,7 +4,7 @@ Numpy restatement of pyPeriod/QOPeriods.py:
   find_periods      :313-596 (default branch: _orthogonalize False, update_weights True)
   _update_weights   :598-643
   get_subspaces     :807-852
-  Pp / Pp_column    :940-1003 (basis_type "natural")
+  Pp / Pp_column    :940-1003 (basis_type "natural"), Cq :1005-1052 (basis_type "ramanujan")
   solve_quadratic   :743-805
   get_periods       :719-741, concatenate_periods :854-887,
   stack_pairwise_gcd_subspaces :889-938, reduce_rows :86-94
@@ -43,8 +43,28 @@ def indicator_rows(p: int, n: int, keep=None) -> np.ndarray:
     return rows
 
 
-def get_subspaces(periods, n: int):
+def ramanujan_rows(q: int, n: int, keep=None) -> np.ndarray:
+    """Ramanujan-basis rows: row i = roll(c_q, i) tiled to n, c_q = real part of the sum of exp(2 pi i k m / q) over
+    k coprime to q -- summed the way the reference sums it (QOPeriods.py:1037-1045), i.e. with its 1e-13 rounding
+    noise; first `keep` rows (QOPeriods.py:968-974)."""
+    q = int(q)
+    vec = np.zeros(q, dtype=complex)
+    ks = [k for k in range(1, q + 1) if np.gcd(k, q) == 1]
+    for i in range(q):
+        for k in ks:
+            vec[i] = vec[i] + np.exp(1j * 2 * np.pi * k * i / q)
+    reps = int(np.ceil(n / q))
+    rows = np.zeros((q, int(n)))
+    for i in range(q):
+        rows[i] = np.real(np.tile(np.roll(vec, i), reps))[: int(n)]
+    if keep:
+        rows = rows[:keep]
+    return rows
+
+
+def get_subspaces(periods, n: int, basis: str = "natural"):
     """Stacked dictionary and {str(q): rows kept}.  QOPeriods.py:807-852."""
+    rows_of = ramanujan_rows if basis == "ramanujan" else indicator_rows
     seen = set()
     dim_before = 0
     layout = {}
@@ -55,7 +75,7 @@ def get_subspaces(periods, n: int):
         dim_before = dim
     blocks = [np.zeros((0, n))]
     for q, keep in layout.items():
-        blocks.append(indicator_rows(int(q), n, keep))
+        blocks.append(rows_of(int(q), n, keep))
     return np.vstack(blocks), layout
 
 
@@ -94,10 +114,14 @@ def solve_quadratic(x: np.ndarray, a: np.ndarray, kind: str = "solve"):
 
 
 def find_periods(x: np.ndarray, num=None, thresh=None, min_length: int = 2, max_length=None,
-                 trunc: bool = False, test_function=None, gcds_extracted: bool = False):
+                 trunc: bool = False, test_function=None, gcds_extracted: bool = False, basis: str = "natural"):
     """QOPeriods.find_periods, default branch.  QOPeriods.py:313-596.  `gcds_extracted` swaps in the
-    dictionary layout of the QOPeriodsWithGCDsExtracted subclass (same loop, inherited)."""
-    get_subspaces = get_subspaces_gcds_extracted if gcds_extracted else globals()["get_subspaces"]
+    dictionary layout of the QOPeriodsWithGCDsExtracted subclass (same loop, inherited); `basis` is the
+    instance's basis_type ("natural" or "ramanujan", QOPeriods.py:153-155, 847-850)."""
+    if gcds_extracted:
+        get_subspaces = get_subspaces_gcds_extracted
+    else:
+        get_subspaces = lambda found, n_: globals()["get_subspaces"](found, n_, basis)
     n = len(x)
     if max_length is None:
         max_length = int(np.floor(n / 3))

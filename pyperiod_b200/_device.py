@@ -221,5 +221,17 @@ def ptr(t) -> C.c_void_p:
     return C.c_void_p(0 if t is None else t.data_ptr())
 
 
+PINNED_D2H_MIN_BYTES = 1 << 20
+
+
 def to_host(t: torch.Tensor) -> np.ndarray:
-    return t.cpu().numpy()
+    """Device tensor -> numpy.  Large results travel through page-locked memory (torch's caching host allocator
+    reuses the blocks): a pageable `.cpu()` of the 2 GB of residuals of a 65,536-window QO batch runs at a
+    quarter of the PCIe rate."""
+    if t.device.type != "cuda" or t.numel() * t.element_size() < PINNED_D2H_MIN_BYTES:
+        return t.cpu().numpy()
+    src = t if t.is_contiguous() else t.contiguous()
+    host = torch.empty(src.shape, dtype=src.dtype, pin_memory=True)
+    host.copy_(src, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return host.numpy()

@@ -17,6 +17,7 @@
 #include "pp_common.cuh"
 #include "pp_sweep.cuh"
 #include "pp_chol.cuh"
+#include "pp_cg.cuh"
 #include "pp_host.cuh"
 
 namespace pp {
@@ -28,10 +29,13 @@ constexpr int kQoCtasPerSm = PP_QO_CTAS;  // persistent CTAs per SM of the QO ke
 
 struct QoPlan {
   int xs_len, n_even, rmax, num, seen_words, hier_len;
+  int u_len;    // Ramanujan basis: a second window-sized vector (A^T p of the conjugate gradients), else 0
+  int cg_len;   // Ramanujan basis: num * pmax, the longest dictionary (rows) and the longest table set (sum of q)
   __host__ __device__ size_t off_x0() const { return (size_t)xs_len * 8; }
   __host__ __device__ size_t off_wv() const { return off_x0() + (size_t)n_even * 8; }
   __host__ __device__ int wv_len() const { return rmax + 2 * kCb; }
-  __host__ __device__ size_t off_chol() const { return off_wv() + (size_t)wv_len() * 8; }
+  __host__ __device__ size_t off_u() const { return off_wv() + (size_t)wv_len() * 8; }
+  __host__ __device__ size_t off_chol() const { return off_u() + (size_t)u_len * 8; }
   // diagonal-block scratch of the Cholesky and the hierarchical-sweep scratch are never live together
   __host__ __device__ size_t chol_bytes() const {
     const size_t a = kCholStageD;
@@ -43,16 +47,20 @@ struct QoPlan {
   __host__ __device__ size_t off_sweep() const { return off_bar() + 16; }
   __host__ __device__ size_t off_ints() const { return off_sweep() + ((sizeof(SweepShared) + 15) & ~15); }
   // ints: found[num] dict_q[num] dict_keep[num] dict_rows[num] dict_off[num+1] prev_rows[2 num] seen[seen_words] misc[16]
-  __host__ __device__ size_t bytes() const { return off_ints() + (size_t)(7 * num + 1 + seen_words + 16) * 4 + 16; }
-  // per-CTA global workspace: packed factor | saved weights (refinement) | round norms
-  __host__ __device__ size_t ws_L() const { return chol_packed_len(rmax) * 8; }
+  //       tab_off[num+1]
+  __host__ __device__ size_t bytes() const { return off_ints() + (size_t)(8 * num + 2 + seen_words + 16) * 4 + 16; }
+  // per-CTA global workspace: packed factor (natural basis) or the conjugate-gradient vectors and Ramanujan-sum
+  // tables (Ramanujan basis: c_q | fold / z | r | p | G p | w, cg_len doubles each) | saved weights | round norms
+  __host__ __device__ size_t ws_L() const { return cg_len ? (size_t)6 * cg_len * 8 : chol_packed_len(rmax) * 8; }
   __host__ __device__ size_t ws_save() const { return (size_t)wv_len() * 8; }
   __host__ __device__ size_t ws_norms() const { return (((size_t)num * 8) + 255) & ~(size_t)255; }
   __host__ __device__ size_t ws_per_cta() const { return ws_L() + ws_save() + ws_norms(); }
 };
 
-__host__ __device__ inline QoPlan make_qo_plan(int N, int pmax, int num, int rmax, bool hier) {
+__host__ __device__ inline QoPlan make_qo_plan(int N, int pmax, int num, int rmax, bool hier, bool ram_basis = false) {
   QoPlan pl;
+  pl.u_len = ram_basis ? ((N + 1) & ~1) : 0;
+  pl.cg_len = ram_basis ? ((num * pmax + 31) & ~31) : 0;
   // the residual buffer doubles as the staging area of the factorisation (it is dead during a solve)
   const int stage_len = (int)(kCholStageBs / 8);
   pl.xs_len = (N + kSweepPad + 1) & ~1;
@@ -86,6 +94,9 @@ struct QoCtx {
   int* misc;            // [0]=ndict [1]=R [3]=layout scratch [8]=entries and [9]=rows of the factor held in L [10]=row_lo
   double* L;            // global, packed factor (pp_chol.cuh)
   double* wsave;        // global, rmax + 64: weights before the refinement step
+  double* u;            // shared, N (Ramanujan basis only): A^T p of the conjugate gradients
+  int* tab_off;         // [ndict+1] (Ramanujan basis only): first table entry of dictionary entry k (prefix sums of q)
+  int cg_len;
   CholStage cs;
   long long* t;         // per-thread phase timers (development aid): [0] layout [1] W + tables [2] factor [3] solves
 };
@@ -269,6 +280,168 @@ __device__ int cta_qo_solve(const QoCtx& c, int nfound, double* e_recon, bool ex
   return PP_STATUS_OK;
 }
 
+// ------------------------------------------------------------------------------------------
+// basis_type = "ramanujan" (QOPeriods.py:970-971, 1005-1052): row i of period q is c_q((n - i) mod q), n < N
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int mobius_int(int m) {
+  int res = 1;
+  for (int d = 2; d * d <= m; ++d) {
+    if (m % d == 0) {
+      m /= d;
+      if (m % d == 0) return 0;
+      res = -res;
+    }
+  }
+  return m > 1 ? -res : res;
+}
+
+// The Ramanujan-sum dictionary applied implicitly: A u is a fold of u per period followed by a circular
+// correlation with c_q, A^T v a circular convolution per period followed by a tiling.
+struct RamBasisOp {
+  int nd, N;
+  const int* dq;
+  const int* drows;
+  const int* doff;    // first row of entry k
+  const int* toff;    // first table element of entry k
+  const double* cq;   // global: c_q tables (exact integers)
+  double* fold;       // global scratch, sum of q
+  __device__ void apply(const double* u, double* out) const {
+    for (int k = 0; k < nd; ++k) {
+      const int q = dq[k];
+      double* f = fold + toff[k];
+      for (int m = threadIdx.x; m < q; m += kThreads) {
+        double s = 0.0;
+        for (int n = m; n < N; n += q) s += u[n];
+        f[m] = s;
+      }
+    }
+    __syncthreads();
+    for (int k = 0; k < nd; ++k) {
+      const int q = dq[k], rows = drows[k];
+      const double* f = fold + toff[k];
+      const double* c = cq + toff[k];
+      for (int i = threadIdx.x; i < rows; i += kThreads) {
+        int idx = i == 0 ? 0 : q - i;   // (0 - i) mod q
+        double s0 = 0.0, s1 = 0.0;
+        int m = 0;
+        for (; m + 1 < q; m += 2) {
+          s0 = fma(c[idx], f[m], s0);
+          if (++idx == q) idx = 0;
+          s1 = fma(c[idx], f[m + 1], s1);
+          if (++idx == q) idx = 0;
+        }
+        if (m < q) s0 = fma(c[idx], f[m], s0);
+        out[doff[k] + i] = s0 + s1;
+      }
+    }
+  }
+  __device__ void apply_t(const double* v, double* out) const {
+    for (int k = 0; k < nd; ++k) {
+      const int q = dq[k], rows = drows[k];
+      double* z = fold + toff[k];
+      const double* c = cq + toff[k];
+      const double* vk = v + doff[k];
+      for (int m = threadIdx.x; m < q; m += kThreads) {
+        int idx = m;   // (m - i) mod q
+        double s0 = 0.0, s1 = 0.0;
+        int i = 0;
+        for (; i + 1 < rows; i += 2) {
+          s0 = fma(vk[i], c[idx], s0);
+          idx = idx == 0 ? q - 1 : idx - 1;
+          s1 = fma(vk[i + 1], c[idx], s1);
+          idx = idx == 0 ? q - 1 : idx - 1;
+        }
+        if (i < rows) s0 = fma(vk[i], c[idx], s0);
+        z[m] = s0 + s1;
+      }
+    }
+    __syncthreads();
+    for (int n = threadIdx.x; n < N; n += kThreads) {
+      double s = 0.0;
+      for (int k = 0; k < nd; ++k) s += fold[toff[k] + n % dq[k]];
+      out[n] = s;
+    }
+  }
+};
+
+// Same contract as cta_qo_solve for the Ramanujan-sum dictionary.  Its Gram matrix is singular by construction (q
+// shifted rows span phi(q) dimensions); the reference's np.linalg.solve runs on the rounding-perturbed matrix and
+// its reconstruction is the orthogonal projection onto the row space to 1e-14, which is what conjugate gradients
+// deliver here (pp_cg.cuh).  The weights returned are the minimum-norm solution (the reference's are whatever its LU
+// produced; only A^T w is determined).
+__device__ int cta_qo_solve_ram(const QoCtx& c, int nfound, double* e_recon) {
+  const int tid = threadIdx.x;
+  const int N = c.N;
+  long long tm = clock64();
+  qo_layout(c, nfound);
+  __syncthreads();
+  { const long long now = clock64(); c.t[0] += now - tm; tm = now; }
+  const int ndict = c.misc[0], R = c.misc[1];
+  // The one EXACT singularity of this dictionary: both rows of period 2 (+1 -1 +1 ... and its negative; cos(pi) is
+  // exactly -1 in the reference's sum of exponentials, QOPeriods.py:1037-1045).  Two exactly opposite rows make the
+  // reference's LU hit a zero pivot: np.linalg.solve raises LinAlgError and the loop keeps the previous round
+  // (:552-559).  Every other dependency of the Ramanujan rows is perturbed by ~1e-13 of rounding and goes through.
+  for (int k = 0; k < ndict; ++k)
+    if (c.dict_q[k] == 2 && c.dict_rows[k] == 2) return PP_STATUS_SINGULAR;
+  if (R > c.rmax) return PP_STATUS_TOO_LARGE;
+  for (int n = tid; n < N; n += kThreads) c.xs[n] = c.x0[n];
+  if (tid == 0) {
+    int off = 0;
+    for (int k = 0; k < ndict; ++k) {
+      c.tab_off[k] = off;
+      off += c.dict_q[k];
+    }
+    c.tab_off[ndict] = off;
+  }
+  __syncthreads();
+  if (R == 0) {
+    *e_recon = 0.0;
+    return PP_STATUS_OK;
+  }
+  double* cq = c.L;
+  double* fold = c.L + c.cg_len;
+  double* r = c.L + 2 * (size_t)c.cg_len;
+  double* p = c.L + 3 * (size_t)c.cg_len;
+  double* ap = c.L + 4 * (size_t)c.cg_len;
+  double* w = c.L + 5 * (size_t)c.cg_len;
+  for (int k = 0; k < ndict; ++k) {
+    const int q = c.dict_q[k], phq = c.phi[q];
+    for (int m = tid; m < q; m += kThreads) {
+      int a = q, bb = m;   // gcd(m, q), gcd(0, q) = q
+      while (bb) {
+        const int t = a % bb;
+        a = bb;
+        bb = t;
+      }
+      const int qg = q / a;
+      cq[c.tab_off[k] + m] = (double)(mobius_int(qg) * (phq / c.phi[qg]));   // c_q(m) = mu(q/g) phi(q) / phi(q/g)
+    }
+  }
+  for (int i = tid; i < R; i += kThreads) w[i] = 0.0;
+  __syncthreads();
+  { const long long now = clock64(); c.t[1] += now - tm; tm = now; }
+  RamBasisOp op{ndict, N, c.dict_q, c.dict_rows, c.dict_off, c.tab_off, cq, fold};
+  const int steps = cta_cg_project(op, R, N, c.xs, c.u, r, p, ap, w, c.red, 500);
+  __syncthreads();
+  if (steps < 0) return PP_STATUS_GUARD;
+  for (int i = tid; i < R; i += kThreads) c.wv[i] = w[i];
+  double e = 0.0;
+  for (int n = tid; n < N; n += kThreads) {
+    const double rr = c.x0[n] - c.xs[n];
+    e = fma(rr, rr, e);
+  }
+  e = warp_sum(e);
+  __syncthreads();
+  if ((tid & 31) == 0) c.red[tid >> 5] = e;
+  __syncthreads();
+  double t = 0.0;
+  for (int wv = 0; wv < kWarps; ++wv) t += c.red[wv];
+  __syncthreads();
+  c.t[3] += clock64() - tm;
+  *e_recon = t;
+  return PP_STATUS_OK;
+}
+
 struct QoOut {
   uint32_t* periods;   // [B, num]  periods reported (found order)
   double* norms;       // [B, num]
@@ -316,6 +489,8 @@ __device__ __forceinline__ QoCtx make_ctx(unsigned char* smem, const QoPlan& pl,
   c.xs = reinterpret_cast<double*>(smem);
   c.x0 = reinterpret_cast<double*>(smem + pl.off_x0());
   c.wv = reinterpret_cast<double*>(smem + pl.off_wv());
+  c.u = reinterpret_cast<double*>(smem + pl.off_u());
+  c.cg_len = pl.cg_len;
   double* chol = reinterpret_cast<double*>(smem + pl.off_chol());
   c.cs.Bs = c.xs;  // the residual buffer is dead while a factorisation runs
   c.cs.D = chol;
@@ -333,6 +508,7 @@ __device__ __forceinline__ QoCtx make_ctx(unsigned char* smem, const QoPlan& pl,
   c.seen = reinterpret_cast<uint32_t*>(ints + 7 * num + 1);
   c.seen_words = pl.seen_words;
   c.misc = ints + 7 * num + 1 + pl.seen_words;
+  c.tab_off = c.misc + 16;
   c.L = reinterpret_cast<double*>(ws_cta);
   c.wsave = reinterpret_cast<double*>(ws_cta + pl.ws_L());
   c.t = nullptr;
@@ -351,13 +527,14 @@ struct QoBatch {
 // ------------------------------------------------------------------------------------------
 // QOPeriods.find_periods, default branch (QOPeriods.py:313-596)
 // ------------------------------------------------------------------------------------------
+template <int BASIS>   // 0 natural (indicator rows, Cholesky), 1 Ramanujan sums (conjugate gradients)
 __global__ void __launch_bounds__(kThreads, 2)
 qo_find_kernel(QoBatch batch, int N, int num, double thresh, int pmin, int pmax, int trunc, int hier, int refine,
                const int32_t* __restrict__ phi, int rmax, QoOut out, unsigned char* __restrict__ ws, size_t ws_per_cta,
                const uint2* __restrict__ tops, int ntops, unsigned long long* __restrict__ prof,
                int* __restrict__ next_window) {
   unsigned char* smem = pp_smem;
-  const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0);
+  const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0, BASIS == 1);
   unsigned char* ws_cta = ws + (size_t)blockIdx.x * ws_per_cta;
   QoCtx c = make_ctx(smem, pl, N, num, refine, phi, ws_cta);
   SweepShared* sweep = reinterpret_cast<SweepShared*>(smem + pl.off_sweep());
@@ -466,7 +643,7 @@ qo_find_kernel(QoBatch batch, int N, int num, double thresh, int pmin, int pmax,
       }
       if (top.p > 0) ++nfound;
       __syncthreads();
-      const int rc = cta_qo_solve(c, nfound, &e_recon);
+      const int rc = BASIS == 1 ? cta_qo_solve_ram(c, nfound, &e_recon) : cta_qo_solve(c, nfound, &e_recon);
       if (rc != PP_STATUS_OK) {  // LinAlgError in the reference: keep the previous round's outputs (:552-559)
         status = rc;
         // the residual buffer may hold staged factor blocks: restore the padding the sweep relies on
@@ -626,10 +803,10 @@ using namespace pp;
 
 extern "C" {
 
-size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax, int32_t ctas) {
+size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax, int32_t ctas, int32_t basis) {
   DeviceFacts f;
   if (device_facts(f)) return 0;
-  const QoPlan pl = make_qo_plan(N, pmax, num, rmax, true);
+  const QoPlan pl = make_qo_plan(N, pmax, num, rmax, true, basis == PP_BASIS_RAMANUJAN);
   size_t grid = (size_t)grid_for(f, pl.bytes(), 0, kQoCtasPerSm);
   if (ctas > 0 && (size_t)ctas < grid) grid = (size_t)ctas;
   return 8192 + (size_t)(pmax + 2) * sizeof(uint2) + grid * pl.ws_per_cta();
@@ -655,8 +832,9 @@ static int qo_grid(const DeviceFacts& f, const QoPlan& pl, int count, size_t ava
 }
 
 int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, double thresh, int32_t pmin,
-                       int32_t pmax, int32_t trunc, int32_t fold_mode, int32_t refine, const int32_t* phi,
-                       int32_t table_pmax, int32_t rmax, const int32_t* order, int32_t n_order, uint32_t* periods,
+                       int32_t pmax, int32_t trunc, int32_t fold_mode, int32_t refine, int32_t basis,
+                       const int32_t* phi, int32_t table_pmax, int32_t rmax, const int32_t* order, int32_t n_order,
+                       uint32_t* periods,
                        double* norms, int32_t* n_periods, int32_t* dict_q, int32_t* dict_keep, int32_t* n_dict,
                        int32_t* n_weights, double* weights, int64_t ldw, double* res, int32_t* status, void* workspace,
                        size_t workspace_bytes, void* profile, void* stream) {
@@ -674,9 +852,12 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   if (int rc = device_facts(f)) return rc;
   if (int rc = check_fold_mode(fold_mode)) return rc;
   const int hier = (fold_mode != PP_FOLD_DIRECT && !trunc) ? 1 : 0;
-  const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0);
+  if (basis != PP_BASIS_NATURAL && basis != PP_BASIS_RAMANUJAN) return fail(-1, "unknown basis%s");
+  const bool ram = basis == PP_BASIS_RAMANUJAN;
+  const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0, ram);
   if (ldw < pl.rmax) return fail(-1, "ldw must be >= rmax rounded up to a multiple of 32%s");
-  if (int rc = prep_kernel(qo_find_kernel, pl.bytes(), f)) return rc;
+  if (int rc = ram ? prep_kernel(qo_find_kernel<1>, pl.bytes(), f) : prep_kernel(qo_find_kernel<0>, pl.bytes(), f))
+    return rc;
   size_t off = 0;
   int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
   uint2* tops = nullptr;
@@ -693,10 +874,16 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   if (grid < 1) return fail(-3, "workspace too small for one factor (see pp_qo_workspace_bytes)%s");
   QoOut o{periods, norms, n_periods, dict_q, dict_keep, n_dict, n_weights, weights, nullptr, ldw, res, status};
   QoBatch batch{x, ldx, count, order};
-  qo_find_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(
-      batch, N, num, thresh, pmin, pmax, trunc, hier, refine, phi, pl.rmax, o,
-      reinterpret_cast<unsigned char*>(workspace) + off, pl.ws_per_cta(), tops, ntops,
-      reinterpret_cast<unsigned long long*>(profile), next_window);
+  if (ram)
+    qo_find_kernel<1><<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(
+        batch, N, num, thresh, pmin, pmax, trunc, hier, refine, phi, pl.rmax, o,
+        reinterpret_cast<unsigned char*>(workspace) + off, pl.ws_per_cta(), tops, ntops,
+        reinterpret_cast<unsigned long long*>(profile), next_window);
+  else
+    qo_find_kernel<0><<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(
+        batch, N, num, thresh, pmin, pmax, trunc, hier, refine, phi, pl.rmax, o,
+        reinterpret_cast<unsigned char*>(workspace) + off, pl.ws_per_cta(), tops, ntops,
+        reinterpret_cast<unsigned long long*>(profile), next_window);
   return check_cuda(cudaGetLastError(), "qo_find_kernel launch");
 }
 

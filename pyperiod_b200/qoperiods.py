@@ -5,9 +5,10 @@ one persistent kernel per batch (csrc/pp_qo.cu): gamma sweep -> dictionary layou
 -> reconstruction / residual -> stop test.  1-D input returns the reference's `(dict, res)`; a
 (B, N) batch returns a QOBatchResult whose `.window(b)` rebuilds that pair for one window.
 
-Supported: the reference's DEFAULT branch (`_orthogonalize=False`, `update_weights=True`,
-`basis_type="natural"`, default `test_function`).  The other branches are out of scope
- and raise NotImplementedError instead of silently doing something else.
+Supported: `_orthogonalize=False`, `update_weights=True`, `basis_type` "natural" (default) and "ramanujan"
+(QOPeriods.py:970-971, 1005-1052), the default `test_function` on the device and a custom one for 1-D input.
+`_orthogonalize=True` is dead in the reference (best_base is None) and `update_weights=False` raises OverflowError
+there under numpy 2: both raise NotImplementedError here instead of silently doing something else.
 Deviation from the reference: the stray `print(nonzero_periods)` at QOPeriods.py:488 is not reproduced.
 """
 from __future__ import annotations
@@ -29,12 +30,12 @@ RMAX_FIRST = 1024      # dictionary rows the first launch holds factors for; lar
 WORKSPACE_FRACTION = 0.5   # share of the free device memory the Cholesky factors of one launch may take
 
 
-def qo_workspace(lib, dev, n, pmax, num, rmax):
+def qo_workspace(lib, dev, n, pmax, num, rmax, basis=_lib.BASIS_NATURAL):
     """Workspace for the QO kernels: factors for the full persistent grid, or as many CTAs as the memory budget holds
     (the launch shrinks its grid to the workspace it is given; one factor of 4096 rows is 68 MB)."""
     with torch.cuda.device(dev):
-        full = int(lib.pp_qo_workspace_bytes(n, pmax, num, rmax, 0))
-        one = int(lib.pp_qo_workspace_bytes(n, pmax, num, rmax, 1))
+        full = int(lib.pp_qo_workspace_bytes(n, pmax, num, rmax, 0, basis))
+        one = int(lib.pp_qo_workspace_bytes(n, pmax, num, rmax, 1, basis))
         free, _ = torch.cuda.mem_get_info(dev)
     budget = max(one, int(free * WORKSPACE_FRACTION))
     return Workspace.get(dev, min(full, budget))   # a cached buffer that is already large enough is reused
@@ -47,9 +48,27 @@ def indicator_rows(q: int, n: int, keep) -> np.ndarray:
     return rows[:keep] if keep else rows
 
 
-def build_subspaces(dict_q, dict_keep, n: int) -> np.ndarray:
-    """The stacked dictionary matrix the reference returns under 'subspaces' (an output structure, 0/1 valued)."""
-    blocks = [np.zeros((0, n))] + [indicator_rows(q, n, k) for q, k in zip(dict_q, dict_keep)]
+def ramanujan_sum(q: int) -> np.ndarray:
+    """c_q(m), m < q, as exact integers: mu(q/g) phi(q) / phi(q/g), g = gcd(m, q) (the reference sums complex
+    exponentials, QOPeriods.py:1037-1045, and is 1e-13 away from these)."""
+    tb = get_tables(max(int(q), 2))
+    g = np.gcd(np.arange(int(q)), int(q))
+    g[0] = int(q)
+    return (tb.mu[int(q) // g] * (int(tb.phi[int(q)]) // tb.phi[int(q) // g])).astype(np.float64)
+
+
+def ramanujan_rows(q: int, n: int, keep) -> np.ndarray:
+    """Ramanujan-basis rows c_q((m - i) mod q), i < keep; keep == 0/None keeps all q rows (QOPeriods.py:970-974)."""
+    c = ramanujan_sum(q)
+    m = np.arange(int(n))
+    rows = c[(m[None, :] - np.arange(int(q))[:, None]) % int(q)]
+    return rows[:keep] if keep else rows
+
+
+def build_subspaces(dict_q, dict_keep, n: int, basis: str = "natural") -> np.ndarray:
+    """The stacked dictionary matrix the reference returns under 'subspaces' (an output structure)."""
+    rows = ramanujan_rows if basis == "ramanujan" else indicator_rows
+    blocks = [np.zeros((0, n))] + [rows(q, n, k) for q, k in zip(dict_q, dict_keep)]
     return np.vstack(blocks)
 
 
@@ -69,6 +88,7 @@ class QOBatchResult:
     n: int = 0
     weights_off: object = None   # (B,) int64 start of window b in the flat `weights` (ragged layout)
     big: object = None           # {window: 1-D weights} of windows whose dictionary outgrew the first launch
+    basis: str = "natural"
 
     def weights_of(self, b: int) -> np.ndarray:
         g = (lambda t: t.cpu().numpy() if isinstance(t, torch.Tensor) else t)
@@ -96,9 +116,53 @@ class QOBatchResult:
         per = np.array(g(self.periods)[b, :npd]).view(np.uint32) if g(self.periods).dtype != np.uint32 \
             else np.array(g(self.periods)[b, :npd])
         out = {"periods": per, "norms": np.array(g(self.norms)[b, :npd]),
-               "subspaces": build_subspaces(dq, dk, self.n), "weights": self.weights_of(b),
+               "subspaces": build_subspaces(dq, dk, self.n, self.basis), "weights": self.weights_of(b),
                "basis_dictionary": {str(int(q)): int(k) for q, k in zip(dq, dk)}}
         return out, res
+
+
+@dataclass
+class PeriodsBatch:
+    """Batched QOPeriods.get_periods: `flat[off[b] : off[b] + sum(q_b)]` holds window b's waveforms back to back."""
+    flat: object      # (sum over windows of sum(q),) float64 -- numpy for host input, torch otherwise
+    off: np.ndarray   # (B + 1,) int64
+    dict_q: np.ndarray
+    n_dict: np.ndarray
+    status: object
+
+    def window(self, b: int):
+        seg = self.flat[int(self.off[b]): int(self.off[b + 1])]
+        seg = seg.cpu().numpy() if isinstance(seg, torch.Tensor) else seg
+        out, pos = [], 0
+        for q in self.dict_q[b, : int(self.n_dict[b])].tolist():
+            out.append(np.array(seg[pos: pos + q]))
+            pos += q
+        return tuple(out)
+
+
+def _extract(dev, dq, dk, nd, dq_h, nd_h, weights_flat, ldw, woff):
+    """Launch pp_qo_get_periods for a batch.  dq/dk/nd: device int32; dq_h/nd_h: the same on the host (sizes)."""
+    lib = _lib.load()
+    bsz, kmax = dq_h.shape
+    valid = np.arange(kmax)[None, :] < nd_h[:, None]
+    qv = np.where(valid, dq_h, 0).astype(np.int64)
+    t = qv.sum(axis=1)
+    rows = np.zeros(bsz, np.int64)
+    for i in range(kmax):
+        for j in range(i + 1, kmax):
+            both = valid[:, i] & valid[:, j]
+            if both.any():
+                rows += np.where(both, np.gcd(np.where(both, qv[:, i], 1), np.where(both, qv[:, j], 1)), 0)
+    off = np.zeros(bsz + 1, np.int64)
+    np.cumsum(t, out=off[1:])
+    out = torch.zeros((max(int(off[-1]), 1),), dtype=torch.float64, device=dev)
+    iters = torch.zeros((bsz,), dtype=torch.int32, device=dev)
+    status = torch.zeros((bsz,), dtype=torch.int32, device=dev)
+    off_d = torch.from_numpy(off[:-1].copy()).to(dev)
+    call(lib.pp_qo_get_periods, "pp_qo_get_periods", dev, bsz, kmax, int(max(t.max(), 1)), int(rows.max()), ptr(dq),
+         ptr(dk), ptr(nd), ptr(weights_flat), int(ldw), ptr(woff), ptr(out), ptr(off_d), ptr(iters), ptr(status),
+         stream_ptr(dev))
+    return out, off, status
 
 
 class QOPeriods(Periods):
@@ -122,13 +186,18 @@ class QOPeriods(Periods):
         Not in the reference: rmax (dictionary rows the first launch holds factors for; windows that outgrow it are
         re-run with room for N rows, so no window is dropped), refine (steps of iterative refinement of the normal
         equations, default 1), return_res."""
-        if "test_function" in kwargs:
-            raise NotImplementedError("custom test_function is evaluated on the device only in its default form")
+        test_function = kwargs.pop("test_function", None)
         if kwargs:
             raise TypeError(f"unexpected arguments {sorted(kwargs)}")
-        if self._orthogonalize or not update_weights or self._basis_type != "natural":
-            raise NotImplementedError("only the reference's default branch (orthogonalize=False, "
-                                      "update_weights=True, basis_type='natural') is implemented")
+        if self._orthogonalize or not update_weights:
+            raise NotImplementedError("orthogonalize=True is dead code in the reference and update_weights=False "
+                                      "raises OverflowError there under numpy 2; neither is implemented")
+        if self._basis_type not in ("natural", "ramanujan"):
+            raise ValueError("basis_type must be 'natural' or 'ramanujan'")
+        if test_function is not None:
+            return self._find_periods_custom_test(data, num, thresh, min_length, max_length, test_function,
+                                                  rmax=rmax, refine=refine)
+        basis = _lib.BASIS_RAMANUJAN if self._basis_type == "ramanujan" else _lib.BASIS_NATURAL
         lib = _lib.load()
         w = stage_windows(data, self._device, pipeline=True)
         n = w.n
@@ -142,7 +211,10 @@ class QOPeriods(Periods):
                 raise TypeError("thresh is None: the reference's default test multiplies it (QOPeriods.py:391)")
             thresh = 0.0
         retry_big = rmax is None
-        rmax = min(n, RMAX_FIRST) if rmax is None else int(rmax)
+        # natural basis: more rows than samples is singular by rank, so N rows is the most a factor ever holds;
+        # Ramanujan basis: rows <= sum of the periods (no factor is stored, rmax is the capacity of `weights`)
+        rows_cap = n if basis == _lib.BASIS_NATURAL else num * int(max_length)
+        rmax = min(rows_cap, RMAX_FIRST) if rmax is None else int(rmax)
         tb = get_tables(max_length)
         dev = w.device
         phi = tb.phi_device(dev)
@@ -159,14 +231,14 @@ class QOPeriods(Periods):
                      dict_keep=torch.zeros((count, num), **i32), n_dict=torch.zeros((count,), **i32),
                      n_weights=torch.zeros((count,), **i32), weights=torch.zeros((count, ldw), **f64),
                      res=torch.empty((count, n), **f64) if return_res else None, status=torch.zeros((count,), **i32))
-            ws = qo_workspace(lib, dev, n, int(max_length), num, rmax_l)
+            ws = qo_workspace(lib, dev, n, int(max_length), num, rmax_l, basis)
             for b0, b1, ready in plan:
                 if ready is not None:
                     cur.wait_event(ready)
                 sl = lambda t: ptr(None if t is None else t[b0:b1])
                 call(lib.pp_qo_find_periods, "pp_qo_find_periods", dev, C.c_void_p(x_ptr + b0 * ldx * 8), ldx, b1 - b0,
                      n, num, float(thresh), int(min_length), int(max_length), int(self._trunc_to_integer_multiple),
-                     self._fold(), int(refine), ptr(phi), tb.pmax, int(rmax_l), ptr(None), 0, sl(o["periods"]),
+                     self._fold(), int(refine), basis, ptr(phi), tb.pmax, int(rmax_l), ptr(None), 0, sl(o["periods"]),
                      sl(o["norms"]), sl(o["n_periods"]), sl(o["dict_q"]), sl(o["dict_keep"]), sl(o["n_dict"]),
                      sl(o["n_weights"]), sl(o["weights"]), ldw, sl(o["res"]), sl(o["status"]), ptr(ws), ws.numel(),
                      _lib.profile_ptr(), stream_ptr(dev))
@@ -174,13 +246,13 @@ class QOPeriods(Periods):
 
         o = launch(w.ptr, w.ldx, w.b, rmax, w.launch_plan())
         big = None
-        if retry_big and rmax < n:
+        if retry_big and rmax < rows_cap:
             idx = torch.nonzero(o["status"] == _lib.STATUS_TOO_LARGE).flatten()
             if idx.numel():
                 # dictionaries of more than rmax rows: re-run just those windows with room for N rows (more rows than
                 # samples is singular by rank); their padded outputs replace the first launch's
                 xb = torch.as_strided(w.tensor, (w.b, n), (w.ldx, 1))[idx].contiguous()
-                o2 = launch(xb.data_ptr(), n, int(idx.numel()), n, [(0, int(idx.numel()), None)])
+                o2 = launch(xb.data_ptr(), n, int(idx.numel()), rows_cap, [(0, int(idx.numel()), None)])
                 for key in ("periods", "norms", "n_periods", "dict_q", "dict_keep", "n_dict", "n_weights", "status"):
                     o[key][idx] = o2[key]
                 if return_res:
@@ -190,7 +262,7 @@ class QOPeriods(Periods):
         out = QOBatchResult(_export(w, o["periods"], True), _export(w, o["norms"]), _export(w, o["n_periods"]),
                             _export(w, o["dict_q"]), _export(w, o["dict_keep"]), _export(w, o["n_dict"]),
                             _export(w, o["weights"]), _export(w, o["n_weights"]), _export(w, o["res"]),
-                            _export(w, o["status"]), n=n, big=big)
+                            _export(w, o["status"]), n=n, big=big, basis=self._basis_type)
         if w.was_1d:
             if int(out.status[0]) == _lib.STATUS_TOO_LARGE:
                 raise ValueError("dictionary has more rows than rmax; pass a larger rmax")
@@ -199,38 +271,156 @@ class QOPeriods(Periods):
             return pair
         return out
 
-    # ------------------------------------------------------------------ extraction (QOPeriods.py:719-741)
-    def get_periods(self, weights, dictionary, decomp_type="row reduction"):
-        """Redistribute shared-GCD energy between the found periods; returns a tuple of per-period waveforms.
+    # ------------------------------------------------------------------ custom stop test (QOPeriods.py:388-391, 418)
+    def _solve_periods(self, w, found, refine):
+        """get_subspaces + solve_quadratic for the periods `found` (in found order) of the 1-D window `w`, on the device
+        (pp_qo_solve).  Returns (layout, weights, residual) as numpy; raises LinAlgError where the reference does."""
+        lib = _lib.load()
+        dev, n = w.device, w.n
+        k = len(found)
+        i32 = dict(dtype=torch.int32, device=dev)
+        per = torch.tensor([list(map(int, found))], **i32)
+        nper = torch.tensor([k], **i32)
+        pmax = int(max(max(map(int, found)), 2))
+        tb = get_tables(pmax)
+        phi = tb.phi_device(dev)
+        rows = torch.zeros((1,), **i32)
+        call(lib.pp_qo_dictionary_rows, "pp_qo_dictionary_rows", dev, 1, k, ptr(per), ptr(nper), pmax, ptr(phi), tb.pmax,
+             ptr(rows), stream_ptr(dev))
+        r = int(rows[0])
+        if r > n:
+            raise np.linalg.LinAlgError("Singular matrix")   # more rows than samples
+        rmax = max(r, 32)
+        ldw = (rmax + 31) // 32 * 32
+        dq, dk = torch.zeros((1, k), **i32), torch.zeros((1, k), **i32)
+        nd, nw, st = (torch.zeros((1,), **i32) for _ in range(3))
+        wts = torch.zeros((1, ldw), dtype=torch.float64, device=dev)
+        res = torch.empty((1, n), dtype=torch.float64, device=dev)
+        ws = qo_workspace(lib, dev, n, pmax, k, rmax)
+        call(lib.pp_qo_solve, "pp_qo_solve", dev, ptr(w.tensor), w.ldx, 1, n, k, ptr(per), ptr(nper), pmax, int(refine),
+             ptr(phi), tb.pmax, rmax, ptr(None), 0, ptr(dq), ptr(dk), ptr(nd), ptr(nw), ptr(wts), ldw, ptr(None), ptr(res),
+             ptr(st), ptr(ws), ws.numel(), stream_ptr(dev))
+        if int(st[0]) != _lib.STATUS_OK:
+            raise np.linalg.LinAlgError("Singular matrix")
+        m = int(nd[0])
+        layout = {str(int(q)): int(c) for q, c in zip(dq[0, :m].tolist(), dk[0, :m].tolist())}
+        return layout, wts[0, : int(nw[0])].cpu().numpy(), res[0].cpu().numpy()
 
-        A small dense problem (sum of the periods unknowns); it runs on the device through torch.linalg.
-        """
+    def _find_periods_custom_test(self, data, num, thresh, min_length, max_length, test_function, rmax=None, refine=1):
+        """The loop of QOPeriods.py:417-594 with a caller-supplied `test_function(self, data, reconstruction)`: a host
+        callable decides after every round, so the rounds are separate launches (gamma sweep of the residual, then
+        dictionary + normal equations of all periods found so far against the original data).  1-D input, natural
+        basis."""
+        if self._basis_type != "natural":
+            raise NotImplementedError("a custom test_function is supported with basis_type='natural'")
+        w = stage_windows(data, self._device)
+        if not w.was_1d:
+            raise NotImplementedError("a custom test_function is a host callable: pass one 1-D signal")
+        n = w.n
+        x = to_host(w.tensor)[0]
+        if max_length is None:
+            max_length = int(np.floor(n / 3))
+        num = n if num is None else int(num)
+        if np.sum(np.abs(x)) <= 1e-16:   # QOPeriods.py:394-406
+            out = {"periods": np.array([1]), "norms": np.array([0]), "subspaces": np.ones((1, n)),
+                   "weights": np.array([0]), "basis_dictionary": {"1": n}}
+            self._output = out
+            return out, np.zeros(n)
+        out = {"periods": [], "norms": [], "subspaces": [], "weights": [], "basis_dictionary": {}}
+        periods = np.zeros(num, dtype=np.uint32)
+        norms = np.zeros(num)
+        res, recon, found = x.copy(), None, periods[:0]
+        sweeper = Periods(self._trunc_to_integer_multiple, False, device=w.device, fold_mode=self._fold_mode)
+        for i in range(num):
+            if i == 0 or test_function(self, x, recon):
+                _, bp, bv = sweeper.sweep(torch.from_numpy(res).to(w.device), metric="gamma", min_length=int(min_length),
+                                          max_length=int(max_length))
+                periods[i], norms[i] = int(bp[0]), float(bv[0])
+                found = periods[periods > 0]
+                try:
+                    layout, wts, res = self._solve_periods(w, found, refine)
+                except np.linalg.LinAlgError:   # QOPeriods.py:552-559: keep the previous round's outputs
+                    break
+                recon = x - res
+                out = {"periods": found, "norms": norms[: len(found)],
+                       "subspaces": build_subspaces([int(q) for q in layout], list(layout.values()), n),
+                       "weights": wts, "basis_dictionary": layout}
+                self._output_bases = out
+            else:   # QOPeriods.py:560-594: weights of all periods, the last period not reported
+                layout, wts, _ = self._solve_periods(w, found, refine)
+                out = {"periods": found[:-1], "norms": norms[: len(found) - 1],
+                       "subspaces": build_subspaces([int(q) for q in layout], list(layout.values()), n),
+                       "weights": wts, "basis_dictionary": layout}
+                break
+        self._output = out
+        return out, res
+
+    # ------------------------------------------------------------------ extraction (QOPeriods.py:719-741)
+    def get_periods(self, weights, dictionary=None, decomp_type="row reduction"):
+        """Redistribute shared-GCD energy between the found periods (QOPeriods.py:719-741).
+
+        Reference form: `get_periods(weights, dictionary, decomp_type)` -> tuple of per-period waveforms.
+        Batch form: `get_periods(result)` with the QOBatchResult of find_periods / find_periods_with_weights ->
+        PeriodsBatch (`.window(b)` is the reference's tuple).  Every window is one CTA of pp_qo_get_periods: the zero
+        padded weights minus their projection onto the row space of the pairwise-GCD matrix, by conjugate gradients
+        with implicit rows -- what every `decomp_type` of the reference computes (they differ in how the dependent
+        rows are removed; the reference's "lu" / "qr" results are rounding noise when rows are dependent).
+        Like the reference, "row reduction" raises LinAlgError when the matrix has rank one (a single period, or two
+        coprime periods): reduce_rows returns a 1-D array there and np.linalg.solve rejects it."""
+        if isinstance(weights, QOBatchResult):
+            return self._get_periods_batch(weights)
+        layout = [(int(q), int(c)) for q, c in dictionary.items()]
         dev = torch.device("cuda", torch.cuda.current_device()) if self._device is None else torch.device(self._device)
-        periods = [int(p) for p in dictionary.keys()]
-        cat = torch.as_tensor(self.concatenate_periods(weights, dictionary), dtype=torch.float64, device=dev)
-        a = torch.as_tensor(self.stack_pairwise_gcd_subspaces(periods), dtype=torch.float64, device=dev)
-        if decomp_type == "row reduction":
-            a = _reduce_rows(a)
-            kind = "solve"
-        elif decomp_type == "lu":
-            _, _, a = torch.linalg.lu(a)
-            kind = "solve"
-        elif decomp_type == "qr":
-            _, a = torch.linalg.qr(a, mode="complete")
-            kind = "solve"
+        k = max(len(layout), 1)
+        dq = np.zeros((1, k), np.int32)
+        dk = np.zeros((1, k), np.int32)
+        for i, (q, c) in enumerate(layout):
+            dq[0, i], dk[0, i] = q, c
+        qs = [q for q, _ in layout]
+        if decomp_type == "row reduction" and (len(qs) == 1 or (len(qs) == 2 and int(np.gcd(qs[0], qs[1])) == 1)):
+            raise np.linalg.LinAlgError("0-dimensional array given. Array must be at least two-dimensional")
+        wt = torch.as_tensor(np.asarray(weights, dtype=np.float64), device=dev).reshape(1, -1)
+        out, off, st = _extract(dev, torch.from_numpy(dq).to(dev), torch.from_numpy(dk).to(dev),
+                                torch.tensor([len(layout)], dtype=torch.int32, device=dev), dq, np.array([len(layout)]),
+                                wt, wt.shape[1], None)
+        if int(st[0]) != _lib.STATUS_OK:
+            raise np.linalg.LinAlgError("pairwise-GCD projection did not converge")
+        flat = out.cpu().numpy()
+        return tuple(np.array(flat[s: s + q]) for s, q in zip(np.cumsum([0] + qs[:-1]), qs))
+
+    def _get_periods_batch(self, r: "QOBatchResult"):
+        g = (lambda t: t.cpu().numpy() if isinstance(t, torch.Tensor) else np.asarray(t))
+        dev = r.dict_q.device if isinstance(r.dict_q, torch.Tensor) else \
+            (torch.device("cuda", torch.cuda.current_device()) if self._device is None else torch.device(self._device))
+        dq_h, nd_h = g(r.dict_q).astype(np.int32), g(r.n_dict).astype(np.int32)
+        to_dev = lambda t, dt: (t if isinstance(t, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(t))).to(dev).to(dt)
+        wts = to_dev(r.weights, torch.float64)
+        if r.weights_off is not None:
+            woff = to_dev(r.weights_off, torch.int64)
+            flat, ldw = wts.reshape(-1), 0
         else:
-            kind = "lstsq"
-        _, rec = self.solve_quadratic(cat, a, kind)
-        actual = (cat - rec).cpu().numpy()
-        out, start = [], 0
-        for p in periods:
-            out.append(actual[start:start + p])
-            start += p
-        return tuple(out)
+            flat, ldw = wts.reshape(-1), wts.shape[1]
+            woff = None
+            if r.big:   # windows whose weights live outside the padded array: append them, address everything by offset
+                woff_h = np.arange(dq_h.shape[0], dtype=np.int64) * ldw
+                parts, pos = [flat], flat.numel()
+                for b, v in r.big.items():
+                    v = to_dev(v, torch.float64).reshape(-1)
+                    woff_h[b] = pos
+                    pos += v.numel()
+                    parts.append(v)
+                flat, woff, ldw = torch.cat(parts), torch.from_numpy(woff_h).to(dev), 0
+        out, off, st = _extract(dev, to_dev(r.dict_q, torch.int32), to_dev(r.dict_keep, torch.int32),
+                                to_dev(r.n_dict, torch.int32), dq_h, nd_h, flat, ldw, woff)
+        host = not isinstance(r.dict_q, torch.Tensor)
+        return PeriodsBatch(to_host(out) if host else out, off, dq_h, nd_h, to_host(st) if host else st)
 
     @staticmethod
     def solve_quadratic(x, A, type="solve", window=None, k=0):
-        """Normal equations (A A^T) w = A x and reconstruction A^T w (QOPeriods.py:743-805), on torch tensors."""
+        """Normal equations (A A^T) w = A x and reconstruction A^T w (QOPeriods.py:743-805) for a caller-supplied dense
+        matrix A, on torch tensors (torch.linalg on the device).  A public helper of the reference's surface only: no
+        algorithm of this package calls it -- find_periods, find_periods_with_weights and get_periods solve their
+        structured systems in the library's own kernels."""
         x = torch.as_tensor(x, dtype=torch.float64, device=A.device if isinstance(A, torch.Tensor) else None)
         A = torch.as_tensor(A, dtype=torch.float64, device=x.device)
         gram, rhs = A @ A.T, A @ x
@@ -277,9 +467,9 @@ class QOPeriods(Periods):
 
     @staticmethod
     def Pp(p, N=1, keep=None, type="natural"):
-        """QOPeriods.py:940-974 (natural basis)."""
-        if type != "natural":
-            raise NotImplementedError("only the natural basis is implemented")
+        """QOPeriods.py:940-974: natural (indicator) or Ramanujan-sum rows."""
+        if type == "ramanujan":
+            return ramanujan_rows(p, N, keep)
         return indicator_rows(p, N, keep)
 
     def get_subspaces(self, Q, N):
@@ -292,25 +482,13 @@ class QOPeriods(Periods):
             dim = int(sum(int(phi[r]) for r in seen))
             layout[str(q)] = dim - dim_before
             dim_before = dim
-        return build_subspaces([int(q) for q in layout], list(layout.values()), N), layout
+        return build_subspaces([int(q) for q in layout], list(layout.values()), N, self._basis_type), layout
 
     # ------------------------------------------------------------------ properties (QOPeriods.py:1237-1310)
     basis_type = property(lambda s: s._basis_type, lambda s, v: setattr(s, "_basis_type", v))
     verbose = property(lambda s: s._verbose, lambda s, v: setattr(s, "_verbose", v))
     k = property(lambda s: s._k, lambda s, v: setattr(s, "_k", v))
     output_bases = property(lambda s: s._output_bases, lambda s, v: setattr(s, "_output_bases", v))
-
-
-def _reduce_rows(a: torch.Tensor) -> torch.Tensor:
-    """Greedy rank-increasing row selection (QOPeriods.py:86-94)."""
-    kept = a[0:1]
-    rank = int(torch.linalg.matrix_rank(kept))
-    for i in range(1, a.shape[0]):
-        trial = torch.cat((kept, a[i:i + 1]))
-        r = int(torch.linalg.matrix_rank(trial))
-        if r > rank:
-            kept, rank = trial, r
-    return kept
 
 
 # ---------------------------------------------------------------------------------------------------------------

@@ -264,7 +264,41 @@ def gen_ties():
     save("ties", **out)
 
 
+# ------------------------------------------------------------------ 10. QOPeriods(basis_type="ramanujan") + get_periods
+QO_RAMBASIS_CASES = [(600, 5, 2, None), (600, 5, 3, None), (1024, 50_001, 3, None), (2000, 7, 4, 300)]
+GETP_CASES = [(2000, 7, 4, 300), (1024, 50_001, 3, 200), (4096, 50_003, 4, None)]
+
+
+def gen_qo_rambasis():
+    """QOPeriods(basis_type="ramanujan").find_periods (QOPeriods.py:970-971, 1005-1052): periods, dictionary, norms
+    and residual (the weights solve a singular system and are not reproducible); and QOPeriods.get_periods in its
+    "row reduction" and lstsq branches on natural-basis results with 3-4 periods."""
+    out = {}
+    for i, (n, seed, num, ml) in enumerate(QO_RAMBASIS_CASES):
+        x = synth.synth(n, seed)
+        q = QOPeriods(basis_type="ramanujan")
+        d, res = quiet(q.find_periods, x, num=num, thresh=0.05, max_length=ml)
+        out[f"c{i}_periods"], out[f"c{i}_norms"], out[f"c{i}_res"] = np.array(d["periods"]), np.array(d["norms"]), res
+        out[f"c{i}_dict_keys"] = np.array([int(k) for k in d["basis_dictionary"]])
+        out[f"c{i}_dict_vals"] = np.array([int(v) for v in d["basis_dictionary"].values()])
+        out[f"c{i}_weights"] = d["weights"]
+    for i, (n, seed, num, ml) in enumerate(GETP_CASES):
+        x = synth.synth(n, seed)
+        q = QOPeriods()
+        d, res = quiet(q.find_periods, x, num=num, thresh=0.01, max_length=ml)
+        out[f"g{i}_dict_keys"] = np.array([int(k) for k in d["basis_dictionary"]])
+        out[f"g{i}_dict_vals"] = np.array([int(v) for v in d["basis_dictionary"].values()])
+        out[f"g{i}_weights"] = d["weights"]
+        for kind in ("row reduction", "lstsq"):
+            try:
+                gp = quiet(q.get_periods, d["weights"], d["basis_dictionary"], kind)
+                out[f"g{i}_{kind.replace(' ', '')}"] = np.concatenate(gp)
+            except np.linalg.LinAlgError:
+                out[f"g{i}_{kind.replace(' ', '')}_linalgerror"] = np.array(1)
+    save("qo_rambasis", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["project", "readme", "mbest_stream", "s2l", "bcorr", "qo_ram", "qo_gcd"]   # + "ram_cfg5" (slow)
+    which = sys.argv[1:] or ["project", "readme", "mbest_stream", "s2l", "bcorr", "qo_ram", "qo_gcd", "qo_rambasis"]   # + "ram_cfg5" (slow)
     for w in which:
         globals()["gen_" + w]()

@@ -93,6 +93,8 @@ def test_unsupported_branches_raise(QO):
         QO(orthogonalize=True).find_periods(x, num=1, thresh=0.1)
     with pytest.raises(NotImplementedError):
         QO().find_periods(x, num=1, thresh=0.1, update_weights=False)
+    with pytest.raises(ValueError):
+        QO(basis_type="fourier").find_periods(x, num=1, thresh=0.1)
     with pytest.raises(TypeError):
         QO().find_periods(x, num=2)
 
@@ -176,3 +178,104 @@ def test_qo_rows_beyond_samples_are_singular(QO):
     assert st in (0, 3)
     if st == 3:
         assert int(out.n_weights[0]) <= 240
+
+
+# ------------------------------------------------------------------ basis_type="ramanujan", get_periods on the device
+RAMBASIS_CASES = [(600, 5, 2, None), (600, 5, 3, None), (1024, 50_001, 3, None), (2000, 7, 4, 300)]
+GETP_CASES = [(2000, 7, 4, 300), (1024, 50_001, 3, 200), (4096, 50_003, 4, None)]
+
+
+def test_qo_ramanujan_basis_vs_golden(QO):
+    """QOPeriods(basis_type="ramanujan").find_periods (QOPeriods.py:970-971, 1005-1052) against the reference's own
+    outputs: periods, dictionary, norms and residual.  The reference's Gram matrix is singular by construction there
+    (q shifted rows span phi(q) dimensions), its weights are one arbitrary solution; the device returns the
+    minimum-norm one, which must reconstruct the same signal."""
+    g = load_golden("qo_rambasis")
+    for i, (n, seed, num, ml) in enumerate(RAMBASIS_CASES):
+        x = synth.synth(n, seed)
+        d, res = QO(basis_type="ramanujan").find_periods(x, num=num, thresh=0.05, max_length=ml)
+        assert np.asarray(d["periods"]).tolist() == g[f"c{i}_periods"].tolist()
+        assert [int(k) for k in d["basis_dictionary"]] == g[f"c{i}_dict_keys"].tolist()
+        assert [int(v) for v in d["basis_dictionary"].values()] == g[f"c{i}_dict_vals"].tolist()
+        np.testing.assert_allclose(d["norms"], g[f"c{i}_norms"], rtol=1e-10)
+        np.testing.assert_allclose(res, g[f"c{i}_res"], rtol=0, atol=1e-10)
+        a = d["subspaces"]
+        assert a.shape == (len(d["weights"]), n)
+        np.testing.assert_allclose(x - a.T @ d["weights"], res, rtol=0, atol=1e-10)
+        # minimum-norm weights: no larger than the reference's
+        assert np.linalg.norm(d["weights"]) <= np.linalg.norm(g[f"c{i}_weights"]) * (1 + 1e-9)
+    # batch form, two windows of one shape
+    xb = np.stack([synth.synth(600, 5), synth.synth(600, 6)])
+    out = QO(basis_type="ramanujan").find_periods(xb, num=2, thresh=0.05)
+    d0, res0 = out.window(0)
+    assert np.asarray(d0["periods"]).tolist() == g["c0_periods"].tolist()
+    np.testing.assert_allclose(res0, g["c0_res"], rtol=0, atol=1e-10)
+    d1, res1 = out.window(1)
+    import contextlib, io
+    with contextlib.redirect_stdout(io.StringIO()):
+        e1, r1 = oq.find_periods(xb[1], num=2, thresh=0.05, basis="ramanujan")
+    assert np.asarray(d1["periods"]).tolist() == np.asarray(e1["periods"]).tolist()
+    np.testing.assert_allclose(res1, r1, rtol=0, atol=1e-10)
+
+
+def test_get_periods_device_vs_golden(QO):
+    """QOPeriods.get_periods on the device (pp_qo_get_periods) against the reference's "row reduction" and lstsq
+    branches on 3-4 period dictionaries, reference form and batch form."""
+    g = load_golden("qo_rambasis")
+    for i in range(len(GETP_CASES)):
+        layout = {str(int(k)): int(v) for k, v in zip(g[f"g{i}_dict_keys"], g[f"g{i}_dict_vals"])}
+        for kind, key in (("row reduction", "rowreduction"), ("lstsq", "lstsq"), ("qr", "lstsq")):
+            gp = QO().get_periods(g[f"g{i}_weights"], layout, kind)
+            assert [len(v) for v in gp] == [int(k) for k in layout]
+            np.testing.assert_allclose(np.concatenate(gp), g[f"g{i}_{key}"], rtol=0, atol=1e-10)
+    # batch form: the result of a batched find_periods goes straight back in
+    xb = np.stack([synth.synth(1024, 50_001 + j) for j in range(5)])
+    r = QO().find_periods(xb, num=3, thresh=0.01, max_length=200)
+    pb = QO().get_periods(r)
+    assert np.asarray(pb.status).tolist() == [0] * 5
+    for b in range(5):
+        d, _ = r.window(b)
+        want = oq.get_periods(d["weights"], d["basis_dictionary"], "lstsq")
+        got = pb.window(b)
+        assert len(got) == len(want)
+        for u, v in zip(got, want):
+            np.testing.assert_allclose(u, v, rtol=0, atol=1e-10)
+
+
+def test_get_periods_rank_one_raises_like_the_reference(QO):
+    """reduce_rows returns a 1-D array when the pairwise-GCD matrix has rank one and np.linalg.solve rejects it
+    (QOPeriods.py:86-94, 794); lstsq goes through."""
+    w = np.arange(1.0, 13.0)
+    with pytest.raises(np.linalg.LinAlgError):
+        QO().get_periods(w[:5], {"5": 5})
+    with pytest.raises(np.linalg.LinAlgError):
+        QO().get_periods(w, {"5": 5, "7": 7})
+    gp = QO().get_periods(w, {"5": 5, "7": 7}, "lstsq")
+    want = oq.get_periods(w, {"5": 5, "7": 7}, "lstsq")
+    for u, v in zip(gp, want):
+        np.testing.assert_allclose(u, v, rtol=0, atol=1e-12)
+    gp = QO().get_periods(w[:5], {"5": 5}, "lstsq")
+    np.testing.assert_allclose(gp[0], w[:5] - w[:5].mean(), rtol=0, atol=1e-13)
+
+
+def test_custom_test_function(QO):
+    """test_function(self, data, reconstruction) (QOPeriods.py:388-391, 418): the default written out by the caller
+    gives the default path's result; another rule is checked against the oracle running the same callable."""
+    import contextlib, io
+    x = synth.synth(1024, 50_002)
+    rms = lambda v: np.sqrt(np.sum(np.power(v, 2)) / len(v))
+    d0, res0 = QO().find_periods(x, num=4, thresh=0.05)
+    d1, res1 = QO().find_periods(x, num=4, thresh=0.05, test_function=lambda s, a, y: rms(y) > rms(a) * 0.05)
+    assert np.asarray(d0["periods"]).tolist() == np.asarray(d1["periods"]).tolist()
+    assert d0["basis_dictionary"] == d1["basis_dictionary"]
+    np.testing.assert_allclose(d1["weights"], d0["weights"], rtol=0, atol=1e-10 * np.max(np.abs(d0["weights"])))
+    np.testing.assert_allclose(res1, res0, rtol=0, atol=1e-12)
+    calls = []
+    stop_after_two = lambda s, a, y: (calls.append(1) or len(calls) < 2)
+    d2, res2 = QO().find_periods(x, num=6, thresh=None, test_function=stop_after_two)
+    calls2 = []
+    with contextlib.redirect_stdout(io.StringIO()):
+        e2, r2 = oq.find_periods(x, num=6, test_function=lambda s, a, y: (calls2.append(1) or len(calls2) < 2))
+    assert np.asarray(d2["periods"]).tolist() == np.asarray(e2["periods"]).tolist()
+    assert d2["basis_dictionary"] == e2["basis_dictionary"]
+    np.testing.assert_allclose(res2, r2, rtol=0, atol=1e-11)
