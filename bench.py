@@ -811,6 +811,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         emit(line)
     if world > 1:
         dist.barrier()
+        sharding.Comm.destroy_all()
         dist.destroy_process_group()
 
 

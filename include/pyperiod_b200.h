@@ -161,6 +161,19 @@ int pp_best_correlation(const double *x, int64_t ldx, int32_t B, int32_t N, int3
                         const int32_t *chain_q, int32_t table_pmax, uint32_t *periods, double *powers,
                         double *bases, int32_t *status, void *workspace, size_t workspace_bytes, void *stream);
 
+/* ---- Periods.best_frequency (Periods.py:351-398), one round for a batch ---------------------------------
+ * mags[B, F]: magnitude spectrum of the current residual (|rfft(work, win_size)|, F = win_size / 2 + 1; the FFT
+ * itself is the FFT library's).  Per window: bin = first arg-max of mags (np.argmax), p = round-half-even(2 *
+ * win_size / bin) (:383-386), base = project(work, p, trunc, orth) bit-exactly, periods[b, round] = p,
+ * norms[b, round] = ||base|| / sqrt(N), bases[b, round, :] = base (nullable), work[b] -= base in place.  Every
+ * window has its own period in the same launch.  status[b] must be PP_STATUS_OK on entry of round 0; a window
+ * whose peak is the DC bin gets PP_STATUS_NO_PERIOD (the reference raises OverflowError on int(round(inf))) and
+ * is skipped by later rounds.  p > N is the reference's one-row padding case (:172-176). */
+int pp_best_frequency_round(double *work, int32_t B, int32_t N, const double *mags, int32_t F, int32_t win_size,
+                            int32_t trunc, int32_t orth, const int32_t *chain_off, const int32_t *chain_q,
+                            int32_t table_pmax, uint32_t *periods, double *norms, double *bases, int32_t round,
+                            int32_t num, int32_t *status, void *stream);
+
 /* ---- QOPeriods.find_periods, default branch (QOPeriods.py:313-643, 743-852) ---------------
  * Per window up to `num` rounds: gamma-norm sweep of the residual over [pmin, pmax]
  * (trunc = the instance's trunc_to_integer_multiple, orthogonalize False, :470-478); dictionary
@@ -271,6 +284,22 @@ int pp_ramanujan_norms_tf32(const double *x, int64_t ldx, int32_t B, int32_t N, 
  * (RamanujanPeriods.py:97-101); nper[b] may exceed kmax, only the first kmax are stored. */
 int pp_ramanujan_select(const double *norms, int32_t B, int32_t ld_norms, int32_t qlen, double thresh,
                         int32_t kmax, int32_t *periods, int32_t *nper, void *stream);
+
+/* ---- the one collective of the path: gather of compact results over NCCL / NVLink ---------
+ * Windows shard across GPUs with no data-path exchange; only the compact outputs (periods u32, powers f64, status
+ * i32: ~124 B per window) travel to one rank.  pp_gather enqueues that exchange on `stream` -- the compute stream,
+ * right behind the last kernel, no host synchronisation -- as ncclGather (NCCL >= 2.28) or the equivalent grouped
+ * ncclSend / ncclRecv.  Every rank sends `bytes` bytes; `recv` (root only, nranks * bytes) receives them in rank order.
+ * NCCL is resolved at run time (dlopen of the libnccl.so.2 already in the process, or the path given to
+ * pp_comm_load); the library has no link-time dependency on it.  Communicator bootstrap: rank 0 calls
+ * pp_comm_unique_id and hands the 128 bytes to the other ranks by any channel (the Python layer broadcasts them
+ * with torch.distributed), then every rank calls pp_comm_init. */
+int pp_comm_load(const char *library_path);        /* optional: explicit path of libnccl.so.2 */
+int pp_comm_version(void);                         /* NCCL version code (e.g. 22809), -1 if NCCL is unavailable */
+int pp_comm_unique_id(void *id_out_128_bytes);
+int pp_comm_init(void **comm_out, int32_t nranks, int32_t rank, const void *id_128_bytes);
+int pp_comm_destroy(void *comm);
+int pp_gather(void *comm, const void *send, void *recv, size_t bytes, int32_t root, void *stream);
 
 /* ---- roofline denominators measured live -----------------------
  * kind 0: shared-memory load bandwidth, out_host[0] = bytes/s over the whole chip;

@@ -44,6 +44,14 @@ SIGNATURES = {
                                     _p, _p, _p, _p, _p, _p, _sz, _p]),
     "pp_best_correlation": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _f64, _i32, _i32, _i32, _p, _p, _i32,
                                       _p, _p, _p, _p, _p, _sz, _p]),
+    "pp_best_frequency_round": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _i32, _i32,
+                                          _p, _p]),
+    "pp_comm_load": (C.c_int, [C.c_char_p]),
+    "pp_comm_version": (C.c_int, []),
+    "pp_comm_unique_id": (C.c_int, [_p]),
+    "pp_comm_init": (C.c_int, [_p, _i32, _i32, _p]),
+    "pp_comm_destroy": (C.c_int, [_p]),
+    "pp_gather": (C.c_int, [_p, _p, _p, _sz, _i32, _p]),
     "pp_microbench": (C.c_int, [_i32, _i32, _p]),
     "pp_ramanujan_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "pp_ramanujan_norms": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _p, _sz, _p]),

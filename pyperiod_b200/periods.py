@@ -342,46 +342,48 @@ class Periods:
     def best_frequency(self, *args, **kw):
         """Best-frequency (Periods.py:351-398).  best_frequency([data,] win_size=None, num=5).
 
-        Not on the north-star hot path: the spectrum comes from torch.fft (cuFFT), the
-        projection and residual update from this library's exact projection kernel.  1-D or (B, N).
-        Like the reference, a window whose DC bin is the largest gives p = round(2*win/0) -> error.
+        Per round: the magnitude spectrum of the residual (torch.fft.rfft -- an FFT, cuFFT's), then ONE fused launch
+        (pp_best_frequency_round) in which every window finds its own peak bin, derives its own period, projects
+        exactly, writes period / norm / basis and updates its residual.  No host synchronisation between rounds.
+        Like the reference, a window whose DC bin is the largest has p = round(2*win/0) = round(inf): OverflowError.
         """
         data, pos = self._split(args, ["win_size", "num"])
         kw = {**pos, **kw}
         win_size = kw.pop("win_size", None)
         num = int(kw.pop("num", 5))
+        return_bases = kw.pop("return_bases", True)
         if kw:
             raise TypeError(f"unexpected arguments {sorted(kw)}")
+        lib = _lib.load()
         w = stage_windows(data, self._device)
         n = w.n
         if win_size is None:
             win_size = n
         elif win_size < n:
             warn("win_size is smaller than the input signal length. It will be truncated and information will be lost.")
-        x = torch.as_strided(w.tensor, (w.b, n), (w.ldx, 1)).clone()
-        data_norm = Periods.periodic_norm(x, device=w.device)
-        periods = torch.zeros((w.b, num), dtype=torch.int32, device=w.device)
-        norms = torch.zeros((w.b, num), dtype=torch.float64, device=w.device)
-        bases = torch.zeros((w.b, num, n), dtype=torch.float64, device=w.device)
+        win_size = int(win_size)
+        dev = w.device
+        work = torch.as_strided(w.tensor, (w.b, n), (w.ldx, 1)).clone()   # data.copy() (Periods.py:381)
+        data_norm = torch.empty((w.b,), dtype=torch.float64, device=dev)
+        call(lib.pp_periodic_norm, "pp_periodic_norm", dev, ptr(work), n, w.b, n, 0, ptr(data_norm), stream_ptr(dev))
+        orth = int(self._orthogonalize)
+        tb = get_tables(n if orth else 2)
+        co, cq, _, _ = tb.device(dev)
+        periods = torch.zeros((w.b, num), dtype=torch.int32, device=dev)
+        norms = torch.zeros((w.b, num), dtype=torch.float64, device=dev)
+        bases = torch.zeros((w.b, num, n), dtype=torch.float64, device=dev) if return_bases else None
+        status = torch.zeros((w.b,), dtype=torch.int32, device=dev)
         for i in range(num):
-            mags = torch.abs(torch.fft.rfft(x, win_size, dim=1))
-            peak = torch.argmax(mags, dim=1)
-            if bool((peak == 0).any()):
-                raise ZeroDivisionError("best_frequency: the DC bin is the spectral peak (p = 2*win/0), as in the reference")
-            p = torch.round((2.0 * win_size) / peak.double()).to(torch.int32)
-            # windows sharing a period are projected together (one kernel launch per distinct period)
-            for pv in torch.unique(p).tolist():
-                rows = torch.nonzero(p == pv).flatten()
-                base = Periods.project(x[rows], int(pv), self._trunc_to_integer_multiple, self._orthogonalize)
-                bases[rows, i] = base
-                norms[rows, i] = Periods.periodic_norm(base, device=w.device)
-                x[rows] = x[rows] - base
-            periods[:, i] = p
+            mags = torch.abs(torch.fft.rfft(work, win_size, dim=1)).contiguous()
+            call(lib.pp_best_frequency_round, "pp_best_frequency_round", dev, ptr(work), w.b, n, ptr(mags), mags.shape[1],
+                 win_size, int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq), tb.pmax, ptr(periods), ptr(norms),
+                 ptr(bases), i, num, ptr(status), stream_ptr(dev))
         powers = norms / data_norm[:, None]
-        res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases),
-                          _export(w, torch.zeros((w.b,), dtype=torch.int32, device=w.device)))
+        res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases), _export(w, status))
         if w.was_1d:
-            return res.periods[0], res.powers[0], res.bases[0]
+            if int(res.status[0]) != _lib.STATUS_OK:
+                raise OverflowError("cannot convert float infinity to integer")   # int(np.round(2*win/0)), Periods.py:386
+            return res.periods[0], res.powers[0], (None if res.bases is None else res.bases[0])
         return res
 
     # ------------------------------------------------------------------ properties (Periods.py:606-644)

@@ -530,3 +530,28 @@ def test_near_ties_are_zero_on_noisy_windows_and_flagged_on_clean_sines(P):
         per0, pw0, _ = op.m_best_gamma(x, 1, 1024)
         assert int(rg.periods[0, 0]) == int(per0[0]) == p0
         np.testing.assert_allclose(rg.powers[0, 0], pw0[0], rtol=1e-12)
+
+
+def test_best_frequency_fused_round_cases(P):
+    """pp_best_frequency_round: every window of a batch gets its own period in one launch; win_size != N; a window whose
+    DC bin is the spectral peak is flagged (the reference raises OverflowError on int(round(inf)), Periods.py:386) while
+    the rest of the batch is unaffected."""
+    xb = synth.synth_batch(6, 1500, 4200)
+    xb[4] += 3.0                                       # DC-dominated window
+    res = P().best_frequency(xb, num=4)
+    assert res.status.tolist() == [0, 0, 0, 0, 1, 0]
+    assert len({tuple(res.periods[b].tolist()) for b in (0, 1, 2, 3, 5)}) > 1     # windows differ in their periods
+    for b in (0, 1, 2, 3, 5):
+        per0, pw0, bs0 = op.best_frequency(xb[b], None, 4)
+        assert np.array_equal(res.periods[b], per0)
+        np.testing.assert_allclose(res.powers[b], pw0, rtol=RTOL)
+        np.testing.assert_allclose(res.bases[b], bs0, rtol=RTOL, atol=1e-14)
+    with pytest.raises(OverflowError):
+        P().best_frequency(xb[4], num=2)
+    x = synth.synth(1000, 4300)
+    for win in (4096, 1000, 999):
+        per, pw, bs = P(True, False).best_frequency(x, win_size=win, num=3)
+        per0, pw0, bs0 = op.best_frequency(x, win, 3, True, False)
+        assert np.array_equal(per, per0)
+        np.testing.assert_allclose(pw, pw0, rtol=RTOL)
+        np.testing.assert_allclose(bs, bs0, rtol=RTOL, atol=1e-14)
