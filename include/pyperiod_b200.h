@@ -261,6 +261,16 @@ int pp_qo_get_periods(int32_t B, int32_t kmax, int32_t tmax, int32_t rmax, const
                       const int64_t *weights_off, double *out, const int64_t *out_off, int32_t *iters,
                       int32_t *status, void *stream);
 
+/* ---- QOPeriods.get_best_period_orthogonal / eq_3 (QOPeriods.py:1122-1232): Muresan's equation-3 finder ----
+ * raw[b, q] = max(eq_3(x_b, q), 0) for q in [1, max_p) (raw[b, 0] = 0), with eq_3 evaluated as
+ * (q / N) * (energy of the residue-class fold - 2 * autocorrelation at lag (N // q) * q) -- the same quantity as the
+ * reference's sum of autocorrelations at multiples of q (:1123-1150);  pows[b, q] = raw minus the powers of the
+ * proper divisors (a Moebius inversion of the reference's sequential subtraction, :1209-1217), negatives clamped,
+ * divided by q when `normalize`;  best[b] = first arg-max of pows, or 1 when all powers are zero (:1226-1232).
+ * raw / pows are nullable, [B, max_p] row-major.  mu: device int32 Moebius table for 0..table_pmax. */
+int pp_muresan_powers(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t max_p, int32_t normalize,
+                      const int32_t *mu, int32_t table_pmax, double *raw, double *pows, int32_t *best, void *stream);
+
 /* ---- RamanujanPeriods.find_periods (RamanujanPeriods.py:67-86, 124-169) ------------------
  * norms[b, q] = sum_n (sum_i <x, r_i> r_i)[n]^2 over the q-row Ramanujan dictionary of period q,
  * evaluated in fp64 as the dense contraction (q / phi(q)^2) * circ(c_q) * S_q on the FP64 tensor

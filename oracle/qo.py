@@ -239,3 +239,40 @@ def get_periods(weights, layout: dict, decomp_type: str = "row reduction"):
         start = int(np.sum(periods[:i]))
         out.append(actual[start: start + p])
     return tuple(out)
+
+
+# --------------------------------------------------------------------------- Muresan eq. 3 (QOPeriods.py:1122-1232)
+def auto_corr(x: np.ndarray, k: int) -> float:
+    """QOPeriods.py:1152-1173."""
+    n = len(x)
+    return float(np.sum(np.prod(np.vstack((x[0: n - k], x[k:n])), 0)))
+
+
+def eq_3(x: np.ndarray, p: int) -> float:
+    """QOPeriods.py:1123-1150: (P / N) * (ac(0) + 2 * sum_{l=1}^{M-1} ac(l P)), M = N // P."""
+    n = len(x)
+    second = 0
+    for ell in range(1, n // p):
+        second += auto_corr(x, int(ell * p))
+    return (p / n) * (auto_corr(x, 0) + 2 * second)
+
+
+def get_best_period_orthogonal(x: np.ndarray, max_p=None, normalize: bool = False, return_powers: bool = False):
+    """QOPeriods.py:1175-1232."""
+    if max_p is None:
+        max_p = len(x) // 2
+    q_all = np.arange(1, max_p)
+    pows = np.zeros(q_all[-1] + 1)
+    for q in q_all:
+        pows[q] = max(eq_3(x, int(q)), 0)
+        for f in divisor_set(int(q)):
+            if f != q:
+                pows[q] -= pows[f]
+    pows[pows < 0] = 0
+    if normalize:
+        pows[1:] = pows[1:] / q_all
+    if return_powers:
+        return pows
+    if np.argmax(pows) > 0:
+        return q_all[np.argmax(pows)] - 1
+    return 1

@@ -46,6 +46,7 @@ SIGNATURES = {
                                       _p, _p, _p, _p, _p, _sz, _p]),
     "pp_best_frequency_round": (C.c_int, [_p, _i32, _i32, _p, _i32, _i32, _i32, _i32, _p, _p, _i32, _p, _p, _p, _i32, _i32,
                                           _p, _p]),
+    "pp_muresan_powers": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _i32, _p, _p, _p, _p]),
     "pp_comm_load": (C.c_int, [C.c_char_p]),
     "pp_comm_version": (C.c_int, []),
     "pp_comm_unique_id": (C.c_int, [_p]),

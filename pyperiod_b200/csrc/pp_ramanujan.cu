@@ -241,155 +241,240 @@ ram_gemm_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count,
 }
 
 // ------------------------------------------------------------------------------------------
-// TF32 option: the same contraction on the 19-bit tensor cores (mma.sync m16n8k8, fp32 accumulate).
-// c_q(n) is an integer with |c_q| <= phi(q) < 2^11, exact in TF32; the fold sums are split into
-// hi + lo TF32 parts (two MMAs per tile), which leaves ~2^-21 relative error per product and the fp32
-// accumulation of q terms: norms agree with the fp64 path to ~1e-5 relative.
+// TF32 option: the same contraction on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulator in
+// tensor memory).  c_q(n) is an integer with |c_q| <= phi(q) < 2^11, exact in TF32; the fold sums are split into
+// hi + lo TF32 parts, both accumulated into the SAME tensor-memory tile (two MMAs per k-step), which leaves ~2^-21
+// relative error per product and the fp32 accumulation of q terms: norms agree with the fp64 path to ~1e-5.
+//
+// Orientation: D[w][m] = sum_k A[w][k] B[m][k] with A[w][k] = S_q[k] of window w (UMMA M = 128 windows, one
+// tensor-memory lane per window) and B[m][k] = c_q((k - m) mod q) (UMMA N = up to 256 output residues).  Each
+// epilogue thread owns one window (one TMEM lane) and accumulates cnt_m * z_m^2 over its columns: no cross-lane
+// reduction.  Both operands are K-major tiles of 32 tf32 (one 128-byte row per window / residue) in the canonical
+// SWIZZLE_128B layout, written by the CTA's own threads (the circulant is generated from c_q, the fold sums are
+// converted from fp64) and handed to the tensor core through fence.proxy.async; two stages, so the tiles of
+// k-block i+1 are built while the MMAs of k-block i run (tcgen05.commit -> mbarrier releases a stage).
 // ------------------------------------------------------------------------------------------
+constexpr int kUW = 128;          // windows per work unit (UMMA M)
+constexpr int kUN = 256;          // output residues per accumulator tile (UMMA N, TMEM columns)
+constexpr int kUK = 32;           // tf32 per k-block: one 128-byte swizzle row
+constexpr int kUStageBytes = (2 * kUW + kUN) * 128;   // A_hi | A_lo | B
+constexpr int kUStages = 2;
+
 __device__ __forceinline__ uint32_t to_tf32(float v) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
   return r;
 }
-__device__ __forceinline__ void mma_tf32_m16n8k8(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+// byte offset of 16-byte chunk c of row r in a K-major SWIZZLE_128B tile (8-row groups of 1024 bytes)
+__device__ __forceinline__ uint32_t sw128_off(int r, int c) {
+  return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) << 4));
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start address >> 4 [0,14), leading byte offset >> 4
+// [16,30) (1: unused for swizzled K-major), stride byte offset >> 4 [32,46) (1024 bytes between 8-row groups),
+// version 1 [46,48), layout SWIZZLE_128B = 2 [61,64)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) |
+         ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32 [4,6), A = B = TF32 (2) [7,10) [10,13), both K-major,
+// N >> 3 [17,23), M >> 4 [24,29)
+__device__ __forceinline__ uint32_t umma_idesc_tf32(int m, int n) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                          uint32_t accumulate) {
   asm volatile(
-      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
-      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-__global__ void __launch_bounds__(kThreads, 2)
-ram_gemm_tf32_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count, int N, int qmin, int qmax,
+// shared-memory plan of the tcgen05 kernel (bytes from a 1024-aligned base)
+struct UmmaPlan {
+  int qpad;
+  __host__ __device__ size_t off_cq() const { return (size_t)kUStages * kUStageBytes; }
+  __host__ __device__ size_t off_red() const { return off_cq() + (size_t)qpad * 4; }
+  __host__ __device__ size_t off_bar() const { return off_red() + (size_t)kUW * 8; }
+  __host__ __device__ size_t bytes() const { return off_bar() + 64 + 1024; }   // + slack for the 1024-byte alignment
+};
+
+// persistent grid; work unit u = (period, 128-window tile), big periods first, handed out by a global counter.
+// S[soff(q) + k * ldS + w] = fold sum of window w at residue k (fold_all_kernel).
+__global__ void __launch_bounds__(kThreads, 1)
+ram_umma_tf32_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count, int N, int qmin, int qmax,
                      const double* __restrict__ cq_all, const int32_t* __restrict__ phi, double* __restrict__ norms,
-                     int ld_norms) {
-  const int q = qmax - blockIdx.y;  // big periods first
-  if (q < qmin) return;
-  const int b0 = blockIdx.x * kGemmN;
-  if (b0 >= b_count) return;
-  float* cqs = reinterpret_cast<float*>(pp_smem);                       // [q] (TF32-exact integers)
-  double* Bs0 = reinterpret_cast<double*>(pp_smem) + ((q + 3) / 2 & ~1);  // [2][kGemmK][kLdB] fp64 fold chunk
-  double* red = Bs0 + 2 * kGemmK * kLdB;                                // [4][kGemmN]
+                     int ld_norms, int* __restrict__ next_unit) {
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-  const int wm = wid >> 1, wn = wid & 1;   // warp tile: rows wm*32.., cols wn*32..
-  const int gid = lane >> 2, tig = lane & 3;
-  const double* cq = cq_all + cq_offset(q);
-  for (int i = tid; i < q; i += kThreads) cqs[i] = (float)cq[i];
-  const double* Sq = S + s_offset(q, qmin, ldS) + b0;
-  const int Mrows = N / q, r0 = N - Mrows * q;
+  const uint32_t base_u32 = (smem_u32(pp_smem) + 1023u) & ~1023u;
+  unsigned char* base = pp_smem + (base_u32 - smem_u32(pp_smem));
+  UmmaPlan pl;
+  pl.qpad = (qmax + 3 + 31) & ~31;
+  float* cqs = reinterpret_cast<float*>(base + pl.off_cq());
+  double* red = reinterpret_cast<double*>(base + pl.off_red());
+  uint64_t* bars = reinterpret_cast<uint64_t*>(base + pl.off_bar());   // [0], [1]: stage free; [2]: accumulator ready
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3);
+  int* unit_slot = reinterpret_cast<int*>(tmem_slot + 1);
 
-  double colacc[4][2];
-#pragma unroll
-  for (int j = 0; j < 4; ++j) colacc[j][0] = colacc[j][1] = 0.0;
+  if (tid == 0) {
+    mbar_init(bars + 0, 1);
+    mbar_init(bars + 1, 1);
+    mbar_init(bars + 2, 1);
+  }
+  if (wid == 0) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(kUN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem = *tmem_slot;
 
-  for (int m0 = 0; m0 < q; m0 += kGemmM) {
-    float acc[2][4][4];
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[i][j][e] = 0.f;
-    auto stage = [&](double* dst, int l0) {
-      for (int idx = tid; idx < kGemmK * kGemmN / 2; idx += kThreads) {
-        const int kk = idx >> 5, n = (idx & 31) * 2;
-        int bytes = 0;
-        if (l0 + kk < q) bytes = min(max(b_count - (b0 + n), 0), 2) * 8;
-        const double* src = bytes ? Sq + (size_t)(l0 + kk) * ldS + n : Sq;
-        cp_async_16(dst + kk * kLdB + n, src, bytes);
-      }
-      cp_async_commit();
-    };
+  const int ntiles_w = (b_count + kUW - 1) / kUW;
+  const int nunits = (qmax - qmin + 1) * ntiles_w;
+  uint32_t phase0 = 0, phase1 = 0, phase_acc = 0;   // mbarrier parities (uniform over the CTA)
+  bool pend0 = false, pend1 = false;                 // a commit on the stage barrier has not been waited for yet
+
+  for (;;) {
+    if (tid == 0) *unit_slot = atomicAdd(next_unit, 1);
     __syncthreads();
-    stage(Bs0, 0);
-    int buf = 0;
-    for (int l0 = 0; l0 < q; l0 += kGemmK, buf ^= 1) {
-      const double* Bs = Bs0 + buf * (kGemmK * kLdB);
-      if (l0 + kGemmK < q) {
-        stage(Bs0 + (buf ^ 1) * (kGemmK * kLdB), l0 + kGemmK);
-        cp_async_wait<1>();
-      } else {
-        cp_async_wait<0>();
-      }
-      __syncthreads();
-#pragma unroll
-      for (int k8 = 0; k8 < kGemmK / 8; ++k8) {
-        // B fragments (k x n = 8 x 8 per tile j): b0 = (k = tig, n = gid), b1 = (k = tig + 4, n = gid); hi + lo split
-        uint32_t bh[4][2], bl[4][2];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-#pragma unroll
-          for (int h = 0; h < 2; ++h) {
-            const double v = Bs[(k8 * 8 + tig + 4 * h) * kLdB + wn * 32 + j * 8 + gid];
-            const float f = (float)v;
-            const uint32_t hi = to_tf32(f);
-            bh[j][h] = hi;
-            bl[j][h] = to_tf32((float)(v - (double)__uint_as_float(hi)));
-          }
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-          // A fragment (m x k = 16 x 8): a0 = (gid, tig), a1 = (gid + 8, tig), a2 = (gid, tig + 4), a3 = (gid + 8, tig + 4)
-          uint32_t a[4];
+    const int u = *unit_slot;
+    if (u >= nunits) break;
+    const int q = qmax - u / ntiles_w;
+    const int w0 = (u % ntiles_w) * kUW;
+    const double* cq = cq_all + cq_offset(q);
+    for (int i = tid; i < q; i += kThreads) cqs[i] = (float)cq[i];
+    const double* Sq = S + s_offset(q, qmin, ldS) + w0;
+    const int wlive = min(kUW, b_count - w0);
+    const int Mrows = N / q, r0 = N - Mrows * q;
+    const int nkb = (q + kUK - 1) / kUK;
+    double wacc = 0.0;   // this thread's window: sum of cnt_m z_m^2 over its half of the columns
+    __syncthreads();
+
+    for (int m0 = 0; m0 < q; m0 += kUN) {
+      const int nt = min(kUN, (q - m0 + 15) & ~15);       // UMMA N of this accumulator tile (multiple of 16)
+      const uint32_t idesc = umma_idesc_tf32(kUW, nt);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int st = kb & 1;
+        unsigned char* stage = base + (size_t)st * kUStageBytes;
+        // the MMAs that read this stage two k-blocks ago must be done before it is rewritten
+        if (st == 0 ? pend0 : pend1) {
+          mbar_wait(bars + st, st == 0 ? phase0 : phase1);
+          if (st == 0) { phase0 ^= 1u; pend0 = false; } else { phase1 ^= 1u; pend1 = false; }
+        }
+        const int k0 = kb * kUK;
+        // ---- A tiles: fold sums of 128 windows x 32 residues, fp64 -> tf32 hi + lo.  One thread = one window row and
+        //      one 16-byte chunk (4 consecutive residues) per step; reads are coalesced over the windows.
+        for (int idx = tid; idx < kUW * 8; idx += kThreads) {
+          const int w = idx & (kUW - 1), c = idx >> 7;
+          uint32_t hi[4], lo[4];
 #pragma unroll
           for (int e = 0; e < 4; ++e) {
-            const int m = m0 + wm * 32 + i * 16 + gid + 8 * (e & 1);
-            const int l = l0 + k8 * 8 + tig + 4 * (e >> 1);
-            float v = 0.f;
-            if (m < q && l < q) {
-              int d = l - m;
+            const int k = k0 + 4 * c + e;
+            double v = 0.0;
+            if (k < q && w < wlive) v = Sq[(size_t)k * ldS + w];
+            const uint32_t h = to_tf32((float)v);
+            hi[e] = h;
+            lo[e] = to_tf32((float)(v - (double)__uint_as_float(h)));
+          }
+          const uint32_t off = sw128_off(w, c);
+          *reinterpret_cast<uint4*>(stage + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(stage + kUW * 128 + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+        // ---- B tile: the circulant, B[m][k] = c_q((k - m) mod q), generated from c_q
+        for (int idx = tid; idx < nt * 8; idx += kThreads) {
+          const int r = idx >> 3, c = idx & 7;
+          const int m = m0 + r;
+          float v[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int k = k0 + 4 * c + e;
+            float x = 0.f;
+            if (m < q && k < q) {
+              int d = k - m;
               if (d < 0) d += q;
-              v = cqs[d];
+              x = cqs[d];
             }
-            a[e] = __float_as_uint(v);  // small integers: already TF32-exact
+            v[e] = x;
           }
+          *reinterpret_cast<float4*>(stage + 2 * kUW * 128 + sw128_off(r, c)) = make_float4(v[0], v[1], v[2], v[3]);
+        }
+        fence_proxy_async();          // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncthreads();
+        if (tid == 0) {
+          asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+          const uint32_t sa = base_u32 + (uint32_t)st * kUStageBytes;
+          const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + kUW * 128),
+                         bd = umma_desc_sw128(sa + 2 * kUW * 128);
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            mma_tf32_m16n8k8(acc[i][j], a, bh[j][0], bh[j][1]);
-            mma_tf32_m16n8k8(acc[i][j], a, bl[j][0], bl[j][1]);
+          for (int k = 0; k < kUK / 8; ++k) {   // UMMA K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
+            umma_tf32(tmem, a_hi + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
+            umma_tf32(tmem, a_lo + 2 * k, bd + 2 * k, idesc, 1u);
+          }
+          umma_commit(bars + st);                       // frees this stage when the MMAs above have read it
+          if (kb == nkb - 1) umma_commit(bars + 2);     // ... and the accumulator tile is complete
+        }
+        if (st == 0) pend0 = true; else pend1 = true;
+      }
+      // ---- epilogue of this accumulator tile: lane = window, columns = output residues m0 .. m0 + nt
+      mbar_wait(bars + 2, phase_acc);
+      phase_acc ^= 1u;
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      {
+        const int half = wid >> 2;                         // warps 0-3: columns [0, 128), warps 4-7: [128, 256)
+        const uint32_t lane_base = (uint32_t)(32 * (wid & 3)) << 16;
+        for (int c0 = half * 128; c0 < min(nt, half * 128 + 128); c0 += 32) {
+          uint32_t r[32];
+          tmem_ld_x32(tmem + lane_base + (uint32_t)c0, r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int m = m0 + c0 + j;
+            if (m < q) {
+              const double z = (double)__uint_as_float(r[j]);
+              wacc = fma((double)(Mrows + (m < r0 ? 1 : 0)) * z, z, wacc);
+            }
           }
         }
       }
-      __syncthreads();
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();   // every warp has read the tile before the next one overwrites it
     }
-    // epilogue: c0,c1 = (row gid, cols 2 tig, 2 tig + 1), c2,c3 = (row gid + 8, same cols)
-#pragma unroll
-    for (int i = 0; i < 2; ++i)
-#pragma unroll
-      for (int hrow = 0; hrow < 2; ++hrow) {
-        const int m = m0 + wm * 32 + i * 16 + gid + 8 * hrow;
-        const double cnt = (m < q) ? (double)(Mrows + (m < r0 ? 1 : 0)) : 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const double z0 = (double)acc[i][j][2 * hrow], z1 = (double)acc[i][j][2 * hrow + 1];
-          colacc[j][0] = fma(cnt * z0, z0, colacc[j][0]);
-          colacc[j][1] = fma(cnt * z1, z1, colacc[j][1]);
-        }
-      }
+    // ---- norms of this unit: the two column halves of a window meet in shared memory
+    const int w = 32 * (wid & 3) + lane;
+    if (wid >= 4) red[w] = wacc;
+    __syncthreads();
+    if (wid < 4 && w < wlive) {
+      const double ph = (double)phi[q];
+      const double scale = (double)q / (ph * ph);
+      norms[(size_t)(b_first + w0 + w) * ld_norms + q] = scale * scale * (wacc + red[w]);
+    }
+    __syncthreads();
   }
-#pragma unroll
-  for (int j = 0; j < 4; ++j)
-#pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      double v = colacc[j][e];
-      v += __shfl_xor_sync(0xffffffffu, v, 4);
-      v += __shfl_xor_sync(0xffffffffu, v, 8);
-      v += __shfl_xor_sync(0xffffffffu, v, 16);
-      colacc[j][e] = v;
-    }
+  // drain: nothing asynchronous may still reference this CTA's shared memory or tensor memory
+  if (pend0) mbar_wait(bars + 0, phase0);
+  if (pend1) mbar_wait(bars + 1, phase1);
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (gid == 0) {
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      red[wm * kGemmN + wn * 32 + j * 8 + 2 * tig] = colacc[j][0];
-      red[wm * kGemmN + wn * 32 + j * 8 + 2 * tig + 1] = colacc[j][1];
-    }
-  }
-  __syncthreads();
-  if (tid < kGemmN && b0 + tid < b_count) {
-    const double ph = (double)phi[q];
-    const double scale = (double)q / (ph * ph);
-    const double t = ((red[tid] + red[kGemmN + tid]) + red[2 * kGemmN + tid]) + red[3 * kGemmN + tid];
-    norms[(size_t)(b_first + b0 + tid) * ld_norms + q] = scale * scale * t;
-  }
+  if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kUN));
 }
 
 // periods whose norm exceeds thresh * |max norm|, ascending (RamanujanPeriods.py:97-101); one warp per window
@@ -427,7 +512,7 @@ size_t pp_ramanujan_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32
   (void)N;
   const size_t ldS = ((size_t)tile_windows + 3) & ~(size_t)3;
   const size_t rows = (size_t)qmax * (qmax + 1) / 2 - (size_t)qmin * (qmin - 1) / 2;
-  return 4096 + (cq_offset(qmax + 1) + 2) * 8 + rows * ldS * 8;
+  return 4096 + 256 + (cq_offset(qmax + 1) + 2) * 8 + rows * ldS * 8;
 }
 
 // norms[b, q] for q in [qmin, qmax] (other entries untouched; the caller zero-fills, RamanujanPeriods.py:71).
@@ -451,23 +536,29 @@ static int ramanujan_norms_impl(const double* x, int64_t ldx, int32_t B, int32_t
   size_t off = 0;
   double* cq = carve(workspace, workspace_bytes, off, (cq_offset(qmax + 1) + 2) * 8);
   double* S = carve(workspace, workspace_bytes, off, rows * (size_t)ldS * 8);
-  if (!cq || !S) return fail(-3, "workspace too small (see pp_ramanujan_workspace_bytes)%s");
+  int* next_unit = reinterpret_cast<int*>(carve(workspace, workspace_bytes, off, 256));
+  if (!cq || !S || !next_unit) return fail(-3, "workspace too small (see pp_ramanujan_workspace_bytes)%s");
   cq_kernel<<<qmax - qmin + 1, 128, 0, st>>>(qmin, qmax, mu, phi, cq);
   const size_t fold_smem = (size_t)kFoldWin * ((N + 1) & ~1) * 8;
   if (int rc = prep_kernel(fold_all_kernel, fold_smem, f)) return rc;
   const size_t gemm_smem = (size_t)(((qmax + 1) & ~1) + 2 * kGemmK * kLdB + 4 * kGemmN) * 8;
   if (int rc = prep_kernel(ram_gemm_kernel, gemm_smem, f)) return rc;
-  if (int rc = prep_kernel(ram_gemm_tf32_kernel, gemm_smem, f)) return rc;
+  UmmaPlan upl;
+  upl.qpad = (qmax + 3 + 31) & ~31;
+  if (tf32)
+    if (int rc = prep_kernel(ram_umma_tf32_kernel, upl.bytes(), f)) return rc;
   for (int b_first = 0; b_first < B; b_first += tile_windows) {
     const int b_count = (B - b_first < tile_windows) ? (B - b_first) : tile_windows;
     int fgrid = (b_count + kFoldWin - 1) / kFoldWin;
     if (fgrid > f.sm_count) fgrid = f.sm_count;
     fold_all_kernel<<<fgrid, kThreads, fold_smem, st>>>(x, ldx, b_first, b_count, N, qmin, qmax, S, ldS);
     dim3 grid((b_count + kGemmN - 1) / kGemmN, qmax - qmin + 1);
-    if (tf32)
-      ram_gemm_tf32_kernel<<<grid, kThreads, gemm_smem, st>>>(S, ldS, b_first, b_count, N, qmin, qmax, cq, phi, norms,
-                                                              ld_norms);
-    else
+    if (tf32) {
+      const int units = (qmax - qmin + 1) * ((b_count + kUW - 1) / kUW);
+      if (int rc = check_cuda(cudaMemsetAsync(next_unit, 0, sizeof(int), st), "cudaMemsetAsync")) return rc;
+      ram_umma_tf32_kernel<<<units < f.sm_count ? units : f.sm_count, kThreads, upl.bytes(), st>>>(
+          S, ldS, b_first, b_count, N, qmin, qmax, cq, phi, norms, ld_norms, next_unit);
+    } else
       ram_gemm_kernel<<<grid, kThreads, gemm_smem, st>>>(S, ldS, b_first, b_count, N, qmin, qmax, cq, phi, norms,
                                                          ld_norms);
   }

@@ -78,8 +78,11 @@ class Periods:
     """Sethares-Staley periodicity transforms, B200-native.  See module docstring."""
 
     def __init__(self, *args, trunc_to_integer_multiple=None, orthogonalize=None, device=None, dtype="fp64",
-                 fold_mode=None):
-        """dtype / fold_mode are not part of the reference API.  dtype="fp32" ranks the M-best sweeps in float
+                 fold_mode=None, devices=None):
+        """device / devices / dtype / fold_mode are not part of the reference API.  devices=[...] (CUDA device indices
+        or names) shards a host (B, N) batch over several GPUs from ONE process: contiguous blocks of windows, one
+        worker thread and one set of launches per device, results concatenated on the host (windows are independent:
+        no collective; the one-process-per-GPU form of the same sharding is pyperiod_b200.sharding).  dtype="fp32" ranks the M-best sweeps in float
         (half the shared-memory traffic) and re-folds every candidate inside the float error bound in fp64, so the
         period lists and norms are those of the fp64 path (the north star's fp32 option).  fold_mode (a
         _lib.FOLD_* value or name) picks how ranking sweeps obtain the residue sums; None = the module default."""
@@ -98,6 +101,10 @@ class Periods:
         self._trunc_to_integer_multiple = bool(trunc)
         self._orthogonalize = bool(orth)
         self._device = device
+        self._devices = None if devices is None else [torch.device("cuda", d) if isinstance(d, int) else torch.device(d)
+                                                      for d in devices]
+        if self._devices is not None and not self._devices:
+            raise ValueError("devices must name at least one CUDA device")
         if dtype not in ("fp64", "fp32"):
             raise ValueError("dtype must be 'fp64' or 'fp32'")
         self._dtype = dtype
@@ -109,6 +116,48 @@ class Periods:
         if self._fold_mode is None and self._dtype == "fp32":
             return _lib.FOLD_NOMINATE_F32
         return _lib.resolve_fold_mode(self._fold_mode)
+
+    # ------------------------------------------------------------------ single-process multi-device sharding
+    def _sharded(self, name, args, kw):
+        """Run method `name` on contiguous row blocks of a host (B, N) batch, one block per entry of `devices`, each
+        from its own thread (the C calls and the copies release the GIL, so the devices work concurrently), and
+        concatenate the per-window results.  Returns None when the call is not a multi-device batch call."""
+        if self._devices is None:
+            return None
+        args = list(args)
+        data = args[0] if args and _is_data(args[0]) else self._data
+        if data is None or (isinstance(data, torch.Tensor) and data.device.type == "cuda") or np.ndim(data) != 2:
+            return None
+        rest = args[1:] if args and _is_data(args[0]) else args
+        from concurrent.futures import ThreadPoolExecutor
+        from .sharding import shard_bounds
+        b = data.shape[0]
+        devs = self._devices[: max(1, min(len(self._devices), b))]
+
+        def work(i):
+            lo, hi = shard_bounds(b, len(devs), i)
+            sub = Periods(self._trunc_to_integer_multiple, self._orthogonalize, device=devs[i], dtype=self._dtype,
+                          fold_mode=self._fold_mode)
+            return getattr(sub, name)(data[lo:hi], *rest, **kw)   # row slices keep hop-framed (overlapping) strides
+
+        with ThreadPoolExecutor(len(devs)) as pool:
+            parts = [p for p in pool.map(work, range(len(devs))) if p.periods.shape[0]]
+
+        def cat(field):
+            vals = [getattr(p, field) for p in parts]
+            if any(v is None for v in vals):
+                return None
+            return np.concatenate([v if isinstance(v, np.ndarray) else v.cpu().numpy() for v in vals])
+        k = max(p.periods.shape[1] for p in parts)
+        for p in parts:   # small_to_large: per-shard capacity may differ
+            if p.periods.shape[1] < k:
+                pad = k - p.periods.shape[1]
+                p.periods = np.pad(p.periods, ((0, 0), (0, pad)))
+                p.powers = np.pad(p.powers, ((0, 0), (0, pad)))
+                if p.bases is not None:
+                    p.bases = np.pad(p.bases, ((0, 0), (0, pad), (0, 0)))
+        return BatchResult(cat("periods"), cat("powers"), cat("bases"), cat("status"), count=cat("count"),
+                           sweeps=cat("sweeps"), near_ties=cat("near_ties"))
 
     # ------------------------------------------------------------------ argument plumbing
     def _split(self, args, names):
@@ -206,6 +255,9 @@ class Periods:
         return self._m_best_meta(True, args, kw)
 
     def _m_best_meta(self, gamma, args, kw):
+        multi = self._sharded("m_best_gamma" if gamma else "m_best", args, kw)
+        if multi is not None:
+            return multi
         data, pos = self._split(args, ["num", "max_length", "min_length"])
         kw = {**pos, **kw}
         return_bases = kw.pop("return_bases", None)
@@ -258,6 +310,9 @@ class Periods:
 
         Batch extras: kmax (capacity per window, default 32), return_bases.
         """
+        multi = self._sharded("small_to_large", args, kw)
+        if multi is not None:
+            return multi
         data, pos = self._split(args, ["thresh", "n_periods"])
         kw = {**pos, **kw}
         thresh = float(kw.pop("thresh", 0.1))
@@ -301,6 +356,9 @@ class Periods:
     # ------------------------------------------------------------------ best correlation
     def best_correlation(self, *args, **kw):
         """Best-correlation (Periods.py:289-349).  best_correlation([data,] num=5, max_length=None, ratio=0.01)."""
+        multi = self._sharded("best_correlation", args, kw)
+        if multi is not None:
+            return multi
         data, pos = self._split(args, ["num", "max_length", "ratio"])
         kw = {**pos, **kw}
         num = int(kw.pop("num", 5))

@@ -246,19 +246,25 @@ class QOPeriods(Periods):
 
         o = launch(w.ptr, w.ldx, w.b, rmax, w.launch_plan())
         big = None
-        if retry_big and rmax < rows_cap:
+        rmax_l = rmax
+        while retry_big and rmax_l < rows_cap:
             idx = torch.nonzero(o["status"] == _lib.STATUS_TOO_LARGE).flatten()
-            if idx.numel():
-                # dictionaries of more than rmax rows: re-run just those windows with room for N rows (more rows than
-                # samples is singular by rank); their padded outputs replace the first launch's
-                xb = torch.as_strided(w.tensor, (w.b, n), (w.ldx, 1))[idx].contiguous()
-                o2 = launch(xb.data_ptr(), n, int(idx.numel()), rows_cap, [(0, int(idx.numel()), None)])
-                for key in ("periods", "norms", "n_periods", "dict_q", "dict_keep", "n_dict", "n_weights", "status"):
-                    o[key][idx] = o2[key]
-                if return_res:
-                    o["res"][idx] = o2["res"]
-                w2 = o2["weights"] if not w.from_host else o2["weights"].cpu()
-                big = {int(b): w2[i] for i, b in enumerate(idx.tolist())}
+            if not idx.numel():
+                break
+            # dictionaries that outgrew the factor storage: re-run just those windows with room for the rows they
+            # reported, at least doubled (a later round may need more: the loop repeats until nothing is left or the
+            # cap -- N rows, more is singular by rank -- is reached).  Small factors keep the re-run in L2.
+            need = int(o["n_weights"][idx].max())
+            rmax_l = min(rows_cap, max(2 * rmax_l, (need + 255) // 256 * 256))
+            xb = torch.as_strided(w.tensor, (w.b, n), (w.ldx, 1))[idx].contiguous()
+            o2 = launch(xb.data_ptr(), n, int(idx.numel()), rmax_l, [(0, int(idx.numel()), None)])
+            for key in ("periods", "norms", "n_periods", "dict_q", "dict_keep", "n_dict", "n_weights", "status"):
+                o[key][idx] = o2[key]
+            if return_res:
+                o["res"][idx] = o2["res"]
+            w2 = o2["weights"] if not w.from_host else o2["weights"].cpu()
+            big = big or {}
+            big.update({int(b): w2[i] for i, b in enumerate(idx.tolist())})
         out = QOBatchResult(_export(w, o["periods"], True), _export(w, o["norms"]), _export(w, o["n_periods"]),
                             _export(w, o["dict_q"]), _export(w, o["dict_keep"]), _export(w, o["n_dict"]),
                             _export(w, o["weights"]), _export(w, o["n_weights"]), _export(w, o["res"]),
@@ -414,6 +420,49 @@ class QOPeriods(Periods):
                                 to_dev(r.n_dict, torch.int32), dq_h, nd_h, flat, ldw, woff)
         host = not isinstance(r.dict_q, torch.Tensor)
         return PeriodsBatch(to_host(out) if host else out, off, dq_h, nd_h, to_host(st) if host else st)
+
+    # ------------------------------------------------------------------ Muresan eq. 3 (QOPeriods.py:1122-1232)
+    def _muresan(self, x, max_p, normalize):
+        lib = _lib.load()
+        w = stage_windows(x, self._device)
+        max_p = w.n // 2 if max_p is None else int(max_p)
+        tb = get_tables(max(max_p, 2))
+        dev = w.device
+        raw = torch.zeros((w.b, max_p), dtype=torch.float64, device=dev)
+        pows = torch.zeros((w.b, max_p), dtype=torch.float64, device=dev)
+        best = torch.zeros((w.b,), dtype=torch.int32, device=dev)
+        call(lib.pp_muresan_powers, "pp_muresan_powers", dev, ptr(w.tensor), w.ldx, w.b, w.n, max_p, int(bool(normalize)),
+             ptr(tb.mu_device(dev)), tb.pmax, ptr(raw), ptr(pows), ptr(best), stream_ptr(dev))
+        return w, raw, pows, best, max_p
+
+    def get_best_period_orthogonal(self, x, max_p=None, normalize=False, return_powers=False):
+        """Muresan's equation-3 period finder (QOPeriods.py:1175-1232), 1-D or (B, N): powers of every period below
+        max_p with the powers of its proper divisors removed; the strongest period, or the powers themselves."""
+        w, _, pows, best, max_p = self._muresan(x, max_p, normalize)
+        if return_powers:
+            out = _export(w, pows)
+            return out[0] if w.was_1d else out
+        out = _export(w, best)
+        if w.was_1d:
+            if int(out[0]) >= max_p - 1 and max_p > 2:
+                raise IndexError(f"index {int(out[0])} is out of bounds for axis 0 with size {max_p - 1}")  # Q[argmax], :1228
+            return int(out[0])
+        return out
+
+    def eq_3(self, x, P):
+        """Equation 3 of Muresan & Parks for period P (QOPeriods.py:1123-1150); 1-D -> float, (B, N) -> (B,).  The
+        device returns max(eq_3, 0) (what the finder uses); eq_3 itself is a sum of squares up to the single lag it
+        leaves out, so negative values only occur at rounding level."""
+        w, raw, _, _, _ = self._muresan(x, int(P) + 1, False)
+        out = _export(w, raw[:, int(P)].contiguous())
+        return float(out[0]) if w.was_1d else out
+
+    def auto_corr(self, x, k):
+        """sum_n x[n] x[n + k] (QOPeriods.py:1152-1173)."""
+        w = stage_windows(x, self._device)
+        xs = torch.as_strided(w.tensor, (w.b, w.n), (w.ldx, 1))
+        out = _export(w, (xs[:, : w.n - int(k)] * xs[:, int(k):]).sum(dim=1))
+        return float(out[0]) if w.was_1d else out
 
     @staticmethod
     def solve_quadratic(x, A, type="solve", window=None, k=0):

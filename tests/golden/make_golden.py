@@ -298,6 +298,22 @@ def gen_qo_rambasis():
     save("qo_rambasis", **out)
 
 
+# ------------------------------------------------------------------ 11. Muresan eq. 3 finder (QOPeriods.py:1122-1232)
+MURESAN_CASES = [(600, 5, None), (1024, 50_001, 300), (2000, 7, None)]
+
+
+def gen_muresan():
+    out = {}
+    q = QOPeriods()
+    for i, (n, seed, max_p) in enumerate(MURESAN_CASES):
+        x = synth.synth(n, seed)
+        for norm in (False, True):
+            out[f"c{i}_pows_{int(norm)}"] = quiet(q.get_best_period_orthogonal, x, max_p, norm, True)
+            out[f"c{i}_best_{int(norm)}"] = np.array(quiet(q.get_best_period_orthogonal, x, max_p, norm, False))
+        out[f"c{i}_eq3"] = np.array([quiet(q.eq_3, x, p) for p in (1, 2, 7, 30, 97, n // 4)])
+    save("muresan", **out)
+
+
 if __name__ == "__main__":
     which = sys.argv[1:] or ["project", "readme", "mbest_stream", "s2l", "bcorr", "qo_ram", "qo_gcd", "qo_rambasis"]   # + "ram_cfg5" (slow)
     for w in which:

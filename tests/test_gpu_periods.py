@@ -555,3 +555,31 @@ def test_best_frequency_fused_round_cases(P):
         assert np.array_equal(per, per0)
         np.testing.assert_allclose(pw, pw0, rtol=RTOL)
         np.testing.assert_allclose(bs, bs0, rtol=RTOL, atol=1e-14)
+
+
+def test_single_process_multi_device_sharding(P):
+    """Periods(devices=[...]): one process, contiguous row blocks per device, one worker thread each.  A one-GPU box
+    runs it with the same device listed twice (two threads, two workspaces, the shard / merge logic); with more GPUs
+    the same call spreads over them."""
+    import torch
+    xb = synth.synth_batch(37, 1024, 5100)
+    ndev = torch.cuda.device_count()
+    devs = [0, 1 % ndev, 0][: 3]
+    one = P().m_best(xb, num=5, max_length=300)
+    many = P(devices=devs).m_best(xb, num=5, max_length=300)
+    assert np.array_equal(one.periods, many.periods) and np.array_equal(one.powers, many.powers)
+    assert np.array_equal(one.sweeps, many.sweeps) and many.status.shape == (37,)
+    s1 = P().small_to_large(xb, thresh=0.08)
+    s2 = P(devices=devs).small_to_large(xb, thresh=0.08)
+    assert np.array_equal(s1.count, s2.count)
+    for b in range(37):
+        assert s1.window(b)[0] == s2.window(b)[0]
+    c1 = P(True, True).best_correlation(xb, num=3, max_length=200)
+    c2 = P(True, True, devices=devs).best_correlation(xb, num=3, max_length=200)
+    assert np.array_equal(c1.periods, c2.periods) and np.array_equal(c1.powers, c2.powers)
+    # hop-framed stream: every shard uploads its own range of the stream (with the halo)
+    stream = synth.synth_stream(64, 1024, 128, 777)
+    win = synth.windows_from_stream(stream, 1024, 128)
+    a = P().m_best_gamma(win, num=4, max_length=256)
+    b2 = P(devices=devs).m_best_gamma(win, num=4, max_length=256)
+    assert np.array_equal(a.periods, b2.periods) and np.array_equal(a.powers, b2.powers)

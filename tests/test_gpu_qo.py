@@ -279,3 +279,30 @@ def test_custom_test_function(QO):
     assert np.asarray(d2["periods"]).tolist() == np.asarray(e2["periods"]).tolist()
     assert d2["basis_dictionary"] == e2["basis_dictionary"]
     np.testing.assert_allclose(res2, r2, rtol=0, atol=1e-11)
+
+
+def test_muresan_eq3_finder_vs_golden(QO):
+    """get_best_period_orthogonal / eq_3 (QOPeriods.py:1122-1232) on the device against the
+    reference's own outputs: equation-3 powers with the divisors' powers removed, plain and normalised, the selected
+    period, and eq_3 itself; 1-D and batched."""
+    g = load_golden("muresan")
+    cases = [(600, 5, None), (1024, 50_001, 300), (2000, 7, None)]
+    for i, (n, seed, max_p) in enumerate(cases):
+        x = synth.synth(n, seed)
+        q = QO()
+        for norm in (False, True):
+            want = g[f"c{i}_pows_{int(norm)}"]
+            got = q.get_best_period_orthogonal(x, max_p, norm, True)
+            assert got.shape == want.shape
+            np.testing.assert_allclose(got, want, rtol=0, atol=1e-10 * np.max(want))
+            assert q.get_best_period_orthogonal(x, max_p, norm) == int(g[f"c{i}_best_{int(norm)}"])
+        got = [q.eq_3(x, p) for p in (1, 2, 7, 30, 97, n // 4)]
+        np.testing.assert_allclose(got, g[f"c{i}_eq3"], rtol=1e-11)
+    xb = np.stack([synth.synth(600, 5), synth.synth(600, 6), synth.synth(600, 7)])
+    best = QO().get_best_period_orthogonal(xb, None, True)
+    pw = QO().get_best_period_orthogonal(xb, None, True, True)
+    assert pw.shape == (3, 300) and int(best[0]) == int(g["c0_best_1"])
+    for b in range(3):
+        np.testing.assert_allclose(pw[b], oq.get_best_period_orthogonal(xb[b], None, True, True), rtol=0,
+                                   atol=1e-10 * np.max(pw[b]))
+    np.testing.assert_allclose(QO().auto_corr(xb[0], 17), oq.auto_corr(xb[0], 17), rtol=1e-12)
