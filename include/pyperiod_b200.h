@@ -283,12 +283,26 @@ int pp_ramanujan_norms(const double *x, int64_t ldx, int32_t B, int32_t N, int32
                        const int32_t *mu, const int32_t *phi, int32_t table_qmax, int32_t tile_windows,
                        double *norms, int32_t ld_norms, void *workspace, size_t workspace_bytes, void *stream);
 
-/* TF32 option of the same periodogram (mma.sync m16n8k8, fp32 accumulation): the Ramanujan sums are exact in
- * TF32, the fold sums are split into hi + lo parts; norms agree with the fp64 path to ~1e-5 relative.  The fold
- * itself stays fp64. */
+/* TF32 option of the same periodogram on the 5th-generation tensor cores (tcgen05.mma kind::tf32, accumulator in
+ * tensor memory, fp32 accumulation): the Ramanujan sums are exact in TF32, the fold sums are split into hi + lo
+ * parts; norms agree with the fp64 path to ~1e-5 relative.  The fold itself stays fp64. */
 int pp_ramanujan_norms_tf32(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
                             const int32_t *mu, const int32_t *phi, int32_t table_qmax, int32_t tile_windows,
                             double *norms, int32_t ld_norms, void *workspace, size_t workspace_bytes, void *stream);
+
+/* float32-compat option: the reference's OWN numbers.  RamanujanPeriods.project stores each projected row in a
+ * float32 array (RamanujanPeriods.py:127-130); find_periods adds the q rows in float32 in row order (np.sum over
+ * axis 0, :77) and sums the squares of the N float32 samples with numpy's pairwise summation (:78).  This entry
+ * reproduces that arithmetic operation by operation on top of the fp64 tensor-core products (<x, r_i> in fp64, each
+ * product rounded to float32 once, sequential float32 row sum, numpy's 8-lane / 128-block pairwise tree), so the
+ * norms equal the reference's to the last float32 bit except where the reference's own 1e-13 noise in Cq
+ * (:142-144, a sum of complex exponentials) moves a rounding.  Workspace: pp_ramanujan_f32compat_workspace_bytes
+ * (the products H S_q of a tile are kept beside its folds).  N <= 32768. */
+size_t pp_ramanujan_f32compat_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32_t tile_windows);
+int pp_ramanujan_norms_f32compat(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
+                                 const int32_t *mu, const int32_t *phi, int32_t table_qmax, int32_t tile_windows,
+                                 double *norms, int32_t ld_norms, void *workspace, size_t workspace_bytes,
+                                 void *stream);
 
 /* periods[b, 0:nper[b]] = ascending q in [0, qlen) with norms[b,q] / |max_q norms[b,q]| > thresh
  * (RamanujanPeriods.py:97-101); nper[b] may exceed kmax, only the first kmax are stored. */

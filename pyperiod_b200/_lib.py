@@ -57,6 +57,9 @@ SIGNATURES = {
     "pp_ramanujan_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "pp_ramanujan_norms": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _p, _sz, _p]),
     "pp_ramanujan_norms_tf32": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _p, _sz, _p]),
+    "pp_ramanujan_f32compat_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "pp_ramanujan_norms_f32compat": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _p, _sz,
+                                              _p]),
     "pp_ramanujan_select": (C.c_int, [_p, _i32, _i32, _i32, _f64, _i32, _p, _p, _p]),
     "pp_qo_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32, _i32]),
     "pp_qo_find_periods": (C.c_int, [_p, _i64, _i32, _i32, _i32, _f64, _i32, _i32, _i32, _i32, _i32, _i32, _p, _i32, _i32,

@@ -129,7 +129,7 @@ __device__ __forceinline__ void dmma_m8n8k4(double (&c)[2], double a, double b) 
 __global__ void __launch_bounds__(kThreads, 2)
 ram_gemm_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count, int N, int qmin, int qmax,
                 const double* __restrict__ cq_all, const int32_t* __restrict__ phi, double* __restrict__ norms,
-                int ld_norms) {
+                int ld_norms, double* __restrict__ zout) {
   const int q = qmax - blockIdx.y;  // big periods first
   if (q < qmin) return;
   const int b0 = blockIdx.x * kGemmN;
@@ -199,6 +199,22 @@ ram_gemm_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count,
         }
       }
       __syncthreads();  // everyone is done with this buffer before the next iteration restages it
+    }
+    // float32-compat mode: the products t = H S_q themselves are kept (same layout as S) for ram_compat_kernel
+    if (zout != nullptr) {
+      double* Zq = zout + s_offset(q, qmin, ldS) + b0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int m = m0 + wm * 32 + i * 8 + lr;
+        if (m < q) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const int col = wn * 32 + j * 8 + 2 * lc;
+            if (b0 + col < b_count) Zq[(size_t)m * ldS + col] = acc[i][j][0];
+            if (b0 + col + 1 < b_count) Zq[(size_t)m * ldS + col + 1] = acc[i][j][1];
+          }
+        }
+      }
     }
     // epilogue of this row block: cnt-weighted squares, accumulated per column
 #pragma unroll
@@ -477,6 +493,150 @@ ram_umma_tf32_kernel(const double* __restrict__ S, int ldS, int b_first, int b_c
   if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(kUN));
 }
 
+// ------------------------------------------------------------------------------------------
+// float32-compat mode: the reference's OWN numbers.  RamanujanPeriods.project stores every projected row in a
+// float32 array (RamanujanPeriods.py:127-130), find_periods sums the q rows in float32 (np.sum over axis 0:
+// sequential in the row index) and then sums the squares of the N float32 samples with numpy's pairwise summation
+// (:77-78).  That rounding noise (1e-7 .. 2e-6 relative) is the distance between the reference and the fp64 value
+// of the same formula; this kernel reproduces it operation by operation:
+//   y_i      = <x, r_i>                       fp64  (t_i / phi(q), t = H S_q from the DMMA kernel)
+//   p_i[m]   = float32(y_i * r_i[m])          r_i[m] = c_q((m - i) mod q) / phi(q), fp64 product rounded once
+//   out[m]   = ((p_0[m] + p_1[m]) + p_2[m]) + ...   float32, in row order   (out[n] depends on n mod q only)
+//   norms[q] = pairwise_float32(out[n mod q]^2, n < N)   numpy's 8-way unrolled blocks of <= 128, split in halves
+// What cannot be reproduced is the 1e-13 noise of the reference's sum of complex exponentials in Cq (:142-144): it
+// moves a float32 rounding once in ~1e6 products.
+// ------------------------------------------------------------------------------------------
+constexpr int kCompatWin = 4;   // windows per CTA
+constexpr int kCompatLeafCap = 512;   // leaves of the pairwise summation (N <= 32768)
+enum { kModeF64 = 0, kModeTf32 = 1, kModeF32Compat = 2 };
+
+// leaves of numpy's pairwise summation of n elements (blocks of <= 128; halves rounded down to a multiple of 8)
+__device__ int pairwise_leaves(int n, int* off, int* len, int cap) {
+  int stack_o[32], stack_n[32], sp = 0, cnt = 0;
+  stack_o[0] = 0;
+  stack_n[0] = n;
+  sp = 1;
+  while (sp > 0) {
+    --sp;
+    const int o = stack_o[sp], m = stack_n[sp];
+    if (m <= 128) {
+      if (cnt < cap) {
+        off[cnt] = o;
+        len[cnt] = m;
+      }
+      ++cnt;
+    } else {
+      int n2 = m / 2;
+      n2 -= n2 % 8;
+      stack_o[sp] = o + n2;   // right half is pushed first: the left half is visited first (in order)
+      stack_n[sp] = m - n2;
+      ++sp;
+      stack_o[sp] = o;
+      stack_n[sp] = n2;
+      ++sp;
+    }
+  }
+  return cnt;
+}
+
+// recombination of the leaf sums in recursion order: result = sum(left) + sum(right), float32
+__device__ float pairwise_combine(int n, const float* leaf, int& next) {
+  if (n <= 128) return leaf[next++];
+  int n2 = n / 2;
+  n2 -= n2 % 8;
+  const float a = pairwise_combine(n2, leaf, next);
+  const float b = pairwise_combine(n - n2, leaf, next);
+  return __fadd_rn(a, b);
+}
+
+__global__ void __launch_bounds__(kThreads, 2)
+ram_compat_kernel(const double* __restrict__ Z, int ldS, int b_first, int b_count, int N, int qmin, int qmax,
+                  const double* __restrict__ cq_all, const int32_t* __restrict__ phi, double* __restrict__ norms,
+                  int ld_norms) {
+  const int q = qmax - blockIdx.y;
+  if (q < qmin) return;
+  const int w0 = blockIdx.x * kCompatWin;
+  if (w0 >= b_count) return;
+  const int qe = (q + 1) & ~1;
+  double* rtab = reinterpret_cast<double*>(pp_smem);          // [q]  c_q(d) / phi(q)
+  double* y = rtab + qe;                                        // [kCompatWin][q]
+  float* o32 = reinterpret_cast<float*>(y + kCompatWin * qe);   // [kCompatWin][q]
+  float* leaf = o32 + kCompatWin * qe;                          // [kCompatWin][nleaf_cap]
+  constexpr int kLeafCap = kCompatLeafCap;
+  int* loff = reinterpret_cast<int*>(leaf + kCompatWin * kLeafCap);
+  int* llen = loff + kLeafCap;
+  __shared__ int s_nleaf;
+  const int tid = threadIdx.x;
+  const double ph = (double)phi[q];
+  const double* cq = cq_all + cq_offset(q);
+  const double* Zq = Z + s_offset(q, qmin, ldS) + w0;
+  for (int i = tid; i < q; i += kThreads) rtab[i] = cq[i] / ph;          // row / max(row): c_q / phi(q)
+  for (int idx = tid; idx < kCompatWin * q; idx += kThreads) {
+    const int w = idx / q, i = idx - w * q;
+    y[w * qe + i] = (w0 + w < b_count) ? Zq[(size_t)i * ldS + w] / ph : 0.0;   // <x, r_i> = t_i / phi(q)
+  }
+  if (tid == 0) s_nleaf = pairwise_leaves(N, loff, llen, kLeafCap);
+  __syncthreads();
+  // out[m] = sequential float32 sum over the rows i of float32(y_i * r_i[m])
+  for (int idx = tid; idx < kCompatWin * q; idx += kThreads) {
+    const int w = idx / q, m = idx - w * q;
+    const double* yw = y + w * qe;
+    int d = m;                                   // (m - i) mod q
+    float acc = __double2float_rn(yw[0] * rtab[d]);
+    for (int i = 1; i < q; ++i) {
+      d = d == 0 ? q - 1 : d - 1;
+      acc = __fadd_rn(acc, __double2float_rn(yw[i] * rtab[d]));
+    }
+    o32[w * qe + m] = acc;
+  }
+  __syncthreads();
+  // squares, pairwise: every leaf keeps numpy's 8 strided partial sums; one thread per (window, leaf, lane-of-8)
+  const int nleaf = min(s_nleaf, kLeafCap);
+  for (int idx = tid; idx < kCompatWin * nleaf * 8; idx += kThreads) {
+    const int j = idx & 7, l = (idx >> 3) % nleaf, w = idx / (8 * nleaf);
+    const float* ow = o32 + w * qe;
+    const int o = loff[l], n = llen[l];
+    float r = 0.f;
+    if (n >= 8) {
+      int pos = (o + j) % q;
+      const int step = 8 % q;
+      float v = ow[pos];
+      r = __fmul_rn(v, v);
+      for (int i = 8; i < n - (n % 8); i += 8) {
+        pos += step;
+        if (pos >= q) pos -= q;
+        v = ow[pos];
+        r = __fadd_rn(r, __fmul_rn(v, v));
+      }
+    }
+    // the 8 partial sums of a leaf meet through shuffles: lanes j .. j+7 of the same leaf are adjacent
+    const float r1 = __fadd_rn(r, __shfl_xor_sync(0xffffffffu, r, 1));      // (r0+r1), (r2+r3), ...
+    const float r2 = __fadd_rn(r1, __shfl_xor_sync(0xffffffffu, r1, 2));    // ((r0+r1)+(r2+r3)), ...
+    float res = __fadd_rn(r2, __shfl_xor_sync(0xffffffffu, r2, 4));
+    if (j == 0) {
+      if (n < 8) {
+        res = 0.f;
+        for (int i = 0; i < n; ++i) {
+          const float v = ow[(o + i) % q];
+          res = __fadd_rn(res, __fmul_rn(v, v));
+        }
+      } else {
+        for (int i = n - (n % 8); i < n; ++i) {
+          const float v = ow[(o + i) % q];
+          res = __fadd_rn(res, __fmul_rn(v, v));
+        }
+      }
+      leaf[w * kLeafCap + l] = res;
+    }
+  }
+  __syncthreads();
+  if (tid < kCompatWin && w0 + tid < b_count) {
+    int next = 0;
+    const float total = __fadd_rn(0.f, pairwise_combine(N, leaf + tid * kLeafCap, next));
+    norms[(size_t)(b_first + w0 + tid) * ld_norms + q] = (double)total;
+  }
+}
+
 // periods whose norm exceeds thresh * |max norm|, ascending (RamanujanPeriods.py:97-101); one warp per window
 __global__ void select_kernel(const double* __restrict__ norms, int B, int ld_norms, int qlen, double thresh, int kmax,
                               int32_t* __restrict__ periods, int32_t* __restrict__ nper) {
@@ -515,13 +675,21 @@ size_t pp_ramanujan_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32
   return 4096 + 256 + (cq_offset(qmax + 1) + 2) * 8 + rows * ldS * 8;
 }
 
+// float32-compat mode keeps the products H S_q of a tile beside its folds: twice the fold storage
+size_t pp_ramanujan_f32compat_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32_t tile_windows) {
+  const size_t ldS = ((size_t)tile_windows + 3) & ~(size_t)3;
+  const size_t rows = (size_t)qmax * (qmax + 1) / 2 - (size_t)qmin * (qmin - 1) / 2;
+  return pp_ramanujan_workspace_bytes(N, qmin, qmax, tile_windows) + 256 + rows * ldS * 8;
+}
+
 // norms[b, q] for q in [qmin, qmax] (other entries untouched; the caller zero-fills, RamanujanPeriods.py:71).
 // mu / phi: device int32 tables for 0..table_qmax.  Windows are processed in tiles of `tile_windows`
 // (workspace holds the folds of one tile).
 static int ramanujan_norms_impl(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
                                 const int32_t* mu, const int32_t* phi, int32_t table_qmax, int32_t tile_windows,
                                 double* norms, int32_t ld_norms, void* workspace, size_t workspace_bytes, void* stream,
-                                bool tf32) {
+                                int mode) {
+  const bool tf32 = mode == kModeTf32, compat = mode == kModeF32Compat;
   if (B == 0) return 0;  // empty batch: nothing to validate or launch
   if (x == nullptr || norms == nullptr || B < 0 || N < 2 || ldx < 1) return fail(-1, "bad window arguments%s");
   if (qmin < 1 || qmax < qmin || qmax > N) return fail(-1, "need 1 <= qmin <= qmax <= N%s");
@@ -537,7 +705,9 @@ static int ramanujan_norms_impl(const double* x, int64_t ldx, int32_t B, int32_t
   double* cq = carve(workspace, workspace_bytes, off, (cq_offset(qmax + 1) + 2) * 8);
   double* S = carve(workspace, workspace_bytes, off, rows * (size_t)ldS * 8);
   int* next_unit = reinterpret_cast<int*>(carve(workspace, workspace_bytes, off, 256));
-  if (!cq || !S || !next_unit) return fail(-3, "workspace too small (see pp_ramanujan_workspace_bytes)%s");
+  double* Z = compat ? carve(workspace, workspace_bytes, off, rows * (size_t)ldS * 8) : nullptr;
+  if (!cq || !S || !next_unit || (compat && !Z))
+    return fail(-3, "workspace too small (see pp_ramanujan_workspace_bytes / pp_ramanujan_f32compat_workspace_bytes)%s");
   cq_kernel<<<qmax - qmin + 1, 128, 0, st>>>(qmin, qmax, mu, phi, cq);
   const size_t fold_smem = (size_t)kFoldWin * ((N + 1) & ~1) * 8;
   if (int rc = prep_kernel(fold_all_kernel, fold_smem, f)) return rc;
@@ -547,6 +717,13 @@ static int ramanujan_norms_impl(const double* x, int64_t ldx, int32_t B, int32_t
   upl.qpad = (qmax + 3 + 31) & ~31;
   if (tf32)
     if (int rc = prep_kernel(ram_umma_tf32_kernel, upl.bytes(), f)) return rc;
+  const size_t qe_max = (size_t)((qmax + 1) & ~1);
+  const size_t compat_smem = (1 + kCompatWin) * qe_max * 8 + kCompatWin * qe_max * 4 +
+                             (size_t)kCompatWin * kCompatLeafCap * 4 + 2 * (size_t)kCompatLeafCap * 4;
+  if (compat) {
+    if ((N + 63) / 64 > kCompatLeafCap) return fail(-1, "float32-compat mode supports N <= 32768%s");
+    if (int rc = prep_kernel(ram_compat_kernel, compat_smem, f)) return rc;
+  }
   for (int b_first = 0; b_first < B; b_first += tile_windows) {
     const int b_count = (B - b_first < tile_windows) ? (B - b_first) : tile_windows;
     int fgrid = (b_count + kFoldWin - 1) / kFoldWin;
@@ -558,9 +735,15 @@ static int ramanujan_norms_impl(const double* x, int64_t ldx, int32_t B, int32_t
       if (int rc = check_cuda(cudaMemsetAsync(next_unit, 0, sizeof(int), st), "cudaMemsetAsync")) return rc;
       ram_umma_tf32_kernel<<<units < f.sm_count ? units : f.sm_count, kThreads, upl.bytes(), st>>>(
           S, ldS, b_first, b_count, N, qmin, qmax, cq, phi, norms, ld_norms, next_unit);
-    } else
+    } else {
       ram_gemm_kernel<<<grid, kThreads, gemm_smem, st>>>(S, ldS, b_first, b_count, N, qmin, qmax, cq, phi, norms,
-                                                         ld_norms);
+                                                         ld_norms, Z);
+      if (compat) {
+        dim3 cgrid((b_count + kCompatWin - 1) / kCompatWin, qmax - qmin + 1);
+        ram_compat_kernel<<<cgrid, kThreads, compat_smem, st>>>(Z, ldS, b_first, b_count, N, qmin, qmax, cq, phi, norms,
+                                                                ld_norms);
+      }
+    }
   }
   return check_cuda(cudaGetLastError(), "ramanujan kernels launch");
 }
@@ -569,14 +752,22 @@ int pp_ramanujan_norms(const double* x, int64_t ldx, int32_t B, int32_t N, int32
                        const int32_t* mu, const int32_t* phi, int32_t table_qmax, int32_t tile_windows,
                        double* norms, int32_t ld_norms, void* workspace, size_t workspace_bytes, void* stream) {
   return ramanujan_norms_impl(x, ldx, B, N, qmin, qmax, mu, phi, table_qmax, tile_windows, norms, ld_norms, workspace,
-                              workspace_bytes, stream, false);
+                              workspace_bytes, stream, kModeF64);
 }
 
 int pp_ramanujan_norms_tf32(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
                             const int32_t* mu, const int32_t* phi, int32_t table_qmax, int32_t tile_windows,
                             double* norms, int32_t ld_norms, void* workspace, size_t workspace_bytes, void* stream) {
   return ramanujan_norms_impl(x, ldx, B, N, qmin, qmax, mu, phi, table_qmax, tile_windows, norms, ld_norms, workspace,
-                              workspace_bytes, stream, true);
+                              workspace_bytes, stream, kModeTf32);
+}
+
+int pp_ramanujan_norms_f32compat(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
+                                 const int32_t* mu, const int32_t* phi, int32_t table_qmax, int32_t tile_windows,
+                                 double* norms, int32_t ld_norms, void* workspace, size_t workspace_bytes,
+                                 void* stream) {
+  return ramanujan_norms_impl(x, ldx, B, N, qmin, qmax, mu, phi, table_qmax, tile_windows, norms, ld_norms, workspace,
+                              workspace_bytes, stream, kModeF32Compat);
 }
 
 // periods[b, 0:nper[b]] = ascending q in [0, qlen) with norms[b, q] / |max_q norms[b, q]| > thresh

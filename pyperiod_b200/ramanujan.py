@@ -22,11 +22,14 @@ TILE_WINDOWS = 2048  # windows whose folds are held at once (7.5 MB per window a
 
 class RamanujanPeriods(QOPeriods):
     def __init__(self, basis_type="natural", device=None, precision="fp64"):
-        """precision: "fp64" (FP64 tensor cores, default) or "tf32" (split TF32 tensor-core contraction, fp32
-        accumulation: norms to ~1e-5 relative; not part of the reference API)."""
+        """precision (not part of the reference API): "fp64" (FP64 tensor cores, default: the fp64 value of the
+        reference's formula), "tf32" (split TF32 contraction on the tcgen05 tensor cores, fp32 accumulation: norms to
+        ~1e-5 relative), or "f32_compat" (the reference's own float32 storage and summation order,
+        RamanujanPeriods.py:127 and :77-78, reproduced operation by operation: norms equal the reference's to the
+        last float32 bit)."""
         super().__init__(basis_type, False, False, device=device)
-        if precision not in ("fp64", "tf32"):
-            raise ValueError("precision must be 'fp64' or 'tf32'")
+        if precision not in ("fp64", "tf32", "f32_compat"):
+            raise ValueError("precision must be 'fp64', 'tf32' or 'f32_compat'")
         self._precision = precision
         self._verbose = None
         self._k = 0
@@ -36,10 +39,13 @@ class RamanujanPeriods(QOPeriods):
         lib = _lib.load()
         tb = get_tables(max_length)
         mu, phi = tb.mu_device(w.device), tb.phi_device(w.device)
-        tile = min(TILE_WINDOWS, max(4, w.b))
-        ws = workspace_for(w.device, lib.pp_ramanujan_workspace_bytes, w.n, min_length, max_length, tile)
+        compat = self._precision == "f32_compat"
+        tile = min(TILE_WINDOWS // 2 if compat else TILE_WINDOWS, max(4, w.b))
+        ws = workspace_for(w.device, lib.pp_ramanujan_f32compat_workspace_bytes if compat
+                           else lib.pp_ramanujan_workspace_bytes, w.n, min_length, max_length, tile)
         norms = torch.zeros((w.b, max_length + 1), dtype=torch.float64, device=w.device)
-        fn = lib.pp_ramanujan_norms_tf32 if self._precision == "tf32" else lib.pp_ramanujan_norms
+        fn = {"fp64": lib.pp_ramanujan_norms, "tf32": lib.pp_ramanujan_norms_tf32,
+              "f32_compat": lib.pp_ramanujan_norms_f32compat}[self._precision]
         call(fn, "pp_ramanujan_norms", w.device, ptr(w.tensor), w.ldx, w.b, w.n, int(min_length), int(max_length),
              ptr(mu), ptr(phi), tb.pmax, tile, ptr(norms), max_length + 1, ptr(ws), ws.numel(), stream_ptr(w.device))
         return norms

@@ -37,6 +37,33 @@ def test_norms_vs_reference_float32_limited(R):
         np.testing.assert_allclose(nb[b], g2[f"ram_{b}_norms"], rtol=2e-6)
 
 
+def test_f32_compat_reproduces_the_reference_numbers(R):
+    """precision='f32_compat': float32 storage (RamanujanPeriods.py:127), sequential float32 row sum and numpy's
+    pairwise sum of squares (:77-78) reproduced on the device.  Against the reference-generated fixtures the norms are
+    equal to the last float32 bit on almost every period (fp64 path: 2e-7 .. 2e-6 away)."""
+    g = load_golden("readme_qo_ram")
+    c = synth.readme_signal(0)
+    got = R(precision="f32_compat").find_periods(c, 2, 120)
+    ref = g["ram_norms"]
+    assert got.shape == ref.shape
+    np.testing.assert_allclose(got, ref, rtol=3e-8)
+    assert np.sum(got == ref) >= 0.95 * len(ref), int(np.sum(got == ref))
+    g2 = load_golden("qo_ram_synth")
+    xb = synth.synth_batch(2, 1024, 50_000)
+    nb = R(precision="f32_compat").find_periods(xb)
+    for b in range(2):
+        ref = g2[f"ram_{b}_norms"]
+        np.testing.assert_allclose(nb[b], ref, rtol=3e-8)
+        assert np.sum(nb[b] == ref) >= 0.9 * len(ref), int(np.sum(nb[b] == ref))
+    # ragged tile (5 windows, odd N) against the oracle's float32 emulation
+    xr = synth.synth_batch(5, 777, 31)
+    nr = R(precision="f32_compat").find_periods(xr, 2, 200)
+    for b in range(5):
+        want = oram.find_periods_f32_exact_cq(xr[b], 2, 200)
+        np.testing.assert_allclose(nr[b], want, rtol=3e-8)
+        assert np.sum(nr[b] == want) >= 0.9 * len(want)
+
+
 def test_batch_tiles_and_odd_sizes(R):
     xb = synth.synth_batch(7, 600, 123)          # 7 windows: partial 4-window fold group and partial GEMM tile
     nb = R().find_periods(xb, 3, 200)
