@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 3
+#define PP_ABI_VERSION 4
 
 /* sweep metrics */
 #define PP_METRIC_NORM 0   /* ||proj_p|| / sqrt(N)                 Periods.py:221-241, 507-508 */
@@ -262,7 +262,7 @@ int pp_qo_get_periods(int32_t B, int32_t kmax, int32_t tmax, int32_t rmax, const
                       int32_t *status, void *stream);
 
 /* ---- QOPeriods.get_best_period_orthogonal / eq_3 (QOPeriods.py:1122-1232): Muresan's equation-3 finder ----
- * raw[b, q] = max(eq_3(x_b, q), 0) for q in [1, max_p) (raw[b, 0] = 0), with eq_3 evaluated as
+ * raw[b, q] = eq_3(x_b, q) for q in [1, max_p) (raw[b, 0] = 0; the finder uses max(raw, 0)), with eq_3 evaluated as
  * (q / N) * (energy of the residue-class fold - 2 * autocorrelation at lag (N // q) * q) -- the same quantity as the
  * reference's sum of autocorrelations at multiples of q (:1123-1150);  pows[b, q] = raw minus the powers of the
  * proper divisors (a Moebius inversion of the reference's sequential subtraction, :1209-1217), negatives clamped,
@@ -275,10 +275,18 @@ int pp_muresan_powers(const double *x, int64_t ldx, int32_t B, int32_t N, int32_
  * norms[b, q] = sum_n (sum_i <x, r_i> r_i)[n]^2 over the q-row Ramanujan dictionary of period q,
  * evaluated in fp64 as the dense contraction (q / phi(q)^2) * circ(c_q) * S_q on the FP64 tensor
  * cores (DMMA), S_q = residue-class fold of the window, followed by the count-weighted column
- * norms.  (The reference stores its projection in float32, :127, so its own norms carry ~1e-7
- * relative noise; this path is the fp64 value.)  mu / phi: device int32 tables (Moebius, totient)
- * for 0..table_qmax.  Only columns qmin..qmax of norms[B, ld_norms] are written. */
-size_t pp_ramanujan_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32_t tile_windows);
+ * norms.  One fused kernel: a CTA folds 16 windows at period q into shared memory and contracts in
+ * place; the folds never reach HBM (traffic: the windows once per L2 group, one norm per period).
+ * (The reference stores its projection in float32, :127, so its own norms carry ~1e-7
+ * relative noise; this path is the fp64 value -- see pp_ramanujan_norms_f32compat for the reference's
+ * own numbers.)  mu / phi: device int32 tables (Moebius, totient) for 0..table_qmax.  Only columns
+ * qmin..qmax of norms[B, ld_norms] are written.  tile_windows: for PP_RAM_FP64 the number of windows
+ * whose samples should stay L2-resident while every period passes over them (1024 = 32 MB at N = 4096);
+ * for the other modes the number of windows whose folds the workspace holds at once. */
+#define PP_RAM_FP64 0
+#define PP_RAM_TF32 1
+#define PP_RAM_F32COMPAT 2
+size_t pp_ramanujan_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32_t tile_windows, int32_t mode);
 int pp_ramanujan_norms(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
                        const int32_t *mu, const int32_t *phi, int32_t table_qmax, int32_t tile_windows,
                        double *norms, int32_t ld_norms, void *workspace, size_t workspace_bytes, void *stream);
@@ -296,9 +304,8 @@ int pp_ramanujan_norms_tf32(const double *x, int64_t ldx, int32_t B, int32_t N, 
  * reproduces that arithmetic operation by operation on top of the fp64 tensor-core products (<x, r_i> in fp64, each
  * product rounded to float32 once, sequential float32 row sum, numpy's 8-lane / 128-block pairwise tree), so the
  * norms equal the reference's to the last float32 bit except where the reference's own 1e-13 noise in Cq
- * (:142-144, a sum of complex exponentials) moves a rounding.  Workspace: pp_ramanujan_f32compat_workspace_bytes
- * (the products H S_q of a tile are kept beside its folds).  N <= 32768. */
-size_t pp_ramanujan_f32compat_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32_t tile_windows);
+ * (:142-144, a sum of complex exponentials) moves a rounding.  Workspace: pp_ramanujan_workspace_bytes with
+ * PP_RAM_F32COMPAT (the products H S_q of a tile are kept beside its folds).  N <= 32768. */
 int pp_ramanujan_norms_f32compat(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t qmin, int32_t qmax,
                                  const int32_t *mu, const int32_t *phi, int32_t table_qmax, int32_t tile_windows,
                                  double *norms, int32_t ld_norms, void *workspace, size_t workspace_bytes,

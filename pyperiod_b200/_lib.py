@@ -12,12 +12,13 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 # PYPERIOD_B200_LIB selects an alternative build of the same library (kernel tuning experiments)
 LIB_PATH = os.environ.get("PYPERIOD_B200_LIB") or os.path.join(HERE, "libpyperiod_b200.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 METRIC_NORM, METRIC_GAMMA, METRIC_MAXABS, METRIC_IMPOSED = 0, 1, 2, 3
 STATUS_OK, STATUS_NO_PERIOD, STATUS_OVERFLOW, STATUS_SINGULAR, STATUS_GUARD = 0, 1, 2, 3, 4
 STATUS_TOO_LARGE, STATUS_ZERO_INPUT = 5, 6
 BASIS_NATURAL, BASIS_RAMANUJAN = 0, 1
+RAM_FP64, RAM_TF32, RAM_F32COMPAT = 0, 1, 2
 ALGO_SWEEP, ALGO_MBEST, ALGO_S2L, ALGO_BCORR, ALGO_QO, ALGO_RAMANUJAN = 0, 1, 2, 3, 4, 5
 
 _p = C.c_void_p
@@ -54,10 +55,9 @@ SIGNATURES = {
     "pp_comm_destroy": (C.c_int, [_p]),
     "pp_gather": (C.c_int, [_p, _p, _p, _sz, _i32, _p]),
     "pp_microbench": (C.c_int, [_i32, _i32, _p]),
-    "pp_ramanujan_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
+    "pp_ramanujan_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32, _i32]),
     "pp_ramanujan_norms": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _p, _sz, _p]),
     "pp_ramanujan_norms_tf32": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _p, _sz, _p]),
-    "pp_ramanujan_f32compat_workspace_bytes": (_sz, [_i32, _i32, _i32, _i32]),
     "pp_ramanujan_norms_f32compat": (C.c_int, [_p, _i64, _i32, _i32, _i32, _i32, _p, _p, _i32, _i32, _p, _i32, _p, _sz,
                                               _p]),
     "pp_ramanujan_select": (C.c_int, [_p, _i32, _i32, _i32, _f64, _i32, _p, _p, _p]),

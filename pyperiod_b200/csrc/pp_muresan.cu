@@ -36,8 +36,12 @@ muresan_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int max_
   loader.init(bar);
   for (int b = blockIdx.x; b < B; b += gridDim.x) {
     loader.load(xs, x + (size_t)b * ldx, N);
-    if (tid == 0) raw[0] = 0.0;
-    // ---- raw[q] = max(eq_3(x, q), 0): one warp per period, lanes over residues, terms in increasing n
+    if (tid == 0) {
+      raw[0] = 0.0;
+      if (raw_out) raw_out[(size_t)b * max_p] = 0.0;
+    }
+    // ---- raw[q] = max(eq_3(x, q), 0) (raw_out keeps eq_3 itself, which the lag it leaves out can make negative):
+    //      one warp per period, lanes over residues, terms in increasing n
     for (int q = 1 + wid; q < max_p; q += kWarps) {
       double e = 0.0;
       for (int r = lane; r < q; r += 32) {
@@ -50,7 +54,11 @@ muresan_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int max_
       for (int n = lane; n < N - lag; n += 32) c = fma(xs[n], xs[n + lag], c);
       e = warp_sum(e);
       c = warp_sum(c);
-      if (lane == 0) raw[q] = fmax(((double)q / (double)N) * (e - 2.0 * c), 0.0);
+      if (lane == 0) {
+        const double v = ((double)q / (double)N) * (e - 2.0 * c);
+        raw[q] = fmax(v, 0.0);
+        if (raw_out) raw_out[(size_t)b * max_p + q] = v;
+      }
     }
     __syncthreads();
     // ---- pows[q] = sum_{d | q} mu(q / d) raw[d], clamp, normalise; arg-max (first maximum)
@@ -97,8 +105,6 @@ muresan_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int max_
       // :1226-1232: the strongest period, or 1 when every power is zero
       best_out[b] = arg > 0 ? arg : 1;
     }
-    if (raw_out)
-      for (int q = tid; q < max_p; q += kThreads) raw_out[(size_t)b * max_p + q] = raw[q];
     if (pows_out)
       for (int q = tid; q < max_p; q += kThreads) pows_out[(size_t)b * max_p + q] = pw[q];
     __syncthreads();

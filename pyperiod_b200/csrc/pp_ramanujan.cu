@@ -22,6 +22,8 @@
 
 namespace pp {
 
+enum { kModeF64 = PP_RAM_FP64, kModeTf32 = PP_RAM_TF32, kModeF32Compat = PP_RAM_F32COMPAT };
+
 // ------------------------------------------------------------------------------------------
 // dictionary: c_q(n) for all q in [0, qmax], concatenated at offset q (q - 1) / 2 (triangular layout)
 // ------------------------------------------------------------------------------------------
@@ -253,6 +255,200 @@ ram_gemm_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count,
     const double scale = (double)q / (ph * ph);  // C^T C = (q / phi^2) circ(c_q)
     const double t = ((red[tid] + red[kGemmN + tid]) + red[2 * kGemmN + tid]) + red[3 * kGemmN + tid];
     norms[(size_t)(b_first + b0 + tid) * ld_norms + q] = scale * scale * t;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Fused periodogram (the default fp64 path): fold and contraction in ONE kernel, the folds never leave the SM.
+//
+// Work unit = (period q, 16 windows).  The CTA folds the 16 windows at q straight from global memory (the
+// windows of a group stay in L2 while every q passes over them) into shared memory, S[l][w] (q x 16 doubles,
+// <= 175 KB at q = 1365), and contracts it with the circulant H[m][l] = c_q((l - m) mod q) on the FP64 tensor
+// cores.  HBM traffic is the window itself (N * 8 bytes) plus one norm per period; the 7.5 MB of folds per
+// window the two-kernel form wrote and re-read are gone, and so is the 15 GB fold buffer.
+//
+//  * 8-row fragments of H are dealt to the 8 warps round-robin (fragment f -> warp f mod 8), eight fragments
+//    per warp pass: the tensor-core work of a unit is balanced to one fragment whatever q is (a 128-row block
+//    tiling wastes up to 127 rows of every period).
+//  * A lane's H element for k-step k of a 32-row chunk is cq2[d + 4 k] with ONE running index d per fragment
+//    (cq2 = c_q tabulated over [0, q + 32): no wrap inside a chunk): an LDS with an immediate offset.
+//  * S rows are 16 doubles with the window slot XOR-swizzled by the row (g(l) = {0, 8, 4, 12}[l mod 4]): the
+//    B fragments (4 rows x 8 windows) and the fold's stores (8 rows x 4 windows) both take the minimum two
+//    wavefronts per 32 doubles.
+// ------------------------------------------------------------------------------------------
+constexpr int kFusedWin = 16;      // windows per unit (two 8-column B fragments)
+constexpr int kFusedFrags = 8;     // 8-row fragments of H per warp pass
+
+struct FusedPlan {
+  int qmax;
+  __host__ __device__ int srows() const { return (qmax + 31) & ~31; }
+  __host__ __device__ size_t off_cq2() const { return (size_t)srows() * kFusedWin * 8; }
+  __host__ __device__ size_t off_red() const { return off_cq2() + (size_t)((qmax + 32 + 1) & ~1) * 8; }
+  __host__ __device__ size_t bytes() const { return off_red() + (size_t)kWarps * kFusedWin * 8 + 16; }
+};
+
+__device__ __forceinline__ int fused_swz(int l) { return ((l & 1) << 3) | ((l & 2) << 1); }
+
+template <bool FULL>
+__device__ __forceinline__ void fused_pass(const double* __restrict__ Ssm, const double* __restrict__ cq2, int q,
+                                           int frag0, int nfr, int Mrows, int r0, double (&colacc)[2][2]) {
+  const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
+  // running index of this lane's H element per fragment: d = (l - m) mod q at l = lc
+  int d[kFusedFrags];
+  double cnt[kFusedFrags];
+#pragma unroll
+  for (int i = 0; i < kFusedFrags; ++i) {
+    const int m = 8 * (frag0 + 8 * i) + lr;   // fragments of this warp are 8 apart
+    const bool live = (FULL || i < nfr) && m < q;
+    int v = lc + q - m;                       // in (0, q + 3] for m < q
+    if (v >= q) v -= q;
+    d[i] = live ? v : 0;
+    cnt[i] = live ? (double)(Mrows + (m < r0 ? 1 : 0)) : 0.0;
+  }
+  double acc[kFusedFrags][2][2];
+#pragma unroll
+  for (int i = 0; i < kFusedFrags; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
+  const int g = fused_swz(lc);
+  const double* bptr = Ssm + lc * kFusedWin;
+  const int slot0 = lr ^ g, slot1 = (8 + lr) ^ g;
+  for (int l0 = 0; l0 < q; l0 += 32) {
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      const double b0 = bptr[(l0 + 4 * k4) * kFusedWin + slot0];
+      const double b1 = bptr[(l0 + 4 * k4) * kFusedWin + slot1];
+#pragma unroll
+      for (int i = 0; i < kFusedFrags; ++i) {
+        if (FULL || i < nfr) {
+          const double a = cq2[d[i] + 4 * k4];
+          dmma_m8n8k4(acc[i][0], a, b0);
+          dmma_m8n8k4(acc[i][1], a, b1);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kFusedFrags; ++i) {
+      d[i] += 32;
+      if (d[i] >= q) {
+        d[i] -= q;
+        if (d[i] >= q) d[i] %= q;   // q < 32 only
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < kFusedFrags; ++i) {
+    if (FULL || i < nfr) {
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        colacc[n][0] = fma(cnt[i] * acc[i][n][0], acc[i][n][0], colacc[n][0]);
+        colacc[n][1] = fma(cnt[i] * acc[i][n][1], acc[i][n][1], colacc[n][1]);
+      }
+    }
+  }
+}
+
+// persistent grid (one CTA per SM); units handed out by a global counter: window groups outermost (a group's
+// windows stay in L2), periods descending inside a group (long units first), 16-window tiles innermost.
+__global__ void __launch_bounds__(kThreads, 1)
+ram_fused_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int qmin, int qmax, int group_windows,
+                 const double* __restrict__ cq_all, const int32_t* __restrict__ phi, double* __restrict__ norms,
+                 int ld_norms, int* __restrict__ next_unit) {
+  FusedPlan pl;
+  pl.qmax = qmax;
+  double* Ssm = reinterpret_cast<double*>(pp_smem);
+  double* cq2 = reinterpret_cast<double*>(pp_smem + pl.off_cq2());
+  double* red = reinterpret_cast<double*>(pp_smem + pl.off_red());
+  int* unit_slot = reinterpret_cast<int*>(red + kWarps * kFusedWin);
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  const int nq = qmax - qmin + 1;
+  const int tiles_per_group = group_windows / kFusedWin;
+  const int ngroups = (B + group_windows - 1) / group_windows;
+  const long long per_group = (long long)nq * tiles_per_group;
+  const long long nunits = per_group * ngroups;
+  int q_tab = 0;   // period whose table is in cq2
+  for (;;) {
+    if (tid == 0) *unit_slot = atomicAdd(next_unit, 1);
+    __syncthreads();   // also: every warp is done with S, cq2 and red of the previous unit
+    const long long u = *unit_slot;
+    if (u >= nunits) break;
+    const int grp = (int)(u / per_group);
+    const int rem = (int)(u - (long long)grp * per_group);
+    const int q = qmax - rem / tiles_per_group;
+    const int w0 = grp * group_windows + (rem % tiles_per_group) * kFusedWin;
+    if (w0 >= B) {           // tail of the last group (uniform over the CTA)
+      __syncthreads();       // everyone has read the unit before thread 0 draws the next one
+      continue;
+    }
+    const int Mrows = N / q, r0 = N - Mrows * q;
+    if (q != q_tab) {
+      const double* cq = cq_all + cq_offset(q);
+      for (int i = tid; i < q + 32; i += kThreads) cq2[i] = cq[i >= q ? (i - q) % q : i];
+      q_tab = q;
+    }
+    // ---- fold: S[m][w] = sum_j x[w][j q + m].  A warp step covers 8 residues x 4 windows (64 contiguous bytes
+    //      per window); four partial sums per lane (rows j mod 4) keep four loads in flight and meet in a fixed order.
+    {
+      const int mi = lane & 7, wi = lane >> 3;
+      const int nmb = (q + 7) >> 3;
+      for (int item = wid; item < nmb * 4; item += kWarps) {
+        const int mb = item >> 2, wb = item & 3;
+        const int m = 8 * mb + mi, w = 4 * wb + wi;
+        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+        if (m < q && w0 + w < B) {
+          const double* src = x + (size_t)(w0 + w) * ldx + m;
+          const int terms = Mrows + (m < r0 ? 1 : 0);
+          int j = 0;
+          for (; j + 4 <= terms; j += 4) {
+            s0 += __ldg(src + (size_t)j * q);
+            s1 += __ldg(src + (size_t)(j + 1) * q);
+            s2 += __ldg(src + (size_t)(j + 2) * q);
+            s3 += __ldg(src + (size_t)(j + 3) * q);
+          }
+          if (j < terms) s0 += __ldg(src + (size_t)j * q);
+          if (j + 1 < terms) s1 += __ldg(src + (size_t)(j + 1) * q);
+          if (j + 2 < terms) s2 += __ldg(src + (size_t)(j + 2) * q);
+        }
+        if (m < q) Ssm[m * kFusedWin + (w ^ fused_swz(m))] = (s0 + s1) + (s2 + s3);
+      }
+      // rows q .. round-up to the k-chunk: zero (their H elements are finite table entries)
+      const int qr = (q + 31) & ~31;
+      for (int i = q * kFusedWin + tid; i < qr * kFusedWin; i += kThreads) Ssm[i] = 0.0;
+    }
+    __syncthreads();
+    // ---- contraction: warp `wid` owns fragments wid, wid + 8, ... (8 rows each), eight per pass
+    double colacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    const int nfrag = (q + 7) >> 3;
+    for (int f0 = wid; f0 < nfrag; f0 += 8 * kFusedFrags) {
+      const int nfr = min(kFusedFrags, (nfrag - f0 + 7) >> 3);
+      if (nfr == kFusedFrags) fused_pass<true>(Ssm, cq2, q, f0, nfr, Mrows, r0, colacc);
+      else fused_pass<false>(Ssm, cq2, q, f0, nfr, Mrows, r0, colacc);
+    }
+    // column sums: over the 8 row-lanes of a fragment, then over the warps in a fixed order
+#pragma unroll
+    for (int n = 0; n < 2; ++n)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = colacc[n][e];
+        v += __shfl_xor_sync(0xffffffffu, v, 4);
+        v += __shfl_xor_sync(0xffffffffu, v, 8);
+        v += __shfl_xor_sync(0xffffffffu, v, 16);
+        colacc[n][e] = v;
+      }
+    if (lane < 4) {
+#pragma unroll
+      for (int n = 0; n < 2; ++n) {
+        red[wid * kFusedWin + n * 8 + 2 * lane] = colacc[n][0];
+        red[wid * kFusedWin + n * 8 + 2 * lane + 1] = colacc[n][1];
+      }
+    }
+    __syncthreads();
+    if (tid < kFusedWin && w0 + tid < B) {
+      const double ph = (double)phi[q];
+      const double scale = (double)q / (ph * ph);   // C^T C = (q / phi^2) circ(c_q)
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < kWarps; ++w) t += red[w * kFusedWin + tid];
+      norms[(size_t)(w0 + tid) * ld_norms + q] = scale * scale * t;
+    }
   }
 }
 
@@ -508,7 +704,6 @@ ram_umma_tf32_kernel(const double* __restrict__ S, int ldS, int b_first, int b_c
 // ------------------------------------------------------------------------------------------
 constexpr int kCompatWin = 4;   // windows per CTA
 constexpr int kCompatLeafCap = 512;   // leaves of the pairwise summation (N <= 32768)
-enum { kModeF64 = 0, kModeTf32 = 1, kModeF32Compat = 2 };
 
 // leaves of numpy's pairwise summation of n elements (blocks of <= 128; halves rounded down to a multiple of 8)
 __device__ int pairwise_leaves(int n, int* off, int* len, int cap) {
@@ -668,18 +863,16 @@ using namespace pp;
 
 extern "C" {
 
-size_t pp_ramanujan_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32_t tile_windows) {
+// mode: PP_RAM_FP64 (fused kernel: the dictionary table and a counter), PP_RAM_TF32 (folds of one tile),
+// PP_RAM_F32COMPAT (folds and products of one tile)
+size_t pp_ramanujan_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32_t tile_windows, int32_t mode) {
   (void)N;
   const size_t ldS = ((size_t)tile_windows + 3) & ~(size_t)3;
   const size_t rows = (size_t)qmax * (qmax + 1) / 2 - (size_t)qmin * (qmin - 1) / 2;
-  return 4096 + 256 + (cq_offset(qmax + 1) + 2) * 8 + rows * ldS * 8;
-}
-
-// float32-compat mode keeps the products H S_q of a tile beside its folds: twice the fold storage
-size_t pp_ramanujan_f32compat_workspace_bytes(int32_t N, int32_t qmin, int32_t qmax, int32_t tile_windows) {
-  const size_t ldS = ((size_t)tile_windows + 3) & ~(size_t)3;
-  const size_t rows = (size_t)qmax * (qmax + 1) / 2 - (size_t)qmin * (qmin - 1) / 2;
-  return pp_ramanujan_workspace_bytes(N, qmin, qmax, tile_windows) + 256 + rows * ldS * 8;
+  size_t bytes = 4096 + 256 + (cq_offset(qmax + 1) + 2) * 8;
+  if (mode == kModeTf32 || mode == kModeF32Compat) bytes += rows * ldS * 8;
+  if (mode == kModeF32Compat) bytes += 256 + rows * ldS * 8;
+  return bytes;
 }
 
 // norms[b, q] for q in [qmin, qmax] (other entries untouched; the caller zero-fills, RamanujanPeriods.py:71).
@@ -702,13 +895,28 @@ static int ramanujan_norms_impl(const double* x, int64_t ldx, int32_t B, int32_t
   const int ldS = (tile_windows + 3) & ~3;
   const size_t rows = (size_t)qmax * (qmax + 1) / 2 - (size_t)qmin * (qmin - 1) / 2;
   size_t off = 0;
+  const bool fused = mode == kModeF64;
   double* cq = carve(workspace, workspace_bytes, off, (cq_offset(qmax + 1) + 2) * 8);
-  double* S = carve(workspace, workspace_bytes, off, rows * (size_t)ldS * 8);
   int* next_unit = reinterpret_cast<int*>(carve(workspace, workspace_bytes, off, 256));
+  double* S = fused ? nullptr : carve(workspace, workspace_bytes, off, rows * (size_t)ldS * 8);
   double* Z = compat ? carve(workspace, workspace_bytes, off, rows * (size_t)ldS * 8) : nullptr;
-  if (!cq || !S || !next_unit || (compat && !Z))
-    return fail(-3, "workspace too small (see pp_ramanujan_workspace_bytes / pp_ramanujan_f32compat_workspace_bytes)%s");
+  if (!cq || !next_unit || (!fused && !S) || (compat && !Z))
+    return fail(-3, "workspace too small (see pp_ramanujan_workspace_bytes)%s");
   cq_kernel<<<qmax - qmin + 1, 128, 0, st>>>(qmin, qmax, mu, phi, cq);
+  if (fused) {
+    // one launch for the whole batch; tile_windows is the L2 group (windows re-read by every period)
+    FusedPlan pl;
+    pl.qmax = qmax;
+    if (int rc = prep_kernel(ram_fused_kernel, pl.bytes(), f)) return rc;
+    const int group = (tile_windows + kFusedWin - 1) / kFusedWin * kFusedWin;
+    const long long units = (long long)(qmax - qmin + 1) * (group / kFusedWin) * ((B + group - 1) / group);
+    if (units > 0x7fffffffLL) return fail(-1, "batch too large for one launch%s");
+    if (int rc = check_cuda(cudaMemsetAsync(next_unit, 0, sizeof(int), st), "cudaMemsetAsync")) return rc;
+    const int grid = units < f.sm_count ? (int)units : f.sm_count;
+    ram_fused_kernel<<<grid, kThreads, pl.bytes(), st>>>(x, ldx, B, N, qmin, qmax, group, cq, phi, norms, ld_norms,
+                                                         next_unit);
+    return check_cuda(cudaGetLastError(), "ram_fused_kernel launch");
+  }
   const size_t fold_smem = (size_t)kFoldWin * ((N + 1) & ~1) * 8;
   if (int rc = prep_kernel(fold_all_kernel, fold_smem, f)) return rc;
   const size_t gemm_smem = (size_t)(((qmax + 1) & ~1) + 2 * kGemmK * kLdB + 4 * kGemmN) * 8;

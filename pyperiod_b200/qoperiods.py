@@ -450,9 +450,8 @@ class QOPeriods(Periods):
         return out
 
     def eq_3(self, x, P):
-        """Equation 3 of Muresan & Parks for period P (QOPeriods.py:1123-1150); 1-D -> float, (B, N) -> (B,).  The
-        device returns max(eq_3, 0) (what the finder uses); eq_3 itself is a sum of squares up to the single lag it
-        leaves out, so negative values only occur at rounding level."""
+        """Equation 3 of Muresan & Parks for period P (QOPeriods.py:1123-1150); 1-D -> float, (B, N) -> (B,).  A sum
+        of squares minus the one lag it leaves out: it can be negative (the finder clamps it, :1210)."""
         w, raw, _, _, _ = self._muresan(x, int(P) + 1, False)
         out = _export(w, raw[:, int(P)].contiguous())
         return float(out[0]) if w.was_1d else out

@@ -17,7 +17,8 @@ from .periods import _export
 from .qoperiods import RMAX_FIRST, QOBatchResult, QOPeriods, qo_workspace
 from .tables import get_tables
 
-TILE_WINDOWS = 2048  # windows whose folds are held at once (7.5 MB per window at qmax = 1365)
+TILE_WINDOWS = 2048      # tf32 / f32_compat: windows whose folds are held at once (7.5 MB per window at qmax = 1365)
+L2_GROUP_WINDOWS = 1024  # fp64 (fused kernel): windows kept L2-resident while every period passes over them
 
 
 class RamanujanPeriods(QOPeriods):
@@ -39,10 +40,13 @@ class RamanujanPeriods(QOPeriods):
         lib = _lib.load()
         tb = get_tables(max_length)
         mu, phi = tb.mu_device(w.device), tb.phi_device(w.device)
-        compat = self._precision == "f32_compat"
-        tile = min(TILE_WINDOWS // 2 if compat else TILE_WINDOWS, max(4, w.b))
-        ws = workspace_for(w.device, lib.pp_ramanujan_f32compat_workspace_bytes if compat
-                           else lib.pp_ramanujan_workspace_bytes, w.n, min_length, max_length, tile)
+        mode = {"fp64": _lib.RAM_FP64, "tf32": _lib.RAM_TF32, "f32_compat": _lib.RAM_F32COMPAT}[self._precision]
+        # fp64: the fused kernel needs no fold storage; `tile` is the group of windows kept L2-resident.  The other
+        # modes hold the folds (and products) of one tile in the workspace (7.5 MB per window at qmax = 1365).
+        tile = {"fp64": L2_GROUP_WINDOWS, "tf32": TILE_WINDOWS, "f32_compat": TILE_WINDOWS // 2}[self._precision]
+        if mode != _lib.RAM_FP64:
+            tile = min(tile, max(4, w.b))
+        ws = workspace_for(w.device, lib.pp_ramanujan_workspace_bytes, w.n, min_length, max_length, tile, mode)
         norms = torch.zeros((w.b, max_length + 1), dtype=torch.float64, device=w.device)
         fn = {"fp64": lib.pp_ramanujan_norms, "tf32": lib.pp_ramanujan_norms_tf32,
               "f32_compat": lib.pp_ramanujan_norms_f32compat}[self._precision]
