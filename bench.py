@@ -548,7 +548,7 @@ def sec_ram(ctx: Ctx):
                         total, ms, ms_e, xh.shape[0], xh.numel() * 8,
                         nbytes_of(r2.periods, r2.norms, r2.n_periods, r2.dict_q, r2.dict_keep, r2.n_dict, r2.weights,
                                   r2.n_weights, r2.res, r2.status),
-                        "3 calls on a 1/32 slice of the batch", "periodogram: 3 per 2048-window tile; select 1; solve 1-2")
+                        "3 calls on a 1/32 slice of the batch", "periodogram 2 (dictionary table + fused fold/DMMA kernel for the whole batch); select 1; row count 1; solve 1-2")
     sec_n = sum(ms_n) / len(ms_n) * 1e-3
     flops = 2.0 * sum(q * q for q in range(2, qmax + 1)) * total / ctx.world
     st = r.status

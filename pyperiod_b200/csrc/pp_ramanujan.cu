@@ -261,22 +261,23 @@ ram_gemm_kernel(const double* __restrict__ S, int ldS, int b_first, int b_count,
 // ------------------------------------------------------------------------------------------
 // Fused periodogram (the default fp64 path): fold and contraction in ONE kernel, the folds never leave the SM.
 //
-// Work unit = (period q, 16 windows).  The CTA folds the 16 windows at q straight from global memory (the
-// windows of a group stay in L2 while every q passes over them) into shared memory, S[l][w] (q x 16 doubles,
-// <= 175 KB at q = 1365), and contracts it with the circulant H[m][l] = c_q((l - m) mod q) on the FP64 tensor
-// cores.  HBM traffic is the window itself (N * 8 bytes) plus one norm per period; the 7.5 MB of folds per
-// window the two-kernel form wrote and re-read are gone, and so is the 15 GB fold buffer.
+// Work unit = (period q, 8 windows).  The CTA folds the 8 windows at q straight from global memory (the windows
+// of a group stay in L2 while every q passes over them) into shared memory, S[l][w] (q x 8 doubles, <= 88 KB at
+// q = 1365), and contracts it with the circulant H[m][l] = c_q((l - m) mod q) on the FP64 tensor cores.  HBM
+// traffic is the window itself (N * 8 bytes) plus one norm per period; the 7.5 MB of folds per window that the
+// two-kernel form wrote and re-read are gone, and so is the 15 GB fold buffer.
 //
-//  * 8-row fragments of H are dealt to the 8 warps round-robin (fragment f -> warp f mod 8), eight fragments
+//  * Two CTAs per SM: the fold of a unit is a chain of L2 round trips (latency bound), the contraction is
+//    tensor-pipe bound; the co-resident CTA's contraction hides the other one's fold.
+//  * 8-row fragments of H are dealt to the 8 warps round-robin (fragment f -> warp f mod 8), up to eight fragments
 //    per warp pass: the tensor-core work of a unit is balanced to one fragment whatever q is (a 128-row block
-//    tiling wastes up to 127 rows of every period).
+//    tiling wastes up to 127 rows of every period).  The pass is compiled for every fragment count 1..8, so the
+//    inner loop carries no predicates.
 //  * A lane's H element for k-step k of a 32-row chunk is cq2[d + 4 k] with ONE running index d per fragment
 //    (cq2 = c_q tabulated over [0, q + 32): no wrap inside a chunk): an LDS with an immediate offset.
-//  * S rows are 16 doubles with the window slot XOR-swizzled by the row (g(l) = {0, 8, 4, 12}[l mod 4]): the
-//    B fragments (4 rows x 8 windows) and the fold's stores (8 rows x 4 windows) both take the minimum two
-//    wavefronts per 32 doubles.
+//  * S rows are 8 doubles: the B fragment (4 rows x 8 windows) is 256 contiguous bytes, the minimum two wavefronts.
 // ------------------------------------------------------------------------------------------
-constexpr int kFusedWin = 16;      // windows per unit (two 8-column B fragments)
+constexpr int kFusedWin = 8;       // windows per unit (one 8-column B fragment)
 constexpr int kFusedFrags = 8;     // 8-row fragments of H per warp pass
 
 struct FusedPlan {
@@ -287,46 +288,33 @@ struct FusedPlan {
   __host__ __device__ size_t bytes() const { return off_red() + (size_t)kWarps * kFusedWin * 8 + 16; }
 };
 
-__device__ __forceinline__ int fused_swz(int l) { return ((l & 1) << 3) | ((l & 2) << 1); }
-
-template <bool FULL>
+// One warp pass: NFR fragments (rows 8 (frag0 + 8 i) .. + 7, i < NFR) against all q rows of S.
+template <int NFR>
 __device__ __forceinline__ void fused_pass(const double* __restrict__ Ssm, const double* __restrict__ cq2, int q,
-                                           int frag0, int nfr, int Mrows, int r0, double (&colacc)[2][2]) {
+                                           int frag0, int Mrows, int r0, double (&colacc)[2]) {
   const int lane = threadIdx.x & 31, lr = lane >> 2, lc = lane & 3;
   // running index of this lane's H element per fragment: d = (l - m) mod q at l = lc
-  int d[kFusedFrags];
-  double cnt[kFusedFrags];
+  int d[NFR];
 #pragma unroll
-  for (int i = 0; i < kFusedFrags; ++i) {
+  for (int i = 0; i < NFR; ++i) {
     const int m = 8 * (frag0 + 8 * i) + lr;   // fragments of this warp are 8 apart
-    const bool live = (FULL || i < nfr) && m < q;
     int v = lc + q - m;                       // in (0, q + 3] for m < q
     if (v >= q) v -= q;
-    d[i] = live ? v : 0;
-    cnt[i] = live ? (double)(Mrows + (m < r0 ? 1 : 0)) : 0.0;
+    d[i] = m < q ? v : 0;                     // rows past q (last fragment): any finite table entry, weight 0 below
   }
-  double acc[kFusedFrags][2][2];
+  double acc[NFR][2];
 #pragma unroll
-  for (int i = 0; i < kFusedFrags; ++i) acc[i][0][0] = acc[i][0][1] = acc[i][1][0] = acc[i][1][1] = 0.0;
-  const int g = fused_swz(lc);
-  const double* bptr = Ssm + lc * kFusedWin;
-  const int slot0 = lr ^ g, slot1 = (8 + lr) ^ g;
+  for (int i = 0; i < NFR; ++i) acc[i][0] = acc[i][1] = 0.0;
+  const double* bptr = Ssm + lc * kFusedWin + lr;
   for (int l0 = 0; l0 < q; l0 += 32) {
 #pragma unroll
     for (int k4 = 0; k4 < 8; ++k4) {
-      const double b0 = bptr[(l0 + 4 * k4) * kFusedWin + slot0];
-      const double b1 = bptr[(l0 + 4 * k4) * kFusedWin + slot1];
+      const double b = bptr[(l0 + 4 * k4) * kFusedWin];
 #pragma unroll
-      for (int i = 0; i < kFusedFrags; ++i) {
-        if (FULL || i < nfr) {
-          const double a = cq2[d[i] + 4 * k4];
-          dmma_m8n8k4(acc[i][0], a, b0);
-          dmma_m8n8k4(acc[i][1], a, b1);
-        }
-      }
+      for (int i = 0; i < NFR; ++i) dmma_m8n8k4(acc[i], cq2[d[i] + 4 * k4], b);
     }
 #pragma unroll
-    for (int i = 0; i < kFusedFrags; ++i) {
+    for (int i = 0; i < NFR; ++i) {
       d[i] += 32;
       if (d[i] >= q) {
         d[i] -= q;
@@ -335,20 +323,17 @@ __device__ __forceinline__ void fused_pass(const double* __restrict__ Ssm, const
     }
   }
 #pragma unroll
-  for (int i = 0; i < kFusedFrags; ++i) {
-    if (FULL || i < nfr) {
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        colacc[n][0] = fma(cnt[i] * acc[i][n][0], acc[i][n][0], colacc[n][0]);
-        colacc[n][1] = fma(cnt[i] * acc[i][n][1], acc[i][n][1], colacc[n][1]);
-      }
-    }
+  for (int i = 0; i < NFR; ++i) {
+    const int m = 8 * (frag0 + 8 * i) + lr;
+    const double cnt = m < q ? (double)(Mrows + (m < r0 ? 1 : 0)) : 0.0;
+    colacc[0] = fma(cnt * acc[i][0], acc[i][0], colacc[0]);
+    colacc[1] = fma(cnt * acc[i][1], acc[i][1], colacc[1]);
   }
 }
 
-// persistent grid (one CTA per SM); units handed out by a global counter: window groups outermost (a group's
-// windows stay in L2), periods descending inside a group (long units first), 16-window tiles innermost.
-__global__ void __launch_bounds__(kThreads, 1)
+// persistent grid (two CTAs per SM); units handed out by a global counter: window groups outermost (a group's
+// windows stay in L2), periods descending inside a group (long units first), 8-window tiles innermost.
+__global__ void __launch_bounds__(kThreads, 2)
 ram_fused_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int qmin, int qmax, int group_windows,
                  const double* __restrict__ cq_all, const int32_t* __restrict__ phi, double* __restrict__ norms,
                  int ld_norms, int* __restrict__ next_unit) {
@@ -384,61 +369,68 @@ ram_fused_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int qm
       for (int i = tid; i < q + 32; i += kThreads) cq2[i] = cq[i >= q ? (i - q) % q : i];
       q_tab = q;
     }
-    // ---- fold: S[m][w] = sum_j x[w][j q + m].  A warp step covers 8 residues x 4 windows (64 contiguous bytes
-    //      per window); four partial sums per lane (rows j mod 4) keep four loads in flight and meet in a fixed order.
+    // ---- fold: S[m][w] = sum_j x[w][j q + m].  A warp step covers 8 residues x 8 windows (64 contiguous bytes per
+    //      window, two windows per lane); two partial sums per chain (rows j mod 2) keep four loads of a lane in
+    //      flight at a time and meet in a fixed order.
     {
       const int mi = lane & 7, wi = lane >> 3;
       const int nmb = (q + 7) >> 3;
-      for (int item = wid; item < nmb * 4; item += kWarps) {
-        const int mb = item >> 2, wb = item & 3;
-        const int m = 8 * mb + mi, w = 4 * wb + wi;
-        double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-        if (m < q && w0 + w < B) {
-          const double* src = x + (size_t)(w0 + w) * ldx + m;
+      for (int mb = wid; mb < nmb; mb += kWarps) {
+        const int m = 8 * mb + mi;
+        double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+        if (m < q) {
+          const bool la = w0 + wi < B, lb = w0 + wi + 4 < B;
+          const double* pa = x + (size_t)(la ? w0 + wi : w0) * ldx + m;
+          const double* pb = x + (size_t)(lb ? w0 + wi + 4 : w0) * ldx + m;
           const int terms = Mrows + (m < r0 ? 1 : 0);
           int j = 0;
-          for (; j + 4 <= terms; j += 4) {
-            s0 += __ldg(src + (size_t)j * q);
-            s1 += __ldg(src + (size_t)(j + 1) * q);
-            s2 += __ldg(src + (size_t)(j + 2) * q);
-            s3 += __ldg(src + (size_t)(j + 3) * q);
+          for (; j + 2 <= terms; j += 2) {
+            a0 += __ldg(pa + (size_t)j * q);
+            a1 += __ldg(pa + (size_t)(j + 1) * q);
+            b0 += __ldg(pb + (size_t)j * q);
+            b1 += __ldg(pb + (size_t)(j + 1) * q);
           }
-          if (j < terms) s0 += __ldg(src + (size_t)j * q);
-          if (j + 1 < terms) s1 += __ldg(src + (size_t)(j + 1) * q);
-          if (j + 2 < terms) s2 += __ldg(src + (size_t)(j + 2) * q);
+          if (j < terms) {
+            a0 += __ldg(pa + (size_t)j * q);
+            b0 += __ldg(pb + (size_t)j * q);
+          }
+          Ssm[m * kFusedWin + wi] = la ? a0 + a1 : 0.0;
+          Ssm[m * kFusedWin + wi + 4] = lb ? b0 + b1 : 0.0;
         }
-        if (m < q) Ssm[m * kFusedWin + (w ^ fused_swz(m))] = (s0 + s1) + (s2 + s3);
       }
       // rows q .. round-up to the k-chunk: zero (their H elements are finite table entries)
       const int qr = (q + 31) & ~31;
       for (int i = q * kFusedWin + tid; i < qr * kFusedWin; i += kThreads) Ssm[i] = 0.0;
     }
     __syncthreads();
-    // ---- contraction: warp `wid` owns fragments wid, wid + 8, ... (8 rows each), eight per pass
-    double colacc[2][2] = {{0.0, 0.0}, {0.0, 0.0}};
+    // ---- contraction: warp `wid` owns fragments wid, wid + 8, ... (8 rows each), up to eight per pass
+    double colacc[2] = {0.0, 0.0};
     const int nfrag = (q + 7) >> 3;
     for (int f0 = wid; f0 < nfrag; f0 += 8 * kFusedFrags) {
       const int nfr = min(kFusedFrags, (nfrag - f0 + 7) >> 3);
-      if (nfr == kFusedFrags) fused_pass<true>(Ssm, cq2, q, f0, nfr, Mrows, r0, colacc);
-      else fused_pass<false>(Ssm, cq2, q, f0, nfr, Mrows, r0, colacc);
+      switch (nfr) {
+        case 8: fused_pass<8>(Ssm, cq2, q, f0, Mrows, r0, colacc); break;
+        case 7: fused_pass<7>(Ssm, cq2, q, f0, Mrows, r0, colacc); break;
+        case 6: fused_pass<6>(Ssm, cq2, q, f0, Mrows, r0, colacc); break;
+        case 5: fused_pass<5>(Ssm, cq2, q, f0, Mrows, r0, colacc); break;
+        case 4: fused_pass<4>(Ssm, cq2, q, f0, Mrows, r0, colacc); break;
+        case 3: fused_pass<3>(Ssm, cq2, q, f0, Mrows, r0, colacc); break;
+        case 2: fused_pass<2>(Ssm, cq2, q, f0, Mrows, r0, colacc); break;
+        default: fused_pass<1>(Ssm, cq2, q, f0, Mrows, r0, colacc); break;
+      }
     }
     // column sums: over the 8 row-lanes of a fragment, then over the warps in a fixed order
 #pragma unroll
-    for (int n = 0; n < 2; ++n)
-#pragma unroll
-      for (int e = 0; e < 2; ++e) {
-        double v = colacc[n][e];
-        v += __shfl_xor_sync(0xffffffffu, v, 4);
-        v += __shfl_xor_sync(0xffffffffu, v, 8);
-        v += __shfl_xor_sync(0xffffffffu, v, 16);
-        colacc[n][e] = v;
-      }
+    for (int e = 0; e < 2; ++e) {
+      double v = colacc[e];
+      v += __shfl_xor_sync(0xffffffffu, v, 4);
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      colacc[e] = v;
+    }
     if (lane < 4) {
-#pragma unroll
-      for (int n = 0; n < 2; ++n) {
-        red[wid * kFusedWin + n * 8 + 2 * lane] = colacc[n][0];
-        red[wid * kFusedWin + n * 8 + 2 * lane + 1] = colacc[n][1];
-      }
+      red[wid * kFusedWin + 2 * lane] = colacc[0];
+      red[wid * kFusedWin + 2 * lane + 1] = colacc[1];
     }
     __syncthreads();
     if (tid < kFusedWin && w0 + tid < B) {
@@ -912,7 +904,8 @@ static int ramanujan_norms_impl(const double* x, int64_t ldx, int32_t B, int32_t
     const long long units = (long long)(qmax - qmin + 1) * (group / kFusedWin) * ((B + group - 1) / group);
     if (units > 0x7fffffffLL) return fail(-1, "batch too large for one launch%s");
     if (int rc = check_cuda(cudaMemsetAsync(next_unit, 0, sizeof(int), st), "cudaMemsetAsync")) return rc;
-    const int grid = units < f.sm_count ? (int)units : f.sm_count;
+    const int ctas = grid_for(f, pl.bytes(), 0, 2);
+    const int grid = units < ctas ? (int)units : ctas;
     ram_fused_kernel<<<grid, kThreads, pl.bytes(), st>>>(x, ldx, B, N, qmin, qmax, group, cq, phi, norms, ld_norms,
                                                          next_unit);
     return check_cuda(cudaGetLastError(), "ram_fused_kernel launch");
