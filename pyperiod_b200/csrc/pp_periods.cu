@@ -716,7 +716,7 @@ s2l_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, double thres
     // the host rejects negative thresholds.
     while (pstart <= n_periods) {
       if (threadIdx.x == 0) sm.sweep->params.pmin = pstart;
-      const SweepResult hit = cta_sweep<0>(sm.sweep);
+      const SweepResult hit = cta_sweep<kSweepFirstHit>(sm.sweep);
       if (hit.p == 0) break;
       const int clen = orth ? tb.chain_off[hit.p + 1] - tb.chain_off[hit.p] : 0;
       cta_project_exact<false>(sm.xs, 0, N, hit.p, trunc, orth ? tb.chain_q + tb.chain_off[hit.p] : nullptr, clen,

@@ -1262,6 +1262,10 @@ __device__ __forceinline__ void warp_hier_top(const RankCtx& rc, uint2 e, double
 // CTA-level sweep
 // ------------------------------------------------------------------------------------------
 constexpr int kMaxVerify = 32;  // candidates re-evaluated exactly after a hierarchical MAXABS sweep
+#ifndef PP_FIRSTHIT_CHUNK
+#define PP_FIRSTHIT_CHUNK 32
+#endif
+constexpr int kFirstHitChunk = PP_FIRSTHIT_CHUNK;  // candidates per speculation chunk of a first-hit sweep
 
 struct SweepShared {
   double rcp[kRcpTab];  // rcp[m] = 1 / m (rcp[0] unused); filled once per CTA by sweep_shared_init
@@ -1297,6 +1301,7 @@ constexpr int kSweepPlain = 8;       // the caller never sweeps with trunc / ort
 constexpr int kSweepNoMetricOut = 16;  // the caller never asks for per-candidate metrics (drops the sqrt / divide of
                                        // key_to_value from every ranking site)
 constexpr int kSweepTieAudit = 32;     // NORM / GAMMA argmax sweeps: exact re-ranking of near-tied candidates
+constexpr int kSweepFirstHit = 64;     // first-hit (threshold) sweeps: small-to-large only
 
 // Rounding bound of a ranking key (an energy sum_r S_r^2 / cnt_r evaluated by any of the folds: sequential,
 // hierarchical, reciprocal weights) against the exactly rounded one, relative to e >= sum x^2 of the swept signal:
@@ -1326,7 +1331,7 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   const int metric = rc.metric;
   const int pmin = sp->pmin, pmax = sp->pmax;
   const double thresh = sp->thresh;
-  const bool first_hit = thresh >= 0.0;
+  const bool first_hit = (FEAT & kSweepFirstHit) != 0 && thresh >= 0.0;
   Best best{0.0, 0};
   // MAXABS (best-correlation) may rank hierarchically only when the caller provides `verify_keys`: the metric
   // must be the reference's bit-exact sequential sum, so the hierarchical pass only NOMINATES candidates and
@@ -1433,20 +1438,16 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
     if (wr.pend_p != 0)  // odd top left without a partner
       consider(hrc, hier_maxabs ? warp_max(wr.pend) : warp_sum(wr.pend), wr.pend_p, wr.best);
     best = warp_best(metric, wr.best);
-  } else {
-    const int ncand = pmax - pmin + 1;
-    while (true) {
-      int idx = 0;
-      if (lane == 0) idx = atomicAdd(&sh->counter, 1);
-      idx = __shfl_sync(0xffffffffu, idx, 0);
-      if (idx >= ncand) break;
-      const int p = pmin + idx;
-      if (first_hit) {
-        const int hp = *reinterpret_cast<volatile int*>(&sh->hit_p);
-        if (p > hp) break;
-      }
-      const double key = (FEAT & kSweepPlain) != 0 ? warp_period_key<kPassEnergy>(sp, p) : warp_period_key_any(sp, p);
-      if (first_hit) {
+  } else if (first_hit) {
+    // First-hit mode walks the candidates in ascending chunks of kFirstHitChunk, every warp folding its share of a
+    // chunk, and stops at the first chunk that holds a hit: the speculation past the hit is bounded by one chunk
+    // (a free-running hand-out lets fast warps fold hundreds of candidates of a residual that is about to change
+    // while one warp is still busy with the long rows of a small period; the kernel time then varied 7x run to run).
+    for (int base = pmin; base <= pmax; base += kFirstHitChunk) {
+      const int last = min(base + kFirstHitChunk - 1, pmax);
+      for (int p = base + wid; p <= last; p += kWarps) {
+        if (p > *reinterpret_cast<volatile int*>(&sh->hit_p)) break;
+        const double key = (FEAT & kSweepPlain) != 0 ? warp_period_key<kPassEnergy>(sp, p) : warp_period_key_any(sp, p);
         if (rc.metric_out != nullptr && lane == 0) rc.metric_out[p] = key;
         if (key > thresh) {
           if (best.p == 0 || p < best.p) {
@@ -1455,9 +1456,20 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
           }
           if (lane == 0) atomicMin(&sh->hit_p, p);
         }
-      } else {
-        consider(rc, key, p, best);
       }
+      __syncthreads();
+      if (*reinterpret_cast<volatile int*>(&sh->hit_p) != 0x7fffffff) break;   // uniform: read behind the barrier
+    }
+  } else {
+    const int ncand = pmax - pmin + 1;
+    while (true) {
+      int idx = 0;
+      if (lane == 0) idx = atomicAdd(&sh->counter, 1);
+      idx = __shfl_sync(0xffffffffu, idx, 0);
+      if (idx >= ncand) break;
+      const int p = pmin + idx;
+      const double key = (FEAT & kSweepPlain) != 0 ? warp_period_key<kPassEnergy>(sp, p) : warp_period_key_any(sp, p);
+      consider(rc, key, p, best);
     }
   }
   if (lane == 0) {

@@ -345,8 +345,10 @@ class Periods:
                      b1 - b0, w.n, thresh, n_periods, int(self._trunc_to_integer_multiple), orth, ptr(co), ptr(cq),
                      tb.pmax, kmax, ptr(periods[b0:b1]), ptr(powers[b0:b1]), ptr(None if bases is None else bases[b0:b1]),
                      ptr(count[b0:b1]), ptr(status[b0:b1]), ptr(ws), ws.numel(), stream_ptr(w.device))
-            need = int(count.max()) if w.b else 0
-            if need <= kmax or not w.was_1d:
+            if not w.was_1d:
+                break    # batch: windows over capacity carry PP_STATUS_OVERFLOW (no host synchronisation here)
+            need = int(count.max())
+            if need <= kmax:
                 break
             kmax = need  # 1-D drop-in: rerun with enough room so nothing is truncated
         res = BatchResult(_export(w, periods, True), _export(w, powers), _export(w, bases), _export(w, status),

@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-T=${TAG:-r02j}
-timeout 600 python -m pytest tests/test_gpu_ramanujan.py -q -x > gpurun_out/${T}_pytest_ram.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest_ram.log
-timeout 600 python tools/perf_ram.py 4096 fp64 > gpurun_out/${T}_perf_ram.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:ram_fused -c 1 -o gpurun_out/${T}_ram_fused python tools/prof_ram.py 1024 > gpurun_out/${T}_ncu_ram.log 2>&1
+T=${TAG:-r02l}
+timeout 900 python -m pytest tests/test_gpu_periods.py tests/test_gpu_determinism.py -q -x > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
+timeout 300 python tools/probe_s2l.py > gpurun_out/${T}_probe_s2l.log 2>&1
+timeout 300 python tools/perf_mbest.py > gpurun_out/${T}_perf_mbest.log 2>&1
