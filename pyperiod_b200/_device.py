@@ -181,7 +181,12 @@ class Workspace:
     a launch owns its workspace until the stream has run it, so calls issued on different CUDA streams or from
     different Python threads never share window counters, job tables or Cholesky factors."""
     _bufs: dict = {}
-    KEEP_BYTES = 1 << 30   # larger buffers are not cached (the caching allocator keeps them instead)
+    # Buffers up to this size stay with their (device, stream, thread) key.  The factor storage of a large-dictionary
+    # QO launch is 20 GB (296 CTAs x 68 MB): handing it back after every call made the next call pay for a fresh
+    # allocation and a 20 GB memset -- 80 to 320 ms for the same 80 ms of kernels.  Workspace.release() frees them.
+    KEEP_BYTES = 48 << 30
+    ZERO_BYTES = 1 << 20   # only the head of a large buffer is zero-filled (counters live there; the library memsets
+                           # what it needs, and a reused buffer is never re-zeroed anyway)
 
     @classmethod
     def get(cls, device: torch.device, nbytes: int) -> torch.Tensor:
@@ -190,13 +195,23 @@ class Workspace:
         key = (str(device), int(stream.cuda_stream), threading.get_ident())
         buf = cls._bufs.get(key)
         if buf is None or buf.numel() < nbytes:
+            cls._bufs.pop(key, None)   # give the smaller buffer back before asking for the larger one
+            buf = None
+            size = max(int(nbytes), 1 << 20)
             with torch.cuda.device(device):
-                buf = torch.zeros(max(int(nbytes), 1 << 20), dtype=torch.uint8, device=device)
+                if size <= (64 << 20):
+                    buf = torch.zeros(size, dtype=torch.uint8, device=device)
+                else:
+                    buf = torch.empty(size, dtype=torch.uint8, device=device)
+                    buf[: cls.ZERO_BYTES].zero_()
             if buf.numel() <= cls.KEEP_BYTES:
                 cls._bufs[key] = buf
-            elif key in cls._bufs:
-                del cls._bufs[key]
         return buf
+
+    @classmethod
+    def release(cls):
+        """Drop every cached workspace (the memory goes back to torch's caching allocator)."""
+        cls._bufs.clear()
 
 
 def stream_ptr(device: torch.device) -> C.c_void_p:

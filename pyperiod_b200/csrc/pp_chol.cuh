@@ -245,61 +245,61 @@ static __device__ __noinline__ bool cta_chol_factor(double* __restrict__ L, int 
         __syncthreads();  // the tile lives where the factor blocks are staged next
       }
       if (tph) tph[0] += clock64() - t_init;
-      // P -= L[rows, 0:j0) L[j, 0:j0)^T, 32 columns of k at a time.  No staging and no barrier in this loop: a warp
-      // reads its own 16 rows of L (the A fragments, in their fragment layout: 16-byte loads, fully used sectors)
-      // and the 32 rows of block row j (the B fragments, shared by every warp of the CTA: first touch from L2, then
-      // L1 hits) straight from global memory, and runs at its own pace -- while one warp waits for its rows (the
-      // factors of the concurrent windows do not fit L2: these are HBM round trips) the others keep the tensor
-      // pipe busy.  Each lane prefetches one 128-byte line of the warp's rows two chunks ahead into L2.
+      // P -= L[rows, 0:j0) L[j, 0:j0)^T, 32 columns of k at a time
+      auto stage = [&](int buf, int kc) {
+        for (int idx = tid; idx < kCb * 16; idx += kThreads) {
+          const int n = idx >> 4, piece = idx & 15;
+          const bool live = j0 + n < R;
+          const double* src = live ? Lj + (size_t)n * ldj + kc * kCb + 2 * piece : Lj;
+          chol_cp_async_16(st.Bs + buf * (kCb * kLdStage) + n * kLdStage + 2 * piece, src, live ? 16 : 0);
+        }
+        chol_cp_async_commit();
+      };
       const bool busy = mt0 < ntile;   // warp-uniform: this warp owns at least one m-tile of the pass
-      if (busy && jb > 0) {
-        const double* pf_row = nullptr;   // this lane's prefetch target: row (lane >> 1) of the warp's 16, half (lane & 1)
-        {
-          const int r = first + 8 * mt0 + (lane >> 1);
-          if (r < R) pf_row = L + chol_row_off(r) + 16 * (lane & 1);
+      if (jb > 0) stage(0, 0);
+      for (int kc = 0; kc < jb; ++kc) {
+        const int buf = kc & 1;
+        if (kc + 1 < jb) {
+          stage(buf ^ 1, kc + 1);
+          chol_cp_async_wait<1>();
+        } else {
+          chol_cp_async_wait<0>();
         }
-        bool brow[4];
+        __syncthreads();
+        if (busy) {
+        double a[2][4][2];
 #pragma unroll
-        for (int nt = 0; nt < 4; ++nt) brow[nt] = j0 + 8 * nt + lr < R;
-        const double* bp = Lj + (size_t)lr * ldj + 2 * lc;
-        if (pf_row != nullptr) {
-          asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row));
-          if (jb > 1) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row + kCb));
-        }
-        for (int kc = 0; kc < jb; ++kc) {
-          if (pf_row != nullptr && kc + 2 < jb) asm volatile("prefetch.global.L2 [%0];" ::"l"(pf_row + (kc + 2) * kCb));
-          double a[2][4][2];
+        for (int mt = 0; mt < 2; ++mt) {
+          if (kind[mt] != 0) {
+            const double2* p = reinterpret_cast<const double2*>(rp[mt] + kc * kCb + 2 * lc);
 #pragma unroll
-          for (int mt = 0; mt < 2; ++mt) {
-            if (kind[mt] != 0) {
-              const double2* p = reinterpret_cast<const double2*>(rp[mt] + kc * kCb + 2 * lc);
-#pragma unroll
-              for (int v = 0; v < 4; ++v) {
-                const double2 d2 = p[4 * v];
-                a[mt][v][0] = -d2.x;
-                a[mt][v][1] = -d2.y;
-              }
-            } else {
-#pragma unroll
-              for (int v = 0; v < 4; ++v) a[mt][v][0] = a[mt][v][1] = 0.0;
+            for (int v = 0; v < 4; ++v) {
+              const double2 d2 = p[4 * v];
+              a[mt][v][0] = -d2.x;
+              a[mt][v][1] = -d2.y;
             }
-          }
+          } else {
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            double2 b[4];
-#pragma unroll
-            for (int nt = 0; nt < 4; ++nt)
-              b[nt] = brow[nt] ? *reinterpret_cast<const double2*>(bp + (size_t)(8 * nt) * ldj + kc * kCb + 8 * v)
-                               : make_double2(0.0, 0.0);
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-              for (int nt = 0; nt < 4; ++nt) {
-                chol_dmma(acc[mt][nt], a[mt][v][0], b[nt].x);
-                chol_dmma(acc[mt][nt], a[mt][v][1], b[nt].y);
-              }
+            for (int v = 0; v < 4; ++v) a[mt][v][0] = a[mt][v][1] = 0.0;
           }
         }
+        const double* Bs = st.Bs + buf * (kCb * kLdStage);
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+          double2 b[4];
+#pragma unroll
+          for (int nt = 0; nt < 4; ++nt)
+            b[nt] = *reinterpret_cast<const double2*>(Bs + (8 * nt + lr) * kLdStage + 8 * v + 2 * lc);
+#pragma unroll
+          for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+            for (int nt = 0; nt < 4; ++nt) {
+              chol_dmma(acc[mt][nt], a[mt][v][0], b[nt].x);
+              chol_dmma(acc[mt][nt], a[mt][v][1], b[nt].y);
+            }
+        }
+        }
+        __syncthreads();  // everyone is done with this buffer before it is restaged
       }
       const bool diag_pass = diag_new && t0 == 0;
       if (diag_pass) {

@@ -1,8 +1,8 @@
 mkdir -p gpurun_out
-T=${TAG:-r02m}
-for v in "" build_variants/lib_ch16.so build_variants/lib_ch24.so build_variants/lib_ch64.so ""; do
-  echo "== variant '$v'" >> gpurun_out/${T}_s2l_variants.log
-  PYPERIOD_B200_LIB=$v timeout 300 python tools/probe_s2l.py 2>&1 | tail -2 >> gpurun_out/${T}_s2l_variants.log
+T=${TAG:-r02r}
+for v in build_variants/lib_chol_staged.so ""; do
+  n=$( [ -z "$v" ] && echo new || echo staged )
+  PYPERIOD_B200_LIB=$v timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:qo_solve --csv --log-file gpurun_out/${T}_launches_$n.csv python tools/prof_ram_solve.py 2048 > gpurun_out/${T}_$n.log 2>&1
+  echo "== $n" >> gpurun_out/${T}_qo.log
+  PYPERIOD_B200_LIB=$v timeout 300 python tools/perf_qo.py 8192 >> gpurun_out/${T}_qo.log 2>&1
 done
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
-timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
