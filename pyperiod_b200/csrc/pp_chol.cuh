@@ -3,10 +3,13 @@
 // The dictionary A of QOPeriods.get_subspaces (pyPeriod/QOPeriods.py:807-852) stacks, per period q, the first
 // rows_q indicator rows 1[n = i (mod q)].  Its Gram matrix G = A A^T (QOPeriods.py:781) is integer valued and never
 // stored: G[(a,i),(b,j)] = #{n < N : n = i (mod q_a), n = j (mod q_b)} has a closed form (Chinese remainder
-// theorem), evaluated where the factorisation consumes it.  What is stored is the Cholesky factor L only, packed
-// by block rows of 32 (row i holds 32 * (i / 32 + 1) doubles, so every 32-column block of a row is one aligned
-// 256-byte segment), with each diagonal block replaced by its INVERSE (the panel below a diagonal block, the
-// forward substitution and the back substitution all multiply by it; the block itself is never needed again).
+// theorem), evaluated where the factorisation consumes it.  What is stored is the Cholesky factor L only, as
+// 32 x 32 blocks of 8 KB each (block row by block row, row major inside a block): the 16 rows x 32 columns a warp
+// needs per k-chunk are 4 KB of CONTIGUOUS memory and the 32 x 32 block of block row j that every warp shares is one
+// 8 KB segment -- the factors of the concurrent windows do not fit L2, and with whole rows stored contiguously
+// (23 KB apart at R = 3000) every chunk opened a new DRAM page per row for 256 bytes.  Each diagonal block is
+// replaced by its INVERSE (the panel below a diagonal block, the forward substitution and the back substitution
+// all multiply by it; the block itself is never needed again).
 //
 // Factorisation: left-looking by block columns.  For block column j (32 columns) the CTA computes
 //     P = G[rows, j] - L[rows, 0:j) L[j, 0:j)^T      (DMMA m8n8k4, FP64 tensor cores)
@@ -31,10 +34,13 @@ constexpr int kCb = 32;        // Cholesky block size
 constexpr int kLdStage = 40;   // doubles per row of a staged 32 x 32 block: 16-byte fragment reads are conflict free
 constexpr int kLdD = 33;       // doubles per row of the diagonal-block scratch
 
-// packed factor: offset of row i, and total length for R rows
-__host__ __device__ inline size_t chol_row_off(int i) {
-  const int bi = i >> 5;
-  return (size_t)32 * (size_t)(bi + 1) * (size_t)(16 * bi + (i & 31));
+// packed factor: offset of the 32 x 32 block (block row bi, block column bk <= bi), of element (r, k), and the total
+// length for R rows
+__host__ __device__ inline size_t chol_blk(int bi, int bk) {
+  return (size_t)1024 * ((size_t)bi * (size_t)(bi + 1) / 2 + (size_t)bk);
+}
+__host__ __device__ inline size_t chol_at(int r, int k) {
+  return chol_blk(r >> 5, k >> 5) + (size_t)((r & 31) * 32 + (k & 31));
 }
 __host__ __device__ inline size_t chol_packed_len(int R) {
   const size_t nb = (size_t)((R + 31) >> 5);
@@ -191,26 +197,26 @@ static __device__ __noinline__ bool cta_chol_factor(double* __restrict__ L, int 
     const bool diag_new = j0 >= row_lo;
     const int first = diag_new ? j0 : row_lo;         // first row computed at this block column
     const int ntile = ((Rv - first) >> 3) + 1;        // m-tiles of 8 rows, the last one holds the virtual row
-    const double* Lj = L + chol_row_off(j0);          // block row j (rows j0 .. j0+31 have equal length 32 (jb+1))
-    const int ldj = kCb * (jb + 1);
+    const double* Lj = L + chol_blk(jb, 0);           // block row j: jb + 1 blocks of 32 x 32, one after the other
     if (!diag_new) {  // inverse of a diagonal block factored by an earlier call
       for (int idx = tid; idx < kCb * kCb; idx += kThreads) {
         const int r = idx >> 5, c = idx & 31;
-        st.Li[r * kLdD + c] = Lj[(size_t)r * ldj + j0 + c];
+        st.Li[r * kLdD + c] = Lj[(size_t)jb * 1024 + r * kCb + c];
       }
     }
     __syncthreads();
     for (int t0 = 0; t0 < ntile; t0 += 2 * kWarps) {
       const int mt0 = t0 + 2 * wid;
       // rows of this warp's two m-tiles: 0 = nothing (padding / past the end), 1 = factor row, 2 = right-hand side
-      int kind[2], row[2];
-      const double* rp[2];
+      int kind[2], row[2], kstr[2];
+      const double* rp[2];   // element (row, 32 kc + c) of the A operand is rp[kc * kstr + c]
 #pragma unroll
       for (int mt = 0; mt < 2; ++mt) {
         const int r = first + 8 * (mt0 + mt) + lr;
         row[mt] = r;
         kind[mt] = (mt0 + mt < ntile) ? (r < R ? 1 : (r == Rv ? 2 : 0)) : 0;
-        rp[mt] = kind[mt] == 1 ? L + chol_row_off(r) : y;
+        rp[mt] = kind[mt] == 1 ? L + chol_blk(r >> 5, 0) + (r & 31) * kCb : y;
+        kstr[mt] = kind[mt] == 1 ? 1024 : kCb;
       }
       double acc[2][4][2];
       const long long t_init = clock64();
@@ -250,7 +256,7 @@ static __device__ __noinline__ bool cta_chol_factor(double* __restrict__ L, int 
         for (int idx = tid; idx < kCb * 16; idx += kThreads) {
           const int n = idx >> 4, piece = idx & 15;
           const bool live = j0 + n < R;
-          const double* src = live ? Lj + (size_t)n * ldj + kc * kCb + 2 * piece : Lj;
+          const double* src = live ? Lj + (size_t)kc * 1024 + n * kCb + 2 * piece : Lj;
           chol_cp_async_16(st.Bs + buf * (kCb * kLdStage) + n * kLdStage + 2 * piece, src, live ? 16 : 0);
         }
         chol_cp_async_commit();
@@ -271,7 +277,7 @@ static __device__ __noinline__ bool cta_chol_factor(double* __restrict__ L, int 
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           if (kind[mt] != 0) {
-            const double2* p = reinterpret_cast<const double2*>(rp[mt] + kc * kCb + 2 * lc);
+            const double2* p = reinterpret_cast<const double2*>(rp[mt] + (size_t)kc * kstr[mt] + 2 * lc);
 #pragma unroll
             for (int v = 0; v < 4; ++v) {
               const double2 d2 = p[4 * v];
@@ -324,10 +330,10 @@ static __device__ __noinline__ bool cta_chol_factor(double* __restrict__ L, int 
         __syncthreads();
         if (tph) tph[1] += clock64() - t_diag;
         if (*st.flag) return false;
-        double* Ljw = L + chol_row_off(j0);
+        double* Ljw = L + chol_blk(jb, jb);
         for (int idx = tid; idx < kCb * kCb; idx += kThreads) {
           const int r = idx >> 5, c = idx & 31;
-          Ljw[(size_t)r * ldj + j0 + c] = st.Li[r * kLdD + c];
+          Ljw[idx] = st.Li[r * kLdD + c];
         }
       }
       // rows below the diagonal block: multiply by the inverse block, out = P Li^T.  The accumulator is the A
@@ -351,7 +357,7 @@ static __device__ __noinline__ bool cta_chol_factor(double* __restrict__ L, int 
 #pragma unroll
         for (int mt = 0; mt < 2; ++mt) {
           if (kind[mt] == 1) {
-            double* p = L + chol_row_off(row[mt]) + j0 + 2 * lc;
+            double* p = L + chol_blk(row[mt] >> 5, jb) + (row[mt] & 31) * kCb + 2 * lc;
 #pragma unroll
             for (int nt = 0; nt < 4; ++nt)
               *reinterpret_cast<double2*>(p + 8 * nt) = make_double2(out[mt][nt][0], out[mt][nt][1]);
@@ -381,11 +387,11 @@ static __device__ __noinline__ void cta_chol_backward(const double* L, int R, do
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nbk = (R + kCb - 1) / kCb;
   for (int jb = nbk - 1; jb >= 0; --jb) {
-    const int j0 = jb * kCb, ldj = kCb * (jb + 1);
-    const double* Lj = L + chol_row_off(j0);
+    const int j0 = jb * kCb;
+    const double* Lj = L + chol_blk(jb, 0);
     for (int idx = tid; idx < kCb * kCb; idx += kThreads) {
       const int r = idx >> 5, c = idx & 31;
-      st.Li[r * kLdD + c] = Lj[(size_t)r * ldj + j0 + c];
+      st.Li[r * kLdD + c] = Lj[(size_t)jb * 1024 + idx];
     }
     __syncthreads();
     if (wid == 0) {  // w_block = Li^T t
@@ -402,11 +408,12 @@ static __device__ __noinline__ void cta_chol_backward(const double* L, int R, do
     __syncthreads();
     // v[k] -= sum_c L[j0 + c][k] w[c] for every k left of the block (row access: coalesced over k)
     for (int k = tid; k < j0; k += kThreads) {
+      const double* col = Lj + (size_t)(k >> 5) * 1024 + (k & 31);   // L[j0 + c][k] = col[32 c]
       double s0 = 0.0, s1 = 0.0;
 #pragma unroll 8
       for (int c = 0; c < kCb; c += 2) {
-        s0 = fma(Lj[(size_t)c * ldj + k], st.rD[c], s0);
-        s1 = fma(Lj[(size_t)(c + 1) * ldj + k], st.rD[c + 1], s1);
+        s0 = fma(col[c * kCb], st.rD[c], s0);
+        s1 = fma(col[(c + 1) * kCb], st.rD[c + 1], s1);
       }
       v[k] -= s0 + s1;
     }
@@ -421,17 +428,17 @@ static __device__ __noinline__ void cta_chol_forward(const double* L, int R, dou
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
   const int nbk = (R + kCb - 1) / kCb;
   for (int jb = 0; jb < nbk; ++jb) {
-    const int j0 = jb * kCb, ldj = kCb * (jb + 1);
-    const double* Lj = L + chol_row_off(j0);
+    const int j0 = jb * kCb;
+    const double* Lj = L + chol_blk(jb, 0);
     for (int idx = tid; idx < kCb * kCb; idx += kThreads) {
       const int r = idx >> 5, c = idx & 31;
-      st.Li[r * kLdD + c] = Lj[(size_t)r * ldj + j0 + c];
+      st.Li[r * kLdD + c] = Lj[(size_t)jb * 1024 + idx];
     }
     // t[c] = v[j0 + c] - sum_{k < j0} L[j0 + c][k] v[k]: one warp per row, lanes over k
     for (int c = wid; c < kCb; c += kWarps) {
       double s = 0.0;
       if (j0 + c < R)
-        for (int k = lane; k < j0; k += 32) s = fma(Lj[(size_t)c * ldj + k], v[k], s);
+        for (int k = lane; k < j0; k += 32) s = fma(Lj[(size_t)(k >> 5) * 1024 + c * kCb + (k & 31)], v[k], s);
       s = warp_sum(s);
       if (lane == 0) st.rD[c] = (j0 + c < R) ? v[j0 + c] - s : 0.0;
     }
