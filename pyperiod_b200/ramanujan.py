@@ -18,6 +18,7 @@ from .qoperiods import RMAX_FIRST, QOBatchResult, QOPeriods, qo_workspace
 from .tables import get_tables
 
 TILE_WINDOWS = 2048      # tf32 / f32_compat: windows whose folds are held at once (7.5 MB per window at qmax = 1365)
+RMAX_TWO_CTAS = 3328     # largest dictionary (rows) whose solve kernel still fits two CTAs per SM at N = 4096
 L2_GROUP_WINDOWS = 1024  # fp64 (fused kernel): windows kept L2-resident while every period passes over them
 
 
@@ -126,9 +127,13 @@ class RamanujanPeriods(QOPeriods):
         small = torch.nonzero(~solvable | (rows <= first)).flatten().int()
         bigw = torch.nonzero(solvable & (rows > first)).flatten()
         launches = [(small, min(first, max(int(kept[small.long()].max()) if small.numel() else 32, 32)))]
-        if bigw.numel():
-            order = bigw[torch.argsort(rows[bigw], descending=True)].int()   # longest factorisations first
-            launches.append((order, int(rows[bigw].max())))
+        # large dictionaries in two launches: up to RMAX_TWO_CTAS rows the right-hand-side arrays still leave room
+        # for two CTAs per SM (the factorisation of one window is a latency-bound chain: a second CTA on the SM
+        # nearly doubles the throughput), only the few windows above it run one CTA per SM
+        for sel in (bigw[rows[bigw] <= RMAX_TWO_CTAS], bigw[rows[bigw] > RMAX_TWO_CTAS]):
+            if sel.numel():
+                order = sel[torch.argsort(rows[sel], descending=True)].int()   # longest factorisations first
+                launches.append((order, int(rows[sel].max())))
         for order, rmax_l in launches:
             if order.numel() == 0:
                 continue

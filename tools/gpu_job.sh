@@ -1,6 +1,6 @@
 mkdir -p gpurun_out
-T=${TAG:-r02t}
-timeout 900 python -m pytest tests/test_gpu_qo.py tests/test_gpu_ramanujan.py tests/test_gpu_determinism.py -q -x > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:qo_solve --csv --log-file gpurun_out/${T}_launches.csv python tools/prof_ram_solve.py 2048 > gpurun_out/${T}_prof.log 2>&1
-timeout 300 python tools/perf_qo.py 8192 > gpurun_out/${T}_qo.log 2>&1
-timeout 300 python tools/perf_ram_weights.py 4096 > gpurun_out/${T}_ramw.log 2>&1
+T=${TAG:-r02v}
+for args in "14 148" "14 592" "18 592" "6 592"; do
+  timeout 300 python tools/probe_solve_big.py $args 2>&1 | tail -2 >> gpurun_out/${T}_big.log
+done
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:qo_solve_kernel -s 1 -c 1 -o gpurun_out/${T}_deep python tools/probe_solve_big.py 14 148 > gpurun_out/${T}_ncu.log 2>&1
