@@ -167,6 +167,23 @@ def test_cfg5_large_dictionaries_are_solved(R):
         _check_against_refined(xb[i], d, res)
 
 
+def test_cfg5_large_dictionaries_in_two_launches(R, monkeypatch):
+    """The large dictionaries go to the solve kernel in two launches (two CTAs per SM up to RMAX_TWO_CTAS rows, one
+    above): with the boundary moved to 2000 rows windows 6 (1234 rows) and 14 (2896 rows) take different launches and
+    the results do not change."""
+    from pyperiod_b200 import ramanujan as ram_mod
+    xb = np.stack([synth.synth(4096, 50_000 + b) for b in (6, 14, 18, 2)])
+    ref = R().find_periods_with_weights(xb, thresh=0.2)
+    monkeypatch.setattr(ram_mod, "RMAX_TWO_CTAS", 2000)
+    out = R().find_periods_with_weights(xb, thresh=0.2)
+    assert out.status.tolist() == ref.status.tolist() == [0, 0, 0, 0]
+    for i in range(4):
+        d0, r0 = ref.window(i)
+        d1, r1 = out.window(i)
+        assert d0["basis_dictionary"] == d1["basis_dictionary"]
+        assert np.array_equal(d0["weights"], d1["weights"]) and np.array_equal(r0, r1)
+
+
 def test_cfg5_reference_fixture(R):
     """Reference-generated fixture (tests/golden/ram_cfg5.npz, make_golden.py ram_cfg5): find_periods_with_weights at
     config 5's shape on windows whose dictionaries have 1234 / 2896 / 1324 rows.  Periods, dictionary layout and norms
