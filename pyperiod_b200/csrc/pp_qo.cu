@@ -29,10 +29,11 @@ constexpr int kQoCtasPerSm = PP_QO_CTAS;  // persistent CTAs per SM of the QO ke
 
 struct QoPlan {
   int xs_len, n_even, rmax, num, seen_words, hier_len;
+  int x0_len;   // doubles of shared memory for the original window: n_even, or 0 when it is read in place from global
   int u_len;    // Ramanujan basis: a second window-sized vector (A^T p of the conjugate gradients), else 0
   int cg_len;   // Ramanujan basis: num * pmax, the longest dictionary (rows) and the longest table set (sum of q)
   __host__ __device__ size_t off_x0() const { return (size_t)xs_len * 8; }
-  __host__ __device__ size_t off_wv() const { return off_x0() + (size_t)n_even * 8; }
+  __host__ __device__ size_t off_wv() const { return off_x0() + (size_t)x0_len * 8; }
   __host__ __device__ int wv_len() const { return rmax + 2 * kCb; }
   __host__ __device__ size_t off_u() const { return off_wv() + (size_t)wv_len() * 8; }
   __host__ __device__ size_t off_chol() const { return off_u() + (size_t)u_len * 8; }
@@ -57,7 +58,8 @@ struct QoPlan {
   __host__ __device__ size_t ws_per_cta() const { return ws_L() + ws_save() + ws_norms(); }
 };
 
-__host__ __device__ inline QoPlan make_qo_plan(int N, int pmax, int num, int rmax, bool hier, bool ram_basis = false) {
+__host__ __device__ inline QoPlan make_qo_plan(int N, int pmax, int num, int rmax, bool hier, bool ram_basis = false,
+                                               bool x0_global = false) {
   QoPlan pl;
   pl.u_len = ram_basis ? ((N + 1) & ~1) : 0;
   pl.cg_len = ram_basis ? ((num * pmax + 31) & ~31) : 0;
@@ -66,6 +68,7 @@ __host__ __device__ inline QoPlan make_qo_plan(int N, int pmax, int num, int rma
   pl.xs_len = (N + kSweepPad + 1) & ~1;
   if (pl.xs_len < stage_len) pl.xs_len = stage_len;
   pl.n_even = (N + 1) & ~1;
+  pl.x0_len = x0_global ? 0 : pl.n_even;
   pl.rmax = (rmax + kCb - 1) / kCb * kCb;
   pl.num = num;
   pl.seen_words = (pmax + 32) / 32;
@@ -687,9 +690,12 @@ __global__ void __launch_bounds__(kThreads, 2)
 qo_solve_kernel(QoBatch batch, int N, int kmax, const int32_t* __restrict__ entries,
                 const int32_t* __restrict__ explicit_rows, const int32_t* __restrict__ n_entries, int pmax, int refine,
                 const int32_t* __restrict__ phi, int rmax, QoOut out, unsigned char* __restrict__ ws,
-                size_t ws_per_cta, int* __restrict__ next_window) {
+                size_t ws_per_cta, int* __restrict__ next_window, int x0_global) {
   unsigned char* smem = pp_smem;
-  const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
+  // x0_global: the window is read in place from global memory (L2) instead of being staged -- 32 KB less shared
+  // memory, which is what lets dictionaries of up to N rows run two CTAs per SM (the factorisation of one window
+  // is a latency-bound chain; the window itself is only read by the right-hand side and the residual)
+  const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false, false, x0_global != 0);
   QoCtx c = make_ctx(smem, pl, N, kmax, refine, phi, ws + (size_t)blockIdx.x * ws_per_cta);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + pl.off_bar());
   double* x0 = const_cast<double*>(c.x0);
@@ -700,7 +706,8 @@ qo_solve_kernel(QoBatch batch, int N, int kmax, const int32_t* __restrict__ entr
   loader.init(bar);
   for (WindowQueue wq(next_window); wq.b < batch.count; wq.next()) {
     const int b = batch.window(wq.b);
-    loader.load(x0, batch.x + (size_t)b * batch.ldx, N);
+    if (x0_global) c.x0 = batch.x + (size_t)b * batch.ldx;
+    else loader.load(x0, batch.x + (size_t)b * batch.ldx, N);
     const int nd = min(max(n_entries[b], 0), kmax);
     if (explicit_rows == nullptr) {
       for (int i = tid; i < nd; i += kThreads) c.found[i] = entries[(size_t)b * kmax + i];
@@ -807,7 +814,9 @@ size_t pp_qo_workspace_bytes(int32_t N, int32_t pmax, int32_t num, int32_t rmax,
   DeviceFacts f;
   if (device_facts(f)) return 0;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, true, basis == PP_BASIS_RAMANUJAN);
-  size_t grid = (size_t)grid_for(f, pl.bytes(), 0, kQoCtasPerSm);
+  // the solve kernel may keep the window in global memory to fit a second CTA per SM: size for the full grid
+  size_t grid = (size_t)kQoCtasPerSm * (size_t)f.sm_count;
+  if (basis == PP_BASIS_RAMANUJAN) grid = (size_t)grid_for(f, pl.bytes(), 0, kQoCtasPerSm);
   if (ctas > 0 && (size_t)ctas < grid) grid = (size_t)ctas;
   return 8192 + (size_t)(pmax + 2) * sizeof(uint2) + grid * pl.ws_per_cta();
 }
@@ -897,7 +906,16 @@ static int qo_solve_launch(const double* x, int64_t ldx, int32_t B, int32_t N, i
   if (refine < 0 || refine > 4) return fail(-1, "refine must be in [0, 4]%s");
   DeviceFacts f;
   if (int rc = device_facts(f)) return rc;
-  const QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
+  QoPlan pl = make_qo_plan(N, pmax, kmax, rmax, false);
+  // keep the window in global memory when that is what makes room for a second CTA per SM
+  int x0_global = 0;
+  if (grid_for(f, pl.bytes(), 0, kQoCtasPerSm) < kQoCtasPerSm * f.sm_count) {
+    const QoPlan alt = make_qo_plan(N, pmax, kmax, rmax, false, false, true);
+    if (grid_for(f, alt.bytes(), 0, kQoCtasPerSm) > grid_for(f, pl.bytes(), 0, kQoCtasPerSm)) {
+      pl = alt;
+      x0_global = 1;
+    }
+  }
   if (o.weights_off == nullptr && o.ldw < pl.rmax)
     return fail(-1, "ldw must be >= rmax rounded up to a multiple of 32 (or pass weights_off)%s");
   if (int rc = prep_kernel(qo_solve_kernel, pl.bytes(), f)) return rc;
@@ -911,7 +929,7 @@ static int qo_solve_launch(const double* x, int64_t ldx, int32_t B, int32_t N, i
   QoBatch batch{x, ldx, count, order};
   qo_solve_kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(
       batch, N, kmax, entries, explicit_rows, n_entries, pmax, refine, phi, pl.rmax, o,
-      reinterpret_cast<unsigned char*>(workspace) + off, pl.ws_per_cta(), next_window);
+      reinterpret_cast<unsigned char*>(workspace) + off, pl.ws_per_cta(), next_window, x0_global);
   return check_cuda(cudaGetLastError(), "qo_solve_kernel launch");
 }
 

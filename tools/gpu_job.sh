@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-T=${TAG:-r02v}
-for args in "14 148" "14 592" "18 592" "6 592"; do
-  timeout 300 python tools/probe_solve_big.py $args 2>&1 | tail -2 >> gpurun_out/${T}_big.log
-done
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:qo_solve_kernel -s 1 -c 1 -o gpurun_out/${T}_deep python tools/probe_solve_big.py 14 148 > gpurun_out/${T}_ncu.log 2>&1
+T=${TAG:-r02y}
+timeout 600 python tools/prof_ram_full.py 65536 > gpurun_out/${T}_full.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_launches.csv python tools/prof_ram_full.py 65536 > gpurun_out/${T}_full_ncu.log 2>&1
