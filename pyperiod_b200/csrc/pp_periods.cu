@@ -233,7 +233,7 @@ sweep_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int pmin, 
       sp.canon_v = sm.vwin;
       sp.canon_u = sm.utmp;
     }
-    const SweepResult r = cta_sweep<kSweepHier | kSweepTieAudit>(sm.sweep);
+    const SweepResult r = cta_sweep<kSweepHier | kSweepHierTrunc | kSweepTieAudit>(sm.sweep);
     if (threadIdx.x == 0) {
       best_p[b] = r.p;
       best_val[b] = r.val;
@@ -397,7 +397,8 @@ mbest_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
     const int guard = 12 * (pmax - pmin + 2) + 12 * num;
     while (true) {
       if (misc[0] >= num || misc[4] != PP_STATUS_OK) break;  // uniform: read after a barrier
-      const SweepResult top = cta_sweep<kSweepHier | kSweepNoMetricOut | kSweepTieAudit | (F32 ? kSweepF32 : 0) | (PLAIN ? kSweepPlain : 0)>(sm.sweep);
+      const SweepResult top = cta_sweep<kSweepHier | kSweepNoMetricOut | kSweepTieAudit | (F32 ? kSweepF32 : 0) |
+                                        (PLAIN ? kSweepPlain : kSweepHierTrunc)>(sm.sweep);
       ++sweeps;
       if (sm.sweep->tie_count > 1) ++tie_sweeps;  // decided by the exact re-ranking
       { const long long t = clock64(); t_sweep += t - t_mark; t_mark = t; }
@@ -853,9 +854,13 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
 // host side
 // ------------------------------------------------------------------------------------------
 // hierarchical ranking sweeps where they apply, unless the call asks for direct folds
+// (orthogonalised sweeps need every candidate's projection vector, not just its energy: sequential folds).  Truncated
+// folds (trunc_to_integer_multiple) rank hierarchically too, on a job table without riders and never in float.
 static bool hier_applies(int fold_mode, int metric, int trunc, int orth) {
-  return fold_mode != PP_FOLD_DIRECT && !trunc && !orth && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
+  (void)trunc;
+  return fold_mode != PP_FOLD_DIRECT && !orth && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
 }
+static bool hier_riders(int fold_mode, int trunc) { return fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS && !trunc; }
 
 // plan used for grid / workspace sizing: the largest any fold mode of the algorithm needs
 static int plan_for(int algo, int N, int pmax, int num, SmemPlan& pl) {
@@ -987,7 +992,7 @@ int pp_sweep(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t pmin, i
   if (ntops > 0) {
     tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)ntops * sizeof(uint2)));
     if (!tops) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
-    ntops = build_hier_jobs(N, pmin, pmax, fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS, tops, (cudaStream_t)stream);
+    ntops = build_hier_jobs(N, pmin, pmax, hier_riders(fold_mode, trunc), tops, (cudaStream_t)stream);
   }
   Tables tb{chain_off, chain_q, nullptr, nullptr};
   int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
@@ -1014,7 +1019,7 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   DeviceFacts f;
   if (int rc = device_facts(f)) return rc;
   const int hier = hier_applies(fold_mode, gamma ? PP_METRIC_GAMMA : PP_METRIC_NORM, trunc, orth) ? 1 : 0;
-  const int f32 = (hier && fold_mode == PP_FOLD_NOMINATE_F32) ? 1 : 0;
+  const int f32 = (hier && !trunc && fold_mode == PP_FOLD_NOMINATE_F32) ? 1 : 0;
   const SmemPlan pl = make_plan(N, pmax, num, true, hier != 0, f32 != 0, true);
   const bool plain = !trunc && !orth;
   auto kernel = f32 ? mbest_kernel<true, true> : (plain ? mbest_kernel<false, true> : mbest_kernel<false, false>);
@@ -1034,7 +1039,7 @@ int pp_mbest(const double* x, int64_t ldx, int32_t B, int32_t N, int32_t num, in
   if (ntops > 0) {
     tops = reinterpret_cast<uint2*>(carve(workspace, workspace_bytes, off, (size_t)ntops * sizeof(uint2)));
     if (!tops) return fail(-3, "workspace too small (see pp_workspace_bytes)%s");
-    ntops = build_hier_jobs(N, pmin, pmax, fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS, tops, (cudaStream_t)stream);
+    ntops = build_hier_jobs(N, pmin, pmax, hier_riders(fold_mode, trunc), tops, (cudaStream_t)stream);
   }
   Tables tb{chain_off, chain_q, fac_off, fac};
   kernel<<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(x, ldx, B, N, num, pmin, pmax, gamma, trunc, orth,

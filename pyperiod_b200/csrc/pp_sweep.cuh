@@ -121,7 +121,6 @@ struct RankCtx {
 __device__ __forceinline__ RankCtx rank_ctx(const SweepParams* sp) {
   return RankCtx{sp->nskip > 0 ? sp->skip : nullptr, sp->metric_out, sp->tie_keys, sp->rcp, sp->sqrtN, sp->metric, sp->N, sp->pmin, sp->pmax};
 }
-
 __device__ __forceinline__ void consider(const RankCtx& rc, double key, int p, Best& best) {
   const int metric = rc.metric;
   if (rc.metric_out != nullptr && (threadIdx.x & 31) == 0) rc.metric_out[p] = key_to_value(metric, key, p, rc.sqrtN);
@@ -258,6 +257,17 @@ static __device__ __noinline__ double rcp_slow(int m) { return 1.0 / (double)m; 
 __device__ __forceinline__ double rcp_of(const double* rcp, int m) {
   return m < kRcpTab ? rcp[m] : rcp_slow(m);
 }
+
+// energy of one candidate from its partial sums: T = sum of S_r^2, A = the part on residues that hold one more sample.
+//   full fold:      sum_r S_r^2 / cnt_r          = T / M + (1 / (M + 1) - 1 / M) A      (cnt_r = M, or M + 1 under A)
+//   truncated fold: sum_r cnt_r (S_r / M)^2      = T / M + A / M^2                      (S_r over the first M rows only)
+template <bool TRUNC>
+__device__ __forceinline__ double hier_energy(const double* rcp, int M, double T, double A) {
+  const double w = rcp_of(rcp, M);
+  if constexpr (TRUNC) return fma(A, w, T) * w;
+  else return fma(rcp_of(rcp, M + 1) - w, A, w * T);
+}
+
 
 // Register tiles are deliberately small and come in exactly two shapes -- kTileCols columns for the
 // body of a residue range, one column for what is left -- so the hot loops are a few hundred bytes
@@ -453,9 +463,16 @@ __host__ __device__ inline int hier_scratch_len(int pmax) { return ((((pmax >> 3
 // energy terms of one level held in `sets` accumulator sets v[0 .. sets): T += sum of squares, A += the part
 // whose residues hold one more term (warp-uniform top sets, and set 0 under the tail row)
 // MAXABS: T = max |sum| instead (best-correlation metric; counts play no role and A is unused).
-template <int SETS, int DIM0, int J, bool MAXABS>
+// TRUNC (trunc_to_integer_multiple): the candidate only uses its first M = floor(N / p) rows.  The accumulator sets
+// hold every complete base row, i.e. `extra` base rows too many for this level: they are the LAST row of each of the
+// top `extra` sets (row M0 - SETS + s of set s), so those sets are corrected by one reloaded row (xrow[s * g + 32 j],
+// xrow = staged window + (M0 - SETS) g + first residue of the lane) before they are squared; the tail row was never
+// accumulated.  The same top sets and tail residues are the ones that hold one more SAMPLE (A) -- there the count,
+// not the sum, is what differs.  live[j]: the lane's residue exists (masked tiles run past g).
+template <int SETS, int DIM0, int J, bool MAXABS, bool TRUNC = false>
 __device__ __forceinline__ void level_energy(const double (&v)[DIM0][J], int extra, const bool (&tail)[J], double& T,
-                                             double& A) {
+                                             double& A, const double* xrow = nullptr, int g = 0,
+                                             const bool* live = nullptr) {
   if constexpr (MAXABS) {
 #pragma unroll
     for (int s = 0; s < SETS; ++s)
@@ -464,9 +481,21 @@ __device__ __forceinline__ void level_energy(const double (&v)[DIM0][J], int ext
   } else {
 #pragma unroll
     for (int s = 0; s < SETS; ++s) {
-      const double q = sum_sq<J>(v[s]);
-      T += q;
-      if (s >= SETS - extra) A += q;  // warp-uniform
+      if (s >= SETS - extra) {  // warp-uniform
+        double q;
+        if constexpr (TRUNC) {
+          double t[J];
+#pragma unroll
+          for (int j = 0; j < J; ++j) t[j] = live[j] ? v[s][j] - xrow[s * g + 32 * j] : 0.0;
+          q = sum_sq<J>(t);
+        } else {
+          q = sum_sq<J>(v[s]);
+        }
+        T += q;
+        A += q;
+      } else {
+        T += sum_sq<J>(v[s]);
+      }
     }
 #pragma unroll
     for (int j = 0; j < J; ++j)
@@ -484,15 +513,20 @@ __device__ __forceinline__ void level_halve(double (&v)[DIM0][J]) {
 }
 
 // levels 2^LV .. 1 of a power-of-two set array (compile-time recursion keeps every index static)
-template <int DIM0, int J, int LV, int NL, bool MAXABS>
+// xt (TRUNC only): staged window + first residue of the lane (row 0)
+template <int DIM0, int J, int LV, int NL, bool MAXABS, bool TRUNC = false>
 struct pow2_levels {
   static __device__ __forceinline__ void run(double (&v)[DIM0][J], int M0, const bool (&tail)[J], double (&T)[NL],
-                                             double (&A)[NL]) {
+                                             double (&A)[NL], const double* xt = nullptr, int g = 0,
+                                             const bool* live = nullptr) {
     constexpr int sets = 1 << LV;
-    level_energy<sets, DIM0, J, MAXABS>(v, M0 & (sets - 1), tail, T[LV], A[LV]);
+    if constexpr (TRUNC)
+      level_energy<sets, DIM0, J, MAXABS, true>(v, M0 & (sets - 1), tail, T[LV], A[LV], xt + (M0 - sets) * g, g, live);
+    else
+      level_energy<sets, DIM0, J, MAXABS>(v, M0 & (sets - 1), tail, T[LV], A[LV]);
     if constexpr (LV > 0) {
       level_halve<sets, DIM0, J>(v);
-      pow2_levels<DIM0, J, LV - 1, NL, MAXABS>::run(v, M0, tail, T, A);
+      pow2_levels<DIM0, J, LV - 1, NL, MAXABS, TRUNC>::run(v, M0, tail, T, A, xt, g, live);
     }
   }
 };
@@ -513,7 +547,7 @@ struct rider_levels {
 // Rows (stride g) of base residues ra + lane + 32 j accumulated into S sets by (row - M0) mod S, plus the
 // predicated tail row into set 0.  head = M0 mod S, groups = M0 / S (warp-uniform, computed once per job).
 // MASK: the tile may run past g (lanes beyond it are zeroed).
-template <int S, int J, bool MASK>
+template <int S, int J, bool MASK, bool TRUNC = false>
 __device__ __forceinline__ void hier_accumulate(const double* __restrict__ xs, int g, int ra, int M0, int rr, int head,
                                                 int groups, double (&acc)[S][J], bool (&tail)[J]) {
   const int lane = threadIdx.x & 31;
@@ -558,7 +592,7 @@ __device__ __forceinline__ void hier_accumulate(const double* __restrict__ xs, i
   }
 #pragma unroll
   for (int j = 0; j < J; ++j) tail[j] = ra + lane + 32 * j < rr;
-  if (ra < rr) {  // warp-uniform: most tiles of a top lie entirely past the tail row
+  if (!TRUNC && ra < rr) {  // warp-uniform: most tiles of a top lie entirely past the tail row
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       double t = 0.0;
@@ -578,15 +612,22 @@ __device__ __forceinline__ void hier_accumulate(const double* __restrict__ xs, i
 }
 
 // One register tile of a plain top q = g * 2^L.
-template <int L, int J, bool MASK, bool MAXABS>
+template <int L, int J, bool MASK, bool MAXABS, bool TRUNC = false>
 __device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, int ra, int M0, int rr,
                                           double (&T)[L + 1], double (&A)[L + 1], double* scr) {
   constexpr int S = 1 << L;
   const int lane = threadIdx.x & 31;
   double acc[S][J];
   bool tail[J];
-  hier_accumulate<S, J, MASK>(xs, g, ra, M0, rr, M0 & (S - 1), M0 >> L, acc, tail);
-  pow2_levels<S, J, L, L + 1, MAXABS>::run(acc, M0, tail, T, A);
+  hier_accumulate<S, J, MASK, TRUNC>(xs, g, ra, M0, rr, M0 & (S - 1), M0 >> L, acc, tail);
+  if constexpr (TRUNC) {
+    bool live[J];
+#pragma unroll
+    for (int j = 0; j < J; ++j) live[j] = !MASK || ra + lane + 32 * j < g;
+    pow2_levels<S, J, L, L + 1, MAXABS, true>::run(acc, M0, tail, T, A, xs + ra + lane, g, live);
+  } else {
+    pow2_levels<S, J, L, L + 1, MAXABS>::run(acc, M0, tail, T, A);
+  }
   if (scr != nullptr) {
 #pragma unroll
     for (int j = 0; j < J; ++j)
@@ -629,7 +670,7 @@ struct hier_cols {
 };
 
 // One top period q = g * 2^L and every candidate q / 2^k below it.  Non-trunc, non-orth, NORM / GAMMA.
-template <int L, bool MAXABS>
+template <int L, bool MAXABS, bool TRUNC = false>
 __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int rr, double* scr, WarpRank& wr) {
   // M0 = floor(N / g) complete base rows; base residues below rr = N - M0 g have one more (tail) row
   constexpr int J = hier_cols<L>::value;
@@ -642,10 +683,10 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
 #pragma unroll
   for (int i = 0; i <= L; ++i) T[i] = A[i] = 0.0;
   int ra = 0;
-  for (; ra + 32 * J <= g; ra += 32 * J) hier_tile<L, J, false, MAXABS>(xs, g, ra, M0, rr, T, A, out);
+  for (; ra + 32 * J <= g; ra += 32 * J) hier_tile<L, J, false, MAXABS, TRUNC>(xs, g, ra, M0, rr, T, A, out);
   if constexpr (J > 2)
-    for (; ra + 64 <= g; ra += 64) hier_tile<L, 2, false, MAXABS>(xs, g, ra, M0, rr, T, A, out);
-  for (; ra < g; ra += 32) hier_tile<L, 1, true, MAXABS>(xs, g, ra, M0, rr, T, A, out);
+    for (; ra + 64 <= g; ra += 64) hier_tile<L, 2, false, MAXABS, TRUNC>(xs, g, ra, M0, rr, T, A, out);
+  for (; ra < g; ra += 32) hier_tile<L, 1, true, MAXABS, TRUNC>(xs, g, ra, M0, rr, T, A, out);
   // per-lane partial energies of the L + 1 levels, reduced together
   constexpr int KP = L == 0 ? 1 : (L == 1 ? 2 : 4);
   double e[KP];
@@ -655,9 +696,7 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
       if constexpr (MAXABS) {
         e[i] = T[i];
       } else {
-        const int M = M0 >> i;
-        const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
-        e[i] = fma(w_diff, A[i], w_lo * T[i]);
+        e[i] = hier_energy<TRUNC>(rc.rcp, M0 >> i, T[i], A[i]);
       }
     } else {
       e[i] = 0.0;
@@ -688,10 +727,12 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
     while (!(h & 1) && (h >> 1) >= rc.pmin) {
       const int h2 = h >> 1;
       const int M = N / h2, r0h = N - M * h2;
-      const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
+      // truncated fold: the halves hold 2 floor(M / 2) rows of period h2; an odd M brings one more complete row
+      const double* odd_row = (TRUNC && (M & 1)) ? xs + (M - 1) * h2 : nullptr;
       double t = 0.0, a = 0.0;
       for (int r = lane; r < h2; r += 32) {
-        const double v = src[r] + src[r + h2];
+        double v = src[r] + src[r + h2];
+        if (TRUNC && odd_row != nullptr) v += odd_row[r];
         dst[r] = v;
         if constexpr (MAXABS) {
           t = fmax(t, fabs(v));
@@ -702,7 +743,7 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
       }
       __syncwarp();
       if constexpr (MAXABS) consider(rc, warp_max(t), h2, best);
-      else consider(rc, warp_sum(fma(w_diff, a, w_lo * t)), h2, best);
+      else consider(rc, warp_sum(hier_energy<TRUNC>(rc.rcp, M, t, a)), h2, best);
       double* swp = src;
       src = dst;
       dst = swp;
@@ -1240,21 +1281,24 @@ inline int build_hier_jobs(int N, int pmin, int pmax, bool want_riders, uint2* t
   return hier_job_count(N, pmin, pmax, riders);
 }
 
-template <bool MAXABS>
+// TRUNC: the job table holds plain tops only (the host builds it without riders for truncated sweeps)
+template <bool MAXABS, bool TRUNC = false>
 __device__ __forceinline__ void warp_hier_top(const RankCtx& rc, uint2 e, double* scr, WarpRank& wr) {
   const int g = e.x & 0xffff, L = (e.x >> 16) & 0xf, M0 = e.y & 0xffff, rr = e.y >> 16;
 #ifndef PP_NO_RIDERS
-  if (e.x >> 20) {
-    if (L == 1) warp_hier_rider_L<1, MAXABS>(rc, g, M0, rr, wr);
-    else warp_hier_rider_L<2, MAXABS>(rc, g, M0, rr, wr);
-    return;
+  if constexpr (!TRUNC) {
+    if (e.x >> 20) {
+      if (L == 1) warp_hier_rider_L<1, MAXABS>(rc, g, M0, rr, wr);
+      else warp_hier_rider_L<2, MAXABS>(rc, g, M0, rr, wr);
+      return;
+    }
   }
 #endif
   switch (L) {
-    case 0: warp_hier_top_L<0, MAXABS>(rc, g, M0, rr, scr, wr); break;
-    case 1: warp_hier_top_L<1, MAXABS>(rc, g, M0, rr, scr, wr); break;
-    case 2: warp_hier_top_L<2, MAXABS>(rc, g, M0, rr, scr, wr); break;
-    default: warp_hier_top_L<3, MAXABS>(rc, g, M0, rr, scr, wr); break;
+    case 0: warp_hier_top_L<0, MAXABS, TRUNC>(rc, g, M0, rr, scr, wr); break;
+    case 1: warp_hier_top_L<1, MAXABS, TRUNC>(rc, g, M0, rr, scr, wr); break;
+    case 2: warp_hier_top_L<2, MAXABS, TRUNC>(rc, g, M0, rr, scr, wr); break;
+    default: warp_hier_top_L<3, MAXABS, TRUNC>(rc, g, M0, rr, scr, wr); break;
   }
 }
 
@@ -1302,6 +1346,7 @@ constexpr int kSweepNoMetricOut = 16;  // the caller never asks for per-candidat
                                        // key_to_value from every ranking site)
 constexpr int kSweepTieAudit = 32;     // NORM / GAMMA argmax sweeps: exact re-ranking of near-tied candidates
 constexpr int kSweepFirstHit = 64;     // first-hit (threshold) sweeps: small-to-large only
+constexpr int kSweepHierTrunc = 128;   // hierarchical NORM / GAMMA ranking of truncated folds (trunc_to_integer_multiple)
 
 // Rounding bound of a ranking key (an energy sum_r S_r^2 / cnt_r evaluated by any of the folds: sequential,
 // hierarchical, reciprocal weights) against the exactly rounded one, relative to e >= sum x^2 of the swept signal:
@@ -1338,7 +1383,7 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
   // the near-maximal ones are re-evaluated exactly below.
   const bool hier_maxabs = (FEAT & kSweepHierMaxAbs) != 0 && metric == PP_METRIC_MAXABS && sp->verify_keys != nullptr;
   const bool hier = (FEAT & (kSweepHier | kSweepHierMaxAbs | kSweepF32)) != 0 && sp->hier_scr != nullptr &&
-                    sp->tops != nullptr && !first_hit && !sp->orth && !sp->trunc &&
+                    sp->tops != nullptr && !first_hit && !sp->orth && (!sp->trunc || (FEAT & kSweepHierTrunc) != 0) &&
                     (((FEAT & (kSweepHier | kSweepF32)) != 0 && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA)) ||
                      hier_maxabs);
   // fp32 nomination: the float pass fills verify_keys[], then every candidate whose upper bound reaches the best
@@ -1432,7 +1477,10 @@ static __device__ __noinline__ SweepResult cta_sweep(SweepShared* sh) {
         if (hier_maxabs) warp_hier_top<true>(hrc, job, scr, wr);
       }
       if constexpr ((FEAT & kSweepHier) != 0) {
-        if (!hier_maxabs) warp_hier_top<false>(hrc, job, scr, wr);
+        if constexpr ((FEAT & kSweepHierTrunc) != 0) {
+          if (!hier_maxabs && sp->trunc) warp_hier_top<false, true>(hrc, job, scr, wr);
+        }
+        if (!hier_maxabs && !sp->trunc) warp_hier_top<false>(hrc, job, scr, wr);
       }
     }
     if (wr.pend_p != 0)  // odd top left without a partner

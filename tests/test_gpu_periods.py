@@ -136,6 +136,56 @@ def test_sweep_hierarchical_matches_direct(P, n, pmin, pmax):
         assert np.array_equal(pd_, pn)
 
 
+@pytest.mark.parametrize("n,pmin,pmax", [(4096, 2, 1024), (2000, 2, 666), (4095, 3, 1000), (1000, 17, 500),
+                                          (8192, 2, 2730), (512, 2, 100), (4096, 600, 1024), (4096, 2, 1365),
+                                          (3001, 2, 1500), (777, 5, 259), (4099, 2, 2049), (1024, 2, 341)])
+def test_sweep_hierarchical_truncated_matches_direct(P, n, pmin, pmax):
+    """trunc_to_integer_multiple=True: the hierarchical sweep (accumulator sets corrected by the rows a level does
+    not use, an extra complete row where the halved period has an odd row count) agrees with the sequential
+    truncated fold to rounding for every candidate period, and picks the same period."""
+    from pyperiod_b200 import _lib
+    xb = synth.synth_batch(3, n, 4343)
+    try:
+        out = {}
+        for mode in (_lib.FOLD_DIRECT, _lib.FOLD_HIERARCHICAL):
+            _lib.set_fold_mode(mode)
+            for metric in ("norm", "gamma"):
+                out[mode, metric] = P(True, False).sweep(xb, metric=metric, min_length=pmin, max_length=pmax)
+    finally:
+        _lib.set_fold_mode(_lib.FOLD_HIERARCHICAL)
+    for metric in ("norm", "gamma"):
+        md, pd_, vd = out[_lib.FOLD_DIRECT, metric]
+        mh, ph, vh = out[_lib.FOLD_HIERARCHICAL, metric]
+        assert np.all(mh[:, :pmin] == 0)
+        np.testing.assert_allclose(mh[:, pmin:], md[:, pmin:], rtol=1e-12, atol=0)
+        assert np.array_equal(pd_, ph)
+        np.testing.assert_allclose(vh, vd, rtol=1e-12)
+    # and against the oracle's projection for one window
+    x = xb[0]
+    for p in sorted({pmin, pmin + 1, (pmin + pmax) // 2, pmax - 1, pmax}):
+        want = op.periodic_norm(op.project(x, p, True, False))
+        assert abs(out[_lib.FOLD_HIERARCHICAL, "norm"][0][0, p] - want) <= 1e-12 * max(want, 1e-300), p
+
+
+def test_mbest_truncated_fold_modes_agree(P):
+    """Periods(True, False).m_best ranks hierarchically: same periods, sweep counts and bit-identical bases as with
+    sequential folds."""
+    from pyperiod_b200 import _lib
+    xb = synth.synth_batch(8, 4096, 778)
+    for gamma in (False, True):
+        try:
+            _lib.set_fold_mode(_lib.FOLD_DIRECT)
+            fn = P(True, False).m_best_gamma if gamma else P(True, False).m_best
+            a = fn(xb, num=10, max_length=1024, return_bases=True)
+            _lib.set_fold_mode(_lib.FOLD_HIERARCHICAL)
+            b = fn(xb, num=10, max_length=1024, return_bases=True)
+        finally:
+            _lib.set_fold_mode(_lib.FOLD_HIERARCHICAL)
+        assert np.array_equal(a.periods, b.periods) and np.array_equal(a.sweeps, b.sweeps)
+        np.testing.assert_allclose(a.powers, b.powers, rtol=1e-12)
+        assert np.array_equal(a.bases, b.bases)
+
+
 def test_mbest_fold_modes_agree(P):
     from pyperiod_b200 import _lib
     xb = synth.synth_batch(8, 4096, 777)

@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-T=${TAG:-r02y}
-timeout 600 python tools/prof_ram_full.py 65536 > gpurun_out/${T}_full.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/${T}_launches.csv python tools/prof_ram_full.py 65536 > gpurun_out/${T}_full_ncu.log 2>&1
+T=${TAG:-r02z}
+timeout 1200 python -m pytest tests/test_gpu_periods.py tests/test_gpu_qo.py -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
+PP_TRUNC=1 timeout 300 python tools/perf_mbest.py 16384 hier,direct > gpurun_out/${T}_perf_trunc.log 2>&1
+timeout 300 python tools/perf_mbest.py 16384 hier > gpurun_out/${T}_perf_plain.log 2>&1

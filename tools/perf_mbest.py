@@ -9,7 +9,8 @@ modes = sys.argv[2].split(",") if len(sys.argv) > 2 else ["hier", "direct"]
 stream = synth.synth_stream(B)
 dev = torch.from_numpy(stream).cuda()
 win = torch.as_strided(dev, (B, 4096), (512, 1))
-P = Periods()
+TRUNC = os.environ.get("PP_TRUNC", "0") == "1"      # PP_TRUNC=1: Periods(True, False), the truncated fold
+P = Periods(True, False) if TRUNC else Periods()
 prof = torch.zeros(8, dtype=torch.int64, device="cuda")
 _lib.set_profile_buffer(prof)
 for mode in modes:
