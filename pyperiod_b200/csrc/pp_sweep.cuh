@@ -830,27 +830,48 @@ struct F32Window {
   }
 };
 
+// Blackwell's packed single-precision add (add.rn.f32x2, SASS FADD2): one instruction for the residue pair a lane
+// owns -- the row loop of the float sweep is one LDS.64 and one FADD2 per 64 residues of a warp
+__device__ __forceinline__ float2 add_f32x2(float2 a, float2 b) {
+#ifndef PP_NO_F32X2
+  unsigned long long ra, rb, rd;
+  ra = *reinterpret_cast<unsigned long long*>(&a);
+  rb = *reinterpret_cast<unsigned long long*>(&b);
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+  return *reinterpret_cast<float2*>(&rd);
+#else
+  return make_float2(a.x + b.x, a.y + b.y);
+#endif
+}
+
 template <int J>
 __device__ __forceinline__ void add_row_f32(float2 (&acc)[J], const float2* __restrict__ row) {
   float2 t[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) t[j] = row[32 * j];
 #pragma unroll
-  for (int j = 0; j < J; ++j) {
-    acc[j].x += t[j].x;
-    acc[j].y += t[j].y;
-  }
+  for (int j = 0; j < J; ++j) acc[j] = add_f32x2(acc[j], t[j]);
+}
+
+__device__ __forceinline__ float2 fma_f32x2(float2 a, float2 b, float2 c) {
+#ifndef PP_NO_F32X2
+  unsigned long long ra, rb, rc, rd;
+  ra = *reinterpret_cast<unsigned long long*>(&a);
+  rb = *reinterpret_cast<unsigned long long*>(&b);
+  rc = *reinterpret_cast<unsigned long long*>(&c);
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  return *reinterpret_cast<float2*>(&rd);
+#else
+  return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y));
+#endif
 }
 
 template <int J>
 __device__ __forceinline__ float sum_sq_f32(const float2 (&v)[J]) {
-  float lo = v[0].x * v[0].x, hi = v[0].y * v[0].y;
+  float2 acc = make_float2(v[0].x * v[0].x, v[0].y * v[0].y);
 #pragma unroll
-  for (int j = 1; j < J; ++j) {
-    lo = fmaf(v[j].x, v[j].x, lo);
-    hi = fmaf(v[j].y, v[j].y, hi);
-  }
-  return lo + hi;
+  for (int j = 1; j < J; ++j) acc = fma_f32x2(v[j], v[j], acc);   // same two chains as the scalar form
+  return acc.x + acc.y;
 }
 
 template <int SETS, int DIM0, int J>
@@ -873,10 +894,7 @@ __device__ __forceinline__ void level_halve_f32(float2 (&v)[DIM0][J]) {
 #pragma unroll
   for (int s = 0; s < SETS / 2; ++s)
 #pragma unroll
-    for (int j = 0; j < J; ++j) {
-      v[s][j].x += v[s + SETS / 2][j].x;
-      v[s][j].y += v[s + SETS / 2][j].y;
-    }
+    for (int j = 0; j < J; ++j) v[s][j] = add_f32x2(v[s][j], v[s + SETS / 2][j]);
 }
 template <int DIM0, int J, int LV, int NL>
 struct pow2_levels_f32 {
