@@ -1,5 +1,5 @@
 mkdir -p gpurun_out
-T=${TAG:-r03a}
-timeout 600 python -m pytest tests/test_gpu_periods.py -q -k "f32 or fold_modes or differential" > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
-timeout 300 python tools/perf_mbest.py 16384 f32,hier,f32 > gpurun_out/${T}_perf.log 2>&1
-timeout 300 python tools/check_f32.py > gpurun_out/${T}_check_f32.log 2>&1
+T=${TAG:-r03c}
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
+timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_smoke.log
