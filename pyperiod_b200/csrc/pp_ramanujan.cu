@@ -900,7 +900,8 @@ static int ramanujan_norms_impl(const double* x, int64_t ldx, int32_t B, int32_t
     FusedPlan pl;
     pl.qmax = qmax;
     if (int rc = prep_kernel(ram_fused_kernel, pl.bytes(), f)) return rc;
-    const int group = (tile_windows + kFusedWin - 1) / kFusedWin * kFusedWin;
+    const int group_req = tile_windows < B ? tile_windows : B;   // a small batch is one (short) group: no empty units
+    const int group = (group_req + kFusedWin - 1) / kFusedWin * kFusedWin;
     const long long units = (long long)(qmax - qmin + 1) * (group / kFusedWin) * ((B + group - 1) / group);
     if (units > 0x7fffffffLL) return fail(-1, "batch too large for one launch%s");
     if (int rc = check_cuda(cudaMemsetAsync(next_unit, 0, sizeof(int), st), "cudaMemsetAsync")) return rc;
