@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define PP_ABI_VERSION 4
+#define PP_ABI_VERSION 5
 
 /* sweep metrics */
 #define PP_METRIC_NORM 0   /* ||proj_p|| / sqrt(N)                 Periods.py:221-241, 507-508 */
@@ -198,7 +198,13 @@ int pp_best_frequency_round(double *work, int32_t B, int32_t N, const double *ma
  * phi: device int32 table of Euler's totient for 0..table_pmax.
  * Outputs: periods u32[B,num] (found order, duplicates possible), norms f64[B,num], n_periods[B];
  * dictionary dict_q/dict_keep i32[B,num] in insertion order with n_dict[B]; weights f64[B,ldw]
- * (ldw >= rmax rounded up to 32) with n_weights[B]; res f64[B,N] (nullable); status[B]. */
+ * (ldw >= rmax rounded up to 32) with n_weights[B]; res f64[B,N] (nullable); status[B].
+ * weights_pool (nullable, natural basis): decouples the size of the dense weights array from rmax.  With a pool, ldw
+ * may be smaller than rmax: a window whose dictionary outgrows ldw rows writes its weights to one slot of
+ * weights_pool[pool_slots, rmax rounded up to 32] instead, pool_slot[b] = the slot (else -1); a window that finds the
+ * pool exhausted reports PP_STATUS_TOO_LARGE.  (Config 5: 1 % of the windows need more than 1024 rows; with the
+ * factor storage sized for 2560 rows and a pool for their weights they are solved in the first launch instead of a
+ * second one that is bound by its single largest window.) */
 /* basis (QOPeriods(basis_type=...), QOPeriods.py:153-155, 940-974):
  *   PP_BASIS_NATURAL    rows 1[n = i (mod q)] (default; Cholesky on the FP64 tensor cores as described above)
  *   PP_BASIS_RAMANUJAN  rows c_q((n - i) mod q) (QOPeriods.py:970-971, 1005-1052).  The q shifted rows of a period span
@@ -216,8 +222,8 @@ int pp_qo_find_periods(const double *x, int64_t ldx, int32_t B, int32_t N, int32
                        const int32_t *phi, int32_t table_pmax, int32_t rmax, const int32_t *order,
                        int32_t n_order, uint32_t *periods, double *norms, int32_t *n_periods, int32_t *dict_q,
                        int32_t *dict_keep, int32_t *n_dict, int32_t *n_weights, double *weights, int64_t ldw,
-                       double *res, int32_t *status, void *workspace, size_t workspace_bytes, void *profile,
-                       void *stream);
+                       double *res, int32_t *status, double *weights_pool, int32_t pool_slots, int32_t *pool_slot,
+                       void *workspace, size_t workspace_bytes, void *profile, void *stream);
 
 /* ---- get_subspaces + solve_quadratic for given periods (QOPeriods.py:743-852; used by
  *      RamanujanPeriods.find_periods_with_weights, RamanujanPeriods.py:106-112) ---------------

@@ -458,19 +458,39 @@ struct QoOut {
   int64_t ldw;
   double* res;         // [B, N] (nullable)
   int32_t* status;     // [B]
+  // overflow pool of the find kernel (nullable): a window whose dictionary outgrows the ldw doubles of its inline
+  // row takes one slot of pool_stride doubles; pool_slot[b] = its index, or -1
+  double* pool = nullptr;
+  int pool_slots = 0;
+  int64_t pool_stride = 0;
+  int* pool_counter = nullptr;
+  int32_t* pool_slot = nullptr;
   __device__ double* weights_of(int b) const { return weights + (weights_off ? weights_off[b] : (int64_t)b * ldw); }
 };
 
-__device__ void qo_commit(const QoCtx& c, const QoOut& o, int b, int nfound, const double* round_norms) {
+// Writes the outputs of a solved round.  Returns false (uniformly, nothing written) when the weights need a pool slot
+// and the pool is exhausted.  misc[11]: pool slot of this window (-1: none yet).  Contains a barrier when a pool is
+// in use.
+__device__ bool qo_commit(const QoCtx& c, const QoOut& o, int b, int nfound, const double* round_norms) {
   const int tid = threadIdx.x;
   const int ndict = c.misc[0], R = c.misc[1];
+  double* w = o.weights_of(b);
+  if (o.pool != nullptr) {
+    if (R > o.ldw) {
+      if (tid == 0 && c.misc[11] < 0) c.misc[11] = atomicAdd(o.pool_counter, 1);
+      __syncthreads();
+      const int slot = c.misc[11];
+      if (slot >= o.pool_slots) return false;
+      w = o.pool + (size_t)slot * o.pool_stride;
+    }
+    if (tid == 0) o.pool_slot[b] = (R > o.ldw) ? c.misc[11] : -1;
+  }
   for (int i = tid; i < c.num; i += kThreads) {
     o.periods[(size_t)b * c.num + i] = i < nfound ? (uint32_t)c.found[i] : 0u;
     o.norms[(size_t)b * c.num + i] = i < nfound ? round_norms[i] : 0.0;
     o.dict_q[(size_t)b * c.num + i] = i < ndict ? c.dict_q[i] : 0;
     o.dict_keep[(size_t)b * c.num + i] = i < ndict ? c.dict_keep[i] : 0;
   }
-  double* w = o.weights_of(b);
   for (int i = tid; i < R; i += kThreads) w[i] = c.wv[i];
   if (o.res)
     for (int n = tid; n < c.N; n += kThreads) o.res[(size_t)b * c.N + n] = c.xs[n];
@@ -479,6 +499,7 @@ __device__ void qo_commit(const QoCtx& c, const QoOut& o, int b, int nfound, con
     o.n_dict[b] = ndict;
     o.n_weights[b] = R;
   }
+  return true;
 }
 
 __device__ __forceinline__ QoCtx make_ctx(unsigned char* smem, const QoPlan& pl, int N, int num, int refine,
@@ -578,6 +599,7 @@ qo_find_kernel(QoBatch batch, int N, int num, double thresh, int pmin, int pmax,
       c.misc[1] = 0;
       c.misc[8] = 0;  // no Cholesky factor of this window in L yet
       c.misc[9] = 0;
+      c.misc[11] = -1;  // no overflow-pool slot yet
     }
     __syncthreads();
     qo_commit(c, out, b, 0, round_norms);
@@ -654,7 +676,11 @@ qo_find_kernel(QoBatch batch, int N, int num, double thresh, int pmin, int pmax,
       }
       // norms are indexed by round in the reference (norms[:len(found)]); rounds without a period only
       // happen once the residual is exactly zero, after which nothing changes
-      qo_commit(c, out, b, nfound, round_norms);
+      if (!qo_commit(c, out, b, nfound, round_norms)) {  // overflow pool exhausted: the caller re-runs this window
+        status = PP_STATUS_TOO_LARGE;
+        if (tid == 0) out.n_weights[b] = c.misc[1];
+        break;
+      }
       reported = nfound;
       __syncthreads();
       // the factorisation used the residual buffer past N as staging space: the sweep reads zeros there
@@ -845,7 +871,8 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
                        const int32_t* phi, int32_t table_pmax, int32_t rmax, const int32_t* order, int32_t n_order,
                        uint32_t* periods,
                        double* norms, int32_t* n_periods, int32_t* dict_q, int32_t* dict_keep, int32_t* n_dict,
-                       int32_t* n_weights, double* weights, int64_t ldw, double* res, int32_t* status, void* workspace,
+                       int32_t* n_weights, double* weights, int64_t ldw, double* res, int32_t* status,
+                       double* weights_pool, int32_t pool_slots, int32_t* pool_slot, void* workspace,
                        size_t workspace_bytes, void* profile, void* stream) {
   if (B == 0) return 0;  // empty batch: nothing to validate or launch
   const int count = order ? n_order : B;
@@ -864,11 +891,18 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   if (basis != PP_BASIS_NATURAL && basis != PP_BASIS_RAMANUJAN) return fail(-1, "unknown basis%s");
   const bool ram = basis == PP_BASIS_RAMANUJAN;
   const QoPlan pl = make_qo_plan(N, pmax, num, rmax, hier != 0, ram);
-  if (ldw < pl.rmax) return fail(-1, "ldw must be >= rmax rounded up to a multiple of 32%s");
+  const bool pooled = weights_pool != nullptr && !ram;
+  if (pooled) {
+    if (pool_slot == nullptr || pool_slots < 1 || ldw < 32) return fail(-1, "bad overflow pool arguments%s");
+  } else if (ldw < pl.rmax) {
+    return fail(-1, "ldw must be >= rmax rounded up to a multiple of 32 (or pass a weights pool)%s");
+  }
   if (int rc = ram ? prep_kernel(qo_find_kernel<1>, pl.bytes(), f) : prep_kernel(qo_find_kernel<0>, pl.bytes(), f))
     return rc;
   size_t off = 0;
   int* next_window = carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream);
+  int* pool_counter = pooled ? carve_window_counter(workspace, workspace_bytes, off, (cudaStream_t)stream) : nullptr;
+  if (pooled && pool_counter == nullptr) return fail(-3, "workspace too small (see pp_qo_workspace_bytes)%s");
   uint2* tops = nullptr;
   int ntops = hier ? hier_top_count(pmin, pmax) : 0;
   if (ntops > 0) {
@@ -882,6 +916,13 @@ int pp_qo_find_periods(const double* x, int64_t ldx, int32_t B, int32_t N, int32
   const int grid = qo_grid(f, pl, count, workspace_bytes - off);
   if (grid < 1) return fail(-3, "workspace too small for one factor (see pp_qo_workspace_bytes)%s");
   QoOut o{periods, norms, n_periods, dict_q, dict_keep, n_dict, n_weights, weights, nullptr, ldw, res, status};
+  if (pooled) {
+    o.pool = weights_pool;
+    o.pool_slots = pool_slots;
+    o.pool_stride = pl.rmax;
+    o.pool_counter = pool_counter;
+    o.pool_slot = pool_slot;
+  }
   QoBatch batch{x, ldx, count, order};
   if (ram)
     qo_find_kernel<1><<<grid, kThreads, pl.bytes(), (cudaStream_t)stream>>>(

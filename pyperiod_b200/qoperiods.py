@@ -26,7 +26,12 @@ from .periods import Periods, _export
 from .tables import get_tables
 
 MAX_ROUNDS = 64  # device-side cap on `num` (the reference's default num = len(data) is "way too many", :377)
-RMAX_FIRST = 1024      # dictionary rows the first launch holds factors for; larger windows get a second launch
+RMAX_FIRST = 1024      # rows of the dense weights array of a batch call (and of the first solve launch of RamanujanPeriods)
+RMAX_FACTOR = 3072     # dictionary rows the first find launch holds Cholesky factors for: windows between RMAX_FIRST
+                       # and this many rows write their weights to an overflow pool instead of waiting for a second
+                       # launch (which is bound by its single largest window); larger ones are re-run
+POOL_FRACTION = 16     # overflow-pool slots = windows / POOL_FRACTION (config 5: 1 % of the windows need one)
+POOL_MIN_SLOTS = 64
 WORKSPACE_FRACTION = 0.5   # share of the free device memory the Cholesky factors of one launch may take
 
 
@@ -214,16 +219,19 @@ class QOPeriods(Periods):
         # natural basis: more rows than samples is singular by rank, so N rows is the most a factor ever holds;
         # Ramanujan basis: rows <= sum of the periods (no factor is stored, rmax is the capacity of `weights`)
         rows_cap = n if basis == _lib.BASIS_NATURAL else num * int(max_length)
-        rmax = min(rows_cap, RMAX_FIRST) if rmax is None else int(rmax)
+        pooled = rmax is None and basis == _lib.BASIS_NATURAL and rows_cap > RMAX_FIRST
+        rmax = min(rows_cap, RMAX_FACTOR if pooled else RMAX_FIRST) if rmax is None else int(rmax)
         tb = get_tables(max_length)
         dev = w.device
         phi = tb.phi_device(dev)
         cur = torch.cuda.current_stream(dev)
 
-        def launch(x_ptr, ldx, count, rmax_l, plan):
+        def launch(x_ptr, ldx, count, rmax_l, plan, pool=False):
             """One pp_qo_find_periods call per piece of `plan` ((first, end, upload event) triples) into one set of
-            batch outputs."""
-            ldw = (rmax_l + 31) // 32 * 32
+            batch outputs.  pool: the dense weights array keeps RMAX_FIRST columns, larger dictionaries (up to rmax_l
+            rows) put their weights into an overflow pool."""
+            rpad = (rmax_l + 31) // 32 * 32
+            ldw = min(rpad, (RMAX_FIRST + 31) // 32 * 32) if pool else rpad
             i32 = dict(dtype=torch.int32, device=dev)
             f64 = dict(dtype=torch.float64, device=dev)
             o = dict(periods=torch.zeros((count, num), **i32), norms=torch.zeros((count, num), **f64),
@@ -231,6 +239,9 @@ class QOPeriods(Periods):
                      dict_keep=torch.zeros((count, num), **i32), n_dict=torch.zeros((count,), **i32),
                      n_weights=torch.zeros((count,), **i32), weights=torch.zeros((count, ldw), **f64),
                      res=torch.empty((count, n), **f64) if return_res else None, status=torch.zeros((count,), **i32))
+            slots = max(POOL_MIN_SLOTS, count // POOL_FRACTION) if pool else 0
+            o["pool"] = torch.empty((slots, rpad), **f64) if pool else None
+            o["pool_slot"] = torch.full((count,), -1, **i32) if pool else None
             ws = qo_workspace(lib, dev, n, int(max_length), num, rmax_l, basis)
             for b0, b1, ready in plan:
                 if ready is not None:
@@ -240,22 +251,35 @@ class QOPeriods(Periods):
                      n, num, float(thresh), int(min_length), int(max_length), int(self._trunc_to_integer_multiple),
                      self._fold(), int(refine), basis, ptr(phi), tb.pmax, int(rmax_l), ptr(None), 0, sl(o["periods"]),
                      sl(o["norms"]), sl(o["n_periods"]), sl(o["dict_q"]), sl(o["dict_keep"]), sl(o["n_dict"]),
-                     sl(o["n_weights"]), sl(o["weights"]), ldw, sl(o["res"]), sl(o["status"]), ptr(ws), ws.numel(),
-                     _lib.profile_ptr(), stream_ptr(dev))
+                     sl(o["n_weights"]), sl(o["weights"]), ldw, sl(o["res"]), sl(o["status"]), ptr(o["pool"]), slots,
+                     sl(o["pool_slot"]), ptr(ws), ws.numel(), _lib.profile_ptr(), stream_ptr(dev))
             return o
 
-        o = launch(w.ptr, w.ldx, w.b, rmax, w.launch_plan())
+        o = launch(w.ptr, w.ldx, w.b, rmax, w.launch_plan(), pool=pooled)
         big = None
+        if pooled:
+            # weights that went to the overflow pool (one host round trip for the slot table)
+            over = torch.nonzero(o["pool_slot"] >= 0).flatten()
+            if over.numel():
+                rows_o = o["n_weights"][over].tolist()
+                slot_o = o["pool_slot"][over].tolist()
+                pool_t = o["pool"] if not w.from_host else o["pool"][: max(slot_o) + 1].cpu()
+                big = {int(b): pool_t[s_, :r_] for b, s_, r_ in zip(over.tolist(), slot_o, rows_o)}
         rmax_l = rmax
-        while retry_big and rmax_l < rows_cap:
+        reruns = 0
+        while retry_big:
             idx = torch.nonzero(o["status"] == _lib.STATUS_TOO_LARGE).flatten()
             if not idx.numel():
                 break
-            # dictionaries that outgrew the factor storage: re-run just those windows with room for the rows they
-            # reported, at least doubled (a later round may need more: the loop repeats until nothing is left or the
-            # cap -- N rows, more is singular by rank -- is reached).  Small factors keep the re-run in L2.
+            # dictionaries that outgrew the factor storage (or found the overflow pool exhausted): re-run just those
+            # windows with room for the rows they reported, at least doubled (a later round may need more: the loop
+            # repeats until nothing is left or the cap -- N rows, more is singular by rank -- is reached)
             need = int(o["n_weights"][idx].max())
-            rmax_l = min(rows_cap, max(2 * rmax_l, (need + 255) // 256 * 256))
+            grown = min(rows_cap, max(2 * rmax_l, (need + 255) // 256 * 256))
+            if grown <= rmax_l and not (pooled and reruns == 0):
+                break    # already at the cap: these windows keep PP_STATUS_TOO_LARGE
+            rmax_l = max(rmax_l, grown)
+            reruns += 1
             xb = torch.as_strided(w.tensor, (w.b, n), (w.ldx, 1))[idx].contiguous()
             o2 = launch(xb.data_ptr(), n, int(idx.numel()), rmax_l, [(0, int(idx.numel()), None)])
             for key in ("periods", "norms", "n_periods", "dict_q", "dict_keep", "n_dict", "n_weights", "status"):

@@ -147,13 +147,21 @@ def test_qo_weights_normwise_1e10(QO):
         np.testing.assert_allclose(res, g[f"qo_{b}_res"], rtol=0, atol=1e-12)
 
 
-def test_qo_second_launch_for_large_dictionaries(QO, monkeypatch):
-    """Windows whose dictionary outgrows the first launch are re-run with room for N rows: same results as a single
-    launch that had the room from the start, and as the oracle."""
+@pytest.mark.parametrize("how", ["pool", "rerun", "pool_exhausted"])
+def test_qo_second_launch_for_large_dictionaries(QO, monkeypatch, how):
+    """Windows whose dictionary outgrows the dense weights array keep their weights in the overflow pool of the first
+    launch ("pool"); those that outgrow the factor storage, or find the pool exhausted, are re-run with room for the
+    rows they need ("rerun", "pool_exhausted"): same results as a single launch that had the room from the start, and
+    as the oracle."""
     from pyperiod_b200 import qoperiods
     xb = synth.synth_batch(6, 1500, 8800)
     ref = QO().find_periods(xb, num=4, thresh=0.05, max_length=400)
     monkeypatch.setattr(qoperiods, "RMAX_FIRST", 96)
+    if how == "rerun":
+        monkeypatch.setattr(qoperiods, "RMAX_FACTOR", 128)
+    if how == "pool_exhausted":
+        monkeypatch.setattr(qoperiods, "POOL_MIN_SLOTS", 1)
+        monkeypatch.setattr(qoperiods, "POOL_FRACTION", 1000)
     out = QO().find_periods(xb, num=4, thresh=0.05, max_length=400)
     assert out.big is not None and len(out.big) >= 1
     assert out.status.tolist() == ref.status.tolist() == [0] * 6

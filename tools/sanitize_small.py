@@ -18,7 +18,23 @@ if "qo" in which:
     out = QOPeriods().find_periods(xb, num=3, thresh=0.05, max_length=100)
     out = QOPeriods(trunc_to_integer_multiple=True).find_periods(xb, num=2, thresh=0.05, max_length=100)
     print("qo ok", flush=True)
+if "periods" in which:
+    P = Periods(trunc_to_integer_multiple=True, orthogonalize=False)     # truncated hierarchical sweep
+    r = P.m_best(xb, num=4, max_length=128)
+    r = Periods().best_frequency(xb, num=2)
+    print("periods (trunc hierarchy, best_frequency) ok", flush=True)
 if "ram" in which:
     R = RamanujanPeriods()
     out = R.find_periods_with_weights(xb, max_length=60, thresh=0.2)
     print("ram ok", flush=True)
+    for prec in ("tf32", "f32_compat"):
+        n = RamanujanPeriods(precision=prec).find_periods(xb, 2, 60)
+    print("ram tf32 / f32_compat ok", flush=True)
+if "qo" in which:
+    q = QOPeriods(basis_type="ramanujan")
+    out = q.find_periods(xb, num=2, thresh=0.05, max_length=60)
+    q2 = QOPeriods()
+    d, res = q2.find_periods(xb[0], num=3, thresh=0.05, max_length=100)
+    gp = q2.get_periods(d["weights"], d["basis_dictionary"])
+    pw = q2.get_best_period_orthogonal(xb[0], None, True, True)
+    print("qo ramanujan basis / get_periods / muresan ok", flush=True)
