@@ -22,6 +22,7 @@ import torch
 
 from . import _lib
 from ._device import Workspace, call, ptr, stage_windows, stream_ptr, to_host
+from ._device import RowDownloader
 from .periods import Periods, _export
 from .tables import get_tables
 
@@ -226,7 +227,7 @@ class QOPeriods(Periods):
         phi = tb.phi_device(dev)
         cur = torch.cuda.current_stream(dev)
 
-        def launch(x_ptr, ldx, count, rmax_l, plan, pool=False):
+        def launch(x_ptr, ldx, count, rmax_l, plan, pool=False, download=False):
             """One pp_qo_find_periods call per piece of `plan` ((first, end, upload event) triples) into one set of
             batch outputs.  pool: the dense weights array keeps RMAX_FIRST columns, larger dictionaries (up to rmax_l
             rows) put their weights into an overflow pool."""
@@ -243,6 +244,12 @@ class QOPeriods(Periods):
             o["pool"] = torch.empty((slots, rpad), **f64) if pool else None
             o["pool_slot"] = torch.full((count,), -1, **i32) if pool else None
             ws = qo_workspace(lib, dev, n, int(max_length), num, rmax_l, basis)
+            # host input: the two large results (residuals, dense weights) travel to the host piece by piece while the
+            # next piece is being computed
+            down = None
+            if download:
+                o["host"] = {"res": np.empty((count, n)) if return_res else None, "weights": np.empty((count, ldw))}
+                down = RowDownloader(dev, {"res": (o["res"], o["host"]["res"]), "weights": (o["weights"], o["host"]["weights"])})
             for b0, b1, ready in plan:
                 if ready is not None:
                     cur.wait_event(ready)
@@ -253,9 +260,16 @@ class QOPeriods(Periods):
                      sl(o["norms"]), sl(o["n_periods"]), sl(o["dict_q"]), sl(o["dict_keep"]), sl(o["n_dict"]),
                      sl(o["n_weights"]), sl(o["weights"]), ldw, sl(o["res"]), sl(o["status"]), ptr(o["pool"]), slots,
                      sl(o["pool_slot"]), ptr(ws), ws.numel(), _lib.profile_ptr(), stream_ptr(dev))
+                if down is not None:
+                    down.mark(b0, b1)
+                    down.drain()
+            if down is not None:
+                down.finish()
             return o
 
-        o = launch(w.ptr, w.ldx, w.b, rmax, w.launch_plan(), pool=pooled)
+        o = launch(w.ptr, w.ldx, w.b, rmax, w.launch_plan(), pool=pooled,
+                   download=w.from_host and w.plan is not None)
+        host = o.get("host")
         big = None
         if pooled:
             # weights that went to the overflow pool (one host round trip for the slot table)
@@ -285,13 +299,17 @@ class QOPeriods(Periods):
             for key in ("periods", "norms", "n_periods", "dict_q", "dict_keep", "n_dict", "n_weights", "status"):
                 o[key][idx] = o2[key]
             if return_res:
-                o["res"][idx] = o2["res"]
+                if host is not None:
+                    host["res"][idx.cpu().numpy()] = o2["res"].cpu().numpy()
+                else:
+                    o["res"][idx] = o2["res"]
             w2 = o2["weights"] if not w.from_host else o2["weights"].cpu()
             big = big or {}
             big.update({int(b): w2[i] for i, b in enumerate(idx.tolist())})
         out = QOBatchResult(_export(w, o["periods"], True), _export(w, o["norms"]), _export(w, o["n_periods"]),
                             _export(w, o["dict_q"]), _export(w, o["dict_keep"]), _export(w, o["n_dict"]),
-                            _export(w, o["weights"]), _export(w, o["n_weights"]), _export(w, o["res"]),
+                            host["weights"] if host is not None else _export(w, o["weights"]), _export(w, o["n_weights"]),
+                            (host["res"] if return_res else None) if host is not None else _export(w, o["res"]),
                             _export(w, o["status"]), n=n, big=big, basis=self._basis_type)
         if w.was_1d:
             if int(out.status[0]) == _lib.STATUS_TOO_LARGE:

@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-T=${TAG:-r03h}
-timeout 900 python bench.py --secondary 5qo > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:qo_find --csv --log-file gpurun_out/${T}_launches.csv python tools/probe_qo_full.py 65536 > gpurun_out/${T}_qo_ncu.log 2>&1
+T=${TAG:-r03m}
+timeout 900 python -m pytest tests/test_gpu_qo.py tests/test_gpu_ramanujan.py -q -x > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
+timeout 600 python tools/probe_qo_e2e.py > gpurun_out/${T}_e2e.log 2>&1
+timeout 900 python bench.py --secondary 5qo,5ram > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
