@@ -855,12 +855,15 @@ bcorr_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int num, i
 // ------------------------------------------------------------------------------------------
 // hierarchical ranking sweeps where they apply, unless the call asks for direct folds
 // (orthogonalised sweeps need every candidate's projection vector, not just its energy: sequential folds).  Truncated
-// folds (trunc_to_integer_multiple) rank hierarchically too, on a job table without riders and never in float.
+// folds (trunc_to_integer_multiple) rank hierarchically too (never in float).
 static bool hier_applies(int fold_mode, int metric, int trunc, int orth) {
   (void)trunc;
   return fold_mode != PP_FOLD_DIRECT && !orth && (metric == PP_METRIC_NORM || metric == PP_METRIC_GAMMA);
 }
-static bool hier_riders(int fold_mode, int trunc) { return fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS && !trunc; }
+static bool hier_riders(int fold_mode, int trunc) {
+  (void)trunc;   // truncated folds ride too (the same top-set correction applies to the 3 * 2^i set arrays)
+  return fold_mode != PP_FOLD_HIERARCHICAL_NO_RIDERS;
+}
 
 // plan used for grid / workspace sizing: the largest any fold mode of the algorithm needs
 static int plan_for(int algo, int N, int pmax, int num, SmemPlan& pl) {

@@ -531,15 +531,19 @@ struct pow2_levels {
   }
 };
 // levels 3 * 2^LV .. 3 of a rider chain
-template <int DIM0, int J, int LV, int NL, bool MAXABS>
+template <int DIM0, int J, int LV, int NL, bool MAXABS, bool TRUNC = false>
 struct rider_levels {
   static __device__ __forceinline__ void run(double (&v)[DIM0][J], int M0, const bool (&tail)[J], double (&T)[NL],
-                                             double (&A)[NL]) {
+                                             double (&A)[NL], const double* xt = nullptr, int g = 0,
+                                             const bool* live = nullptr) {
     constexpr int sets = 3 << LV;
-    level_energy<sets, DIM0, J, MAXABS>(v, M0 % sets, tail, T[LV], A[LV]);
+    if constexpr (TRUNC)
+      level_energy<sets, DIM0, J, MAXABS, true>(v, M0 % sets, tail, T[LV], A[LV], xt + (M0 - sets) * g, g, live);
+    else
+      level_energy<sets, DIM0, J, MAXABS>(v, M0 % sets, tail, T[LV], A[LV]);
     if constexpr (LV > 0) {
       level_halve<sets, DIM0, J>(v);
-      rider_levels<DIM0, J, LV - 1, NL, MAXABS>::run(v, M0, tail, T, A);
+      rider_levels<DIM0, J, LV - 1, NL, MAXABS, TRUNC>::run(v, M0, tail, T, A, xt, g, live);
     }
   }
 };
@@ -637,24 +641,31 @@ __device__ __forceinline__ void hier_tile(const double* __restrict__ xs, int g, 
 
 // One register tile of a host + rider job: S = 3 * 2^LH sets.  Th/Ah: host levels 2^LH .. 1, Tr/Ar: rider
 // levels 3 * 2^(LH-1) .. 3.
-template <int LH, int J, bool MASK, bool MAXABS>
+template <int LH, int J, bool MASK, bool MAXABS, bool TRUNC = false>
 __device__ __forceinline__ void rider_tile(const double* __restrict__ xs, int g, int ra, int M0, int rr, int head,
                                            int groups, double (&Th)[LH + 1], double (&Ah)[LH + 1], double (&Tr)[LH],
                                            double (&Ar)[LH]) {
   constexpr int S = 3 << LH, SH = 1 << LH;
+  const int lane = threadIdx.x & 31;
   double acc[S][J];
   bool tail[J];
-  hier_accumulate<S, J, MASK>(xs, g, ra, M0, rr, head, groups, acc, tail);
-  {  // host chain: sets t, t + SH, t + 2 SH fold into level SH
+  hier_accumulate<S, J, MASK, TRUNC>(xs, g, ra, M0, rr, head, groups, acc, tail);
+  bool live[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) live[j] = !MASK || ra + lane + 32 * j < g;
+  const double* xt = xs + ra + lane;
+  {  // host chain: sets t, t + SH, t + 2 SH fold into level SH (set t = rows with (row - M0) mod SH == t)
     double hv[SH][J];
 #pragma unroll
     for (int t = 0; t < SH; ++t)
 #pragma unroll
       for (int j = 0; j < J; ++j) hv[t][j] = (acc[t][j] + acc[t + SH][j]) + acc[t + 2 * SH][j];
-    pow2_levels<SH, J, LH, LH + 1, MAXABS>::run(hv, M0, tail, Th, Ah);
+    if constexpr (TRUNC) pow2_levels<SH, J, LH, LH + 1, MAXABS, true>::run(hv, M0, tail, Th, Ah, xt, g, live);
+    else pow2_levels<SH, J, LH, LH + 1, MAXABS>::run(hv, M0, tail, Th, Ah);
   }
   level_halve<S, S, J>(acc);  // level 3 * 2^(LH-1)
-  rider_levels<S, J, LH - 1, LH, MAXABS>::run(acc, M0, tail, Tr, Ar);
+  if constexpr (TRUNC) rider_levels<S, J, LH - 1, LH, MAXABS, true>::run(acc, M0, tail, Tr, Ar, xt, g, live);
+  else rider_levels<S, J, LH - 1, LH, MAXABS>::run(acc, M0, tail, Tr, Ar);
 }
 
 // register columns per accumulator set of a hierarchical tile: 8 accumulators per lane (8 / 4 / 2 / 1 columns
@@ -755,7 +766,7 @@ __device__ __forceinline__ void warp_hier_top_L(RankCtx rc, int g, int M0, int r
 
 // A host top q = g 2^LH (g odd) together with its rider; candidates g 2^i (i <= LH) and 3 g 2^i (i < LH) that
 // lie in [pmin, pmax].
-template <int LH, bool MAXABS>
+template <int LH, bool MAXABS, bool TRUNC = false>
 __device__ __forceinline__ void warp_hier_rider_L(RankCtx rc, int g, int M0, int rr, WarpRank& wr) {
   constexpr int S = 3 << LH;
 #ifndef PP_RIDER_J1
@@ -772,10 +783,10 @@ __device__ __forceinline__ void warp_hier_rider_L(RankCtx rc, int g, int M0, int
   for (int i = 0; i < LH; ++i) Tr[i] = Ar[i] = 0.0;
   int ra = 0;
   for (; ra + 32 * J <= g; ra += 32 * J)
-    rider_tile<LH, J, false, MAXABS>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+    rider_tile<LH, J, false, MAXABS, TRUNC>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
   if constexpr (J > 2)
-    for (; ra + 64 <= g; ra += 64) rider_tile<LH, 2, false, MAXABS>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
-  for (; ra < g; ra += 32) rider_tile<LH, 1, true, MAXABS>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+    for (; ra + 64 <= g; ra += 64) rider_tile<LH, 2, false, MAXABS, TRUNC>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
+  for (; ra < g; ra += 32) rider_tile<LH, 1, true, MAXABS, TRUNC>(xs, g, ra, M0, rr, head, groups, Th, Ah, Tr, Ar);
   // values 0 .. LH: host levels g 2^i; values LH+1 .. 2 LH: rider levels 3 g 2^i
   constexpr int NV = 2 * LH + 1;          // 3 or 5
   constexpr int KP = NV <= 4 ? 4 : 8;
@@ -787,9 +798,7 @@ __device__ __forceinline__ void warp_hier_rider_L(RankCtx rc, int g, int M0, int
     if constexpr (MAXABS) {
       e[i] = Th[i];
     } else {
-      const int M = M0 >> i;
-      const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
-      e[i] = fma(w_diff, Ah[i], w_lo * Th[i]);
+      e[i] = hier_energy<TRUNC>(rc.rcp, M0 >> i, Th[i], Ah[i]);
     }
   }
 #pragma unroll
@@ -797,9 +806,7 @@ __device__ __forceinline__ void warp_hier_rider_L(RankCtx rc, int g, int M0, int
     if constexpr (MAXABS) {
       e[LH + 1 + i] = Tr[i];
     } else {
-      const int M = M0 / (3 << i);
-      const double w_lo = rcp_of(rc.rcp, M), w_diff = rcp_of(rc.rcp, M + 1) - w_lo;
-      e[LH + 1 + i] = fma(w_diff, Ar[i], w_lo * Tr[i]);
+      e[LH + 1 + i] = hier_energy<TRUNC>(rc.rcp, M0 / (3 << i), Tr[i], Ar[i]);
     }
   }
   const double key = warp_sum_multi<KP, MAXABS>(e);
@@ -1299,17 +1306,14 @@ inline int build_hier_jobs(int N, int pmin, int pmax, bool want_riders, uint2* t
   return hier_job_count(N, pmin, pmax, riders);
 }
 
-// TRUNC: the job table holds plain tops only (the host builds it without riders for truncated sweeps)
 template <bool MAXABS, bool TRUNC = false>
 __device__ __forceinline__ void warp_hier_top(const RankCtx& rc, uint2 e, double* scr, WarpRank& wr) {
   const int g = e.x & 0xffff, L = (e.x >> 16) & 0xf, M0 = e.y & 0xffff, rr = e.y >> 16;
 #ifndef PP_NO_RIDERS
-  if constexpr (!TRUNC) {
-    if (e.x >> 20) {
-      if (L == 1) warp_hier_rider_L<1, MAXABS>(rc, g, M0, rr, wr);
-      else warp_hier_rider_L<2, MAXABS>(rc, g, M0, rr, wr);
-      return;
-    }
+  if (e.x >> 20) {
+    if (L == 1) warp_hier_rider_L<1, MAXABS, TRUNC>(rc, g, M0, rr, wr);
+    else warp_hier_rider_L<2, MAXABS, TRUNC>(rc, g, M0, rr, wr);
+    return;
   }
 #endif
   switch (L) {
