@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-T=${TAG:-r03o}
-timeout 900 python -m pytest tests/test_gpu_ramanujan.py tests/test_gpu_qo.py -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
-timeout 600 python tools/prof_ram_full.py 65536 > gpurun_out/${T}_full.log 2>&1
-for args in "14 592" "18 592" "6 592"; do timeout 300 python tools/probe_solve_big.py $args 2>&1 | tail -1 >> gpurun_out/${T}_big.log; done
+T=${TAG:-r03p}
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
+timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_smoke.log
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 1 --warmup 3 --windows 8192 --e2e-steps 1 --no-cpu-baseline --secondary none > gpurun_out/${T}_ncu_launches.log 2>&1
