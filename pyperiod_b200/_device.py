@@ -241,6 +241,7 @@ STAGE_BYTES = 64 << 20      # size of each of the two page-locked staging buffer
 COPY_THREADS = 4            # host threads that move a staged chunk into the caller's array (first touch of fresh pages)
 _stage_bufs: dict = {}
 _down_streams: dict = {}
+_stage_locks: dict = {}
 _copy_pool = None
 
 
@@ -277,11 +278,16 @@ class RowDownloader:
         self.dev = device
         self.pairs = {k: v for k, v in pairs.items() if v[0] is not None}
         key = str(device)
+        import threading
         if key not in _stage_bufs:
-            _stage_bufs[key] = [torch.empty(STAGE_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
-            _down_streams[key] = torch.cuda.Stream(device)
+            _stage_locks.setdefault(key, threading.Lock())
+            with _stage_locks[key]:
+                if key not in _stage_bufs:
+                    _down_streams[key] = torch.cuda.Stream(device)
+                    _stage_bufs[key] = [torch.empty(STAGE_BYTES, dtype=torch.uint8, pin_memory=True) for _ in range(2)]
         self.stage = _stage_bufs[key]
         self.cs = _down_streams[key]
+        self.lock = _stage_locks[key]   # the staging buffers of a device are shared by every thread that uses it
         self.pending = []   # (b0, b1, event)
 
     def mark(self, b0: int, b1: int):
@@ -290,6 +296,10 @@ class RowDownloader:
         self.pending.append((b0, b1, ev))
 
     def _copy(self, b0: int, b1: int, ev):
+        with self.lock:
+            self._copy_locked(b0, b1, ev)
+
+    def _copy_locked(self, b0: int, b1: int, ev):
         self.cs.wait_event(ev)
         for src, dst in self.pairs.values():
             s = src[b0:b1].reshape(-1).view(torch.uint8)
