@@ -1,6 +1,4 @@
 mkdir -p gpurun_out
-T=${TAG:-r03p}
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
-timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_smoke.log
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${T}_launches.csv python bench.py --steps 1 --warmup 3 --windows 8192 --e2e-steps 1 --no-cpu-baseline --secondary none > gpurun_out/${T}_ncu_launches.log 2>&1
+T=${TAG:-r03r}
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:ram_umma_tf32 -s 1 -c 1 -o gpurun_out/${T}_tf32 python tools/prof_ram_tf32.py 1024 > gpurun_out/${T}_ncu_tf32.log 2>&1
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:qo_find_kernel -s 1 -c 1 -o gpurun_out/${T}_qo_find python tools/prof_qo.py 2368 > gpurun_out/${T}_ncu_qo.log 2>&1
