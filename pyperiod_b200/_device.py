@@ -239,6 +239,7 @@ def ptr(t) -> C.c_void_p:
 PINNED_D2H_MIN_BYTES = 1 << 20
 STAGE_BYTES = 64 << 20      # size of each of the two page-locked staging buffers of a pipelined download
 COPY_THREADS = 4            # host threads that move a staged chunk into the caller's array (first touch of fresh pages)
+COPY_THREADS_MIN_BYTES = 8 << 20
 _stage_bufs: dict = {}
 _down_streams: dict = {}
 _stage_locks: dict = {}
@@ -250,7 +251,7 @@ def _host_copy(dst: np.ndarray, src: np.ndarray):
     freshly allocated pages, which made the host side of a 2.6 GB download longer than the kernels it hides behind)."""
     global _copy_pool
     n = dst.shape[0]
-    if n < (8 << 20) or COPY_THREADS < 2:
+    if n < COPY_THREADS_MIN_BYTES or COPY_THREADS < 2:
         np.copyto(dst, src)
         return
     if _copy_pool is None:

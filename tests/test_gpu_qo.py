@@ -177,6 +177,50 @@ def test_qo_second_launch_for_large_dictionaries(QO, monkeypatch, how):
         np.testing.assert_allclose(res, res0, rtol=0, atol=1e-11)
 
 
+def test_qo_pipelined_download_matches_device_resident(QO, monkeypatch):
+    """A large host batch is uploaded in pieces and its residuals / weights come back piece by piece through the
+    two staging buffers of RowDownloader (here shrunk to 1 MB so that every piece takes several chunks, with the
+    threaded host copy forced on): same results as the device-resident call."""
+    import torch
+    from pyperiod_b200 import _device
+    monkeypatch.setattr(_device, "PIPELINE_MIN_WINDOWS", 512)
+    monkeypatch.setattr(_device, "STAGE_BYTES", 1 << 20)
+    monkeypatch.setattr(_device, "COPY_THREADS_MIN_BYTES", 1 << 16)
+    _device._stage_bufs.clear()                      # staging buffers are sized when first used
+    rng = np.random.default_rng(11)
+    base = synth.synth_batch(64, 512, 9100)
+    xb = np.concatenate([base * (1.0 + 0.01 * k) + 1e-3 * rng.standard_normal(base.shape) for k in range(10)])[:600]
+    ref = QO().find_periods(torch.from_numpy(xb).cuda(), num=3, thresh=0.05, max_length=150)
+    got = QO().find_periods(torch.from_numpy(xb).pin_memory(), num=3, thresh=0.05, max_length=150)
+    assert isinstance(got.res, np.ndarray) and isinstance(got.weights, np.ndarray)
+    assert np.array_equal(got.res, ref.res.cpu().numpy())
+    assert np.array_equal(got.weights, ref.weights.cpu().numpy())
+    assert np.array_equal(np.asarray(got.periods), ref.periods.cpu().numpy().view(np.asarray(got.periods).dtype))
+    assert np.array_equal(np.asarray(got.status), ref.status.cpu().numpy())
+    _device._stage_bufs.clear()
+
+
+def test_to_host_staged_path(monkeypatch):
+    """to_host above STAGED_D2H_MIN_BYTES: chunks through the page-locked staging buffers into an ordinary array
+    (odd sizes, several chunks, int and float payloads)."""
+    import torch
+    from pyperiod_b200 import _device
+    monkeypatch.setattr(_device, "STAGED_D2H_MIN_BYTES", 1 << 20)
+    monkeypatch.setattr(_device, "PINNED_D2H_MIN_BYTES", 1 << 10)
+    monkeypatch.setattr(_device, "STAGE_BYTES", 1 << 20)
+    monkeypatch.setattr(_device, "COPY_THREADS_MIN_BYTES", 1 << 16)
+    _device._stage_bufs.clear()
+    g = torch.Generator(device="cuda").manual_seed(3)
+    for shape, dt in (((1237, 1031), torch.float64), ((5_000_011,), torch.int32), ((3, 700, 1001), torch.float64)):
+        t = (torch.rand(shape, device="cuda", generator=g) * 1000).to(dt)
+        h = _device.to_host(t)
+        assert isinstance(h, np.ndarray) and h.shape == tuple(shape)
+        assert np.array_equal(h, t.cpu().numpy())
+    tt = torch.arange(4_000_000, device="cuda", dtype=torch.float64).reshape(2000, 2000).t()   # non-contiguous
+    assert np.array_equal(_device.to_host(tt), tt.cpu().numpy())
+    _device._stage_bufs.clear()
+
+
 def test_qo_rows_beyond_samples_are_singular(QO):
     """More dictionary rows than samples: A A^T is singular by rank.  The reference's LU either raises LinAlgError or
     returns rounding noise; the device reports SINGULAR and keeps the previous round's outputs (QOPeriods.py:552-559)."""

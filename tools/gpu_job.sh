@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-T=${TAG:-r03t}
-timeout 300 python tools/perf_qo.py 8192 > gpurun_out/${T}_perf.log 2>&1
-timeout 300 python tools/perf_qo.py 8192 >> gpurun_out/${T}_perf.log 2>&1
-timeout 300 python tools/perf_qo_trunc.py 8192 >> gpurun_out/${T}_perf.log 2>&1
+T=${TAG:-r03u}
+timeout 900 python -m pytest tests/test_gpu_qo.py -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
