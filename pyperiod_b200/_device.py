@@ -185,8 +185,6 @@ class Workspace:
     # QO launch is 20 GB (296 CTAs x 68 MB): handing it back after every call made the next call pay for a fresh
     # allocation and a 20 GB memset -- 80 to 320 ms for the same 80 ms of kernels.  Workspace.release() frees them.
     KEEP_BYTES = 48 << 30
-    ZERO_BYTES = 1 << 20   # only the head of a large buffer is zero-filled (counters live there; the library memsets
-                           # what it needs, and a reused buffer is never re-zeroed anyway)
 
     @classmethod
     def get(cls, device: torch.device, nbytes: int) -> torch.Tensor:
@@ -199,11 +197,7 @@ class Workspace:
             buf = None
             size = max(int(nbytes), 1 << 20)
             with torch.cuda.device(device):
-                if size <= (64 << 20):
-                    buf = torch.zeros(size, dtype=torch.uint8, device=device)
-                else:
-                    buf = torch.empty(size, dtype=torch.uint8, device=device)
-                    buf[: cls.ZERO_BYTES].zero_()
+                buf = torch.zeros(size, dtype=torch.uint8, device=device)   # once per buffer: it stays cached
             if buf.numel() <= cls.KEEP_BYTES:
                 cls._bufs[key] = buf
         return buf

@@ -455,11 +455,12 @@ def test_mbest_pipelined_host_upload_matches_device_resident():
     strided = np.lib.stride_tricks.as_strided(stream, shape=(B, N), strides=(hop * 8, 8), writeable=False)
     got_np = P.m_best(strided, num=3, max_length=64)
     dense = P.m_best(np.ascontiguousarray(strided), num=3, max_length=64)
-    for g in (got, got_np, dense):
+    rp, rw, rs = ref.periods.cpu().numpy().view(np.uint32), ref.powers.cpu().numpy(), ref.status.cpu().numpy()
+    for name, g in (("pinned", got), ("strided numpy", got_np), ("dense numpy", dense)):
         assert isinstance(g.periods, np.ndarray)
-        assert np.array_equal(g.periods, ref.periods.cpu().numpy().view(np.uint32))
-        assert np.array_equal(g.powers, ref.powers.cpu().numpy())
-        assert np.array_equal(g.status, ref.status.cpu().numpy())
+        bad = np.nonzero((g.periods != rp).any(axis=1) | (g.powers != rw).any(axis=1) | (g.status != rs))[0]
+        assert bad.size == 0, (name, bad.size, bad[:8].tolist(), g.periods[bad[:2]].tolist(), rp[bad[:2]].tolist(),
+                               g.powers[bad[:2]].tolist(), rw[bad[:2]].tolist(), g.status[bad[:4]].tolist())
 
 
 def test_best_correlation_hierarchical_nomination_is_exact(P):
