@@ -216,3 +216,21 @@ def test_pipeline_bounds_partition_the_batch():
         assert all(lo < hi for lo, hi in bounds)
         assert all(bounds[i][1] == bounds[i + 1][0] for i in range(len(bounds) - 1))
         assert len(bounds) <= 10
+
+
+def test_threaded_host_copy_is_a_plain_copy(monkeypatch):
+    """_device._host_copy (the staging-buffer -> result-array step of a pipelined download) splits a chunk over a few
+    threads on 4 KB boundaries: odd lengths, lengths below the threading threshold, one thread."""
+    from pyperiod_b200 import _device
+    rng = np.random.default_rng(0)
+    monkeypatch.setattr(_device, "COPY_THREADS_MIN_BYTES", 1 << 12)
+    for n in (1, 4095, 4096, 4097, 65_537, 1_000_003):
+        src = rng.integers(0, 256, n, dtype=np.uint8)
+        dst = np.zeros(n, dtype=np.uint8)
+        _device._host_copy(dst, src)
+        assert np.array_equal(dst, src), n
+    monkeypatch.setattr(_device, "COPY_THREADS", 1)
+    src = rng.integers(0, 256, 70_001, dtype=np.uint8)
+    dst = np.zeros_like(src)
+    _device._host_copy(dst, src)
+    assert np.array_equal(dst, src)
