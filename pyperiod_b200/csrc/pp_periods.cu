@@ -45,9 +45,13 @@ struct SmemPlan {
   __host__ __device__ size_t off_utmp() const { return off_vwin() + (size_t)pv * 8; }
   // the hierarchical-sweep scratch is only live inside a sweep, vwin/utmp only between sweeps: they share bytes
   __host__ __device__ size_t off_hier() const { return off_vwin(); }
+  // M-best step 2 also parks 32 doubles per warp at vwin (warp_slot_factor_norm): for max_length < 127 that is more
+  // than two single-period vectors.  (Without this term warps 5..7 wrote into norms / fval behind the region: one
+  // window in ~2 million came out with garbage powers at max_length = 64 -- found by a soak of the GPU suite.)
   __host__ __device__ size_t union_bytes() const {
-    const size_t a = 2 * (size_t)pv * 8, b = (size_t)kWarps * hier_len * 8;
-    return a > b ? a : b;
+    const size_t a = 2 * (size_t)pv * 8, b = (size_t)kWarps * hier_len * 8, c = (size_t)kWarps * 32 * 8;
+    const size_t ab = a > b ? a : b;
+    return ab > c ? ab : c;
   }
   __host__ __device__ size_t off_red() const { return off_vwin() + union_bytes(); }
   __host__ __device__ size_t off_norms() const { return off_red() + 2 * kWarps * 8; }

@@ -65,3 +65,27 @@ def test_ramanujan_repeatable():
     first = r.find_periods(xb, max_length=128)
     for _ in range(REPS - 1):
         assert _same(first, r.find_periods(xb, max_length=128))
+
+
+@pytest.mark.parametrize("pmax", [24, 64, 100, 126])
+def test_mbest_small_max_length_repeatable_and_exact(pmax):
+    """max_length < 127: the per-warp scratch of M-best step 2 (8 x 32 doubles) is larger than the two single-period
+    vectors it shares shared memory with; the plan has to size that region for it.  (It did not: about one window in
+    two million came out with garbage powers at max_length = 64, depending on which window a CTA had processed
+    before.)  Many short windows, twice, bit for bit -- and a sample against the oracle."""
+    import torch
+    from oracle import periods as op
+    from pyperiod_b200 import Periods
+    B, N, hop = 20_000, 256, 64
+    rng = np.random.default_rng(100 + pmax)
+    stream = torch.from_numpy(rng.standard_normal((B - 1) * hop + N)).cuda()
+    win = torch.as_strided(stream, (B, N), (hop, 1))
+    a = Periods().m_best(win, num=3, max_length=pmax)
+    b = Periods().m_best(win, num=3, max_length=pmax)
+    assert torch.equal(a.periods.view(torch.int32), b.periods.view(torch.int32)) and torch.equal(a.powers, b.powers)
+    assert float(a.powers.min()) >= 0.0 and bool(torch.isfinite(a.powers).all())
+    host = stream.cpu().numpy()
+    for i in (0, 1, 777, 12_345, B - 1):
+        per0, pw0, _ = op.m_best(host[i * hop: i * hop + N], 3, pmax)
+        assert a.periods[i].cpu().numpy().view(np.uint32).tolist() == [int(v) for v in per0]
+        np.testing.assert_allclose(a.powers[i].cpu().numpy(), pw0, rtol=1e-10)
