@@ -229,7 +229,7 @@ int pp_qo_find_periods(const double *x, int64_t ldx, int32_t B, int32_t N, int32
  *      RamanujanPeriods.find_periods_with_weights, RamanujanPeriods.py:106-112) ---------------
  * periods i32[B,kmax] with nper[B] valid entries each, in the caller's order.  weights of window b go to
  * weights + weights_off[b] when weights_off is given (a ragged layout sized by pp_qo_dictionary_rows),
- * else to weights + b * ldw. */
+ * else to weights + b * ldw.  A window that is not solved (PP_STATUS_SINGULAR / PP_STATUS_TOO_LARGE) gets res = x. */
 int pp_qo_solve(const double *x, int64_t ldx, int32_t B, int32_t N, int32_t kmax, const int32_t *periods,
                 const int32_t *nper, int32_t pmax, int32_t refine, const int32_t *phi, int32_t table_pmax,
                 int32_t rmax, const int32_t *order, int32_t n_order, int32_t *dict_q, int32_t *dict_keep,

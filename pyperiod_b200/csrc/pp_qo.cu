@@ -770,6 +770,9 @@ qo_solve_kernel(QoBatch batch, int N, int kmax, const int32_t* __restrict__ entr
       for (int i = tid; i < R; i += kThreads) w[i] = c.wv[i];
       if (out.res)
         for (int n = tid; n < N; n += kThreads) out.res[(size_t)b * N + n] = c.xs[n];
+    } else if (out.res) {
+      // not solved (singular / too large): nothing was explained, the residual is the data (the reference raises here)
+      for (int n = tid; n < N; n += kThreads) out.res[(size_t)b * N + n] = c.x0[n];
     }
     if (tid == 0) {
       if (out.n_dict != nullptr) out.n_dict[b] = rc == PP_STATUS_OK ? ndict : 0;

@@ -1,5 +1,3 @@
 mkdir -p gpurun_out
-T=${TAG:-r04c}
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
-timeout 900 python bench.py > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_smoke.log
+T=${TAG:-r04d}
+timeout 1200 python tools/soak_determinism.py > gpurun_out/${T}_soak_det.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_soak_det.log
