@@ -234,3 +234,6 @@ def test_threaded_host_copy_is_a_plain_copy(monkeypatch):
     dst = np.zeros_like(src)
     _device._host_copy(dst, src)
     assert np.array_equal(dst, src)
+    if _device._copy_pool is not None:     # leave no worker threads behind (later tests fork)
+        _device._copy_pool.shutdown()
+        _device._copy_pool = None
