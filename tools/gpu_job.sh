@@ -1,6 +1,5 @@
 mkdir -p gpurun_out
-T=${TAG:-r04f}
-: > gpurun_out/${T}_soak_det.log
-for i in $(seq 1 24); do
-  timeout 300 python tools/soak_determinism.py 2>&1 | grep -v "Warn\|warn(" | grep -v " ok$" >> gpurun_out/${T}_soak_det.log
-done
+T=${TAG:-r04g}
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_smoke.log
+timeout 600 python bench.py --secondary 5ram,2 > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
