@@ -459,7 +459,10 @@ ram_fused_kernel(const double* __restrict__ x, int64_t ldx, int B, int N, int qm
 // k-block i+1 are built while the MMAs of k-block i run (tcgen05.commit -> mbarrier releases a stage).
 // ------------------------------------------------------------------------------------------
 constexpr int kUW = 128;          // windows per work unit (UMMA M)
-constexpr int kUN = 256;          // output residues per accumulator tile (UMMA N, TMEM columns)
+constexpr int kUN = 512;          // output residues per accumulator tile: ALL 512 tensor-memory columns, two UMMAs of
+                                  // N <= 256 per k-step -- the kernel is bound by fetching the folds (once per tile), so
+                                  // a tile twice as wide halves that traffic
+constexpr int kUNh = 256;         // UMMA N of one half
 constexpr int kUK = 32;           // tf32 per k-block: one 128-byte swizzle row
 constexpr int kUStageBytes = (2 * kUW + kUN) * 128;   // A_hi | A_lo | B
 constexpr int kUStages = 2;
@@ -575,8 +578,9 @@ ram_umma_tf32_kernel(const double* __restrict__ S, int ldS, int b_first, int b_c
     __syncthreads();
 
     for (int m0 = 0; m0 < q; m0 += kUN) {
-      const int nt = min(kUN, (q - m0 + 15) & ~15);       // UMMA N of this accumulator tile (multiple of 16)
-      const uint32_t idesc = umma_idesc_tf32(kUW, nt);
+      const int nt = min(kUN, (q - m0 + 15) & ~15);       // columns of this accumulator tile (multiple of 16)
+      const int nt0 = min(nt, kUNh), nt1 = nt - nt0;      // UMMA N of the two halves (nt1 may be 0)
+      const uint32_t idesc0 = umma_idesc_tf32(kUW, nt0), idesc1 = umma_idesc_tf32(kUW, nt1 > 0 ? nt1 : 16);
       for (int kb = 0; kb < nkb; ++kb) {
         const int st = kb & 1;
         unsigned char* stage = base + (size_t)st * kUStageBytes;
@@ -630,9 +634,15 @@ ram_umma_tf32_kernel(const double* __restrict__ S, int ldS, int b_first, int b_c
           const uint64_t a_hi = umma_desc_sw128(sa), a_lo = umma_desc_sw128(sa + kUW * 128),
                          bd = umma_desc_sw128(sa + 2 * kUW * 128);
 #pragma unroll
+          const uint64_t bd1 = umma_desc_sw128(sa + 2 * kUW * 128 + kUNh * 128);   // rows 256.. of the B tile
           for (int k = 0; k < kUK / 8; ++k) {   // UMMA K = 8 tf32 = 32 bytes: advance the start address by 2 (x16 B)
-            umma_tf32(tmem, a_hi + 2 * k, bd + 2 * k, idesc, (kb > 0 || k > 0) ? 1u : 0u);
-            umma_tf32(tmem, a_lo + 2 * k, bd + 2 * k, idesc, 1u);
+            const uint32_t accum = (kb > 0 || k > 0) ? 1u : 0u;
+            umma_tf32(tmem, a_hi + 2 * k, bd + 2 * k, idesc0, accum);
+            umma_tf32(tmem, a_lo + 2 * k, bd + 2 * k, idesc0, 1u);
+            if (nt1 > 0) {                      // second half: tensor-memory columns 256 ..
+              umma_tf32(tmem + kUNh, a_hi + 2 * k, bd1 + 2 * k, idesc1, accum);
+              umma_tf32(tmem + kUNh, a_lo + 2 * k, bd1 + 2 * k, idesc1, 1u);
+            }
           }
           umma_commit(bars + st);                       // frees this stage when the MMAs above have read it
           if (kb == nkb - 1) umma_commit(bars + 2);     // ... and the accumulator tile is complete
@@ -644,9 +654,9 @@ ram_umma_tf32_kernel(const double* __restrict__ S, int ldS, int b_first, int b_c
       phase_acc ^= 1u;
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       {
-        const int half = wid >> 2;                         // warps 0-3: columns [0, 128), warps 4-7: [128, 256)
+        const int half = wid >> 2;                         // warps 0-3: columns [0, 256), warps 4-7: [256, 512)
         const uint32_t lane_base = (uint32_t)(32 * (wid & 3)) << 16;
-        for (int c0 = half * 128; c0 < min(nt, half * 128 + 128); c0 += 32) {
+        for (int c0 = half * kUNh; c0 < min(nt, half * kUNh + kUNh); c0 += 32) {
           uint32_t r[32];
           tmem_ld_x32(tmem + lane_base + (uint32_t)c0, r);
 #pragma unroll
