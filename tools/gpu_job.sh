@@ -1,4 +1,5 @@
 mkdir -p gpurun_out
-T=${TAG:-r04i}
-timeout 300 python -m pytest tests/test_gpu_ramanujan.py -q -x -k "tf32" > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
-timeout 300 python tools/perf_ram.py 4096 fp64,tf32 > gpurun_out/${T}_perf.log 2>&1
+T=${TAG:-r04j}
+timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
+timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_smoke.log
+timeout 600 python bench.py --secondary none > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
