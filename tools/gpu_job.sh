@@ -1,5 +1,8 @@
 mkdir -p gpurun_out
-T=${TAG:-r04j}
-timeout 1500 python -m pytest tests -m gpu -q > gpurun_out/${T}_pytest.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_pytest.log
-timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${T}_smoke.log 2>&1; echo "rc=$?" >> gpurun_out/${T}_smoke.log
-timeout 600 python bench.py --secondary none > gpurun_out/${T}_bench.json 2> gpurun_out/${T}_bench.err; echo "rc=$?" >> gpurun_out/${T}_bench.err
+T=${TAG:-r04k}
+: > gpurun_out/${T}_soak.log
+for i in 1 2 3 4; do
+  timeout 600 python -m pytest tests -m gpu -q -x -p no:cacheprovider > /tmp/run_$i.log 2>&1
+  tail -1 /tmp/run_$i.log >> gpurun_out/${T}_soak.log
+  if grep -q "failed" /tmp/run_$i.log; then cp /tmp/run_$i.log gpurun_out/${T}_fail_$i.log; fi
+done
